@@ -1,0 +1,204 @@
+/*
+ * rocket_landing_b200.h -- C ABI of the B200-native batched rocket-landing environment step.
+ *
+ * This is the drop-in boundary for ONE path of adimail/rocket-landing-rl: the environment
+ * step behind RocketLandingEnv.reset()/step() (reference backend/envs/lander.py:168,188),
+ * i.e. physics (backend/physics/engine.py, backend/rocket/base.py:132), reward /
+ * termination / landing class (backend/rl/reward.py:27, backend/utils.py:1), observation
+ * clipping (lander.py:124) and the VecEnv auto-reset the reference trains under
+ * (scripts/train.py:82-88).  The reference is pure Python and has no FFI; these entry
+ * points are what a ctypes binding inside the reference would call (INTEGRATION.md shows
+ * that binding).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative RL_E_* code otherwise;
+ *    rl_last_error() returns a thread-local, human-readable message for the last failure.
+ *  - all buffer arguments of rl_reset / rl_step / rl_set_state / rl_get_state / rl_stats are
+ *    DEVICE pointers on the handle's device, owned by the caller (e.g. torch tensors); the
+ *    library borrows them for the duration of the enqueue.  rl_step_host / rl_reset_host
+ *    take HOST pointers and do the copies themselves.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only
+ *    ENQUEUE work on it and never synchronise (rl_*_host excepted); rl_step allocates
+ *    nothing and is CUDA-graph capturable.  One handle per (device, stream); a handle is
+ *    not thread-safe.
+ *  - layouts: actions [N,2] f32 row-major (throttle, cold gas); obs [N,8] f32 row-major
+ *    (x, y, vx, vy, ax, ay, angle, angular velocity; lander.py:129-141); reward [N] f32;
+ *    terminated / truncated [N] u8 (0/1).
+ */
+#ifndef ROCKET_LANDING_B200_H_
+#define ROCKET_LANDING_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RL_ABI_VERSION 1
+
+#define RL_OK 0
+#define RL_E_INVALID (-1)   /* bad argument                        */
+#define RL_E_CUDA (-2)      /* a CUDA runtime call / launch failed */
+#define RL_E_NOMEM (-3)     /* allocation failed                   */
+
+/* Words of the public state format used by rl_set_state / rl_get_state: float32 [10][N]
+ * (structure of arrays, word-major).  RL_W_META holds raw int32 bits. */
+#define RL_STATE_WORDS 10
+#define RL_W_X 0        /* m                                                              */
+#define RL_W_Y 1        /* m                                                              */
+#define RL_W_ANGLE 2    /* deg, normalised to [-180, 180)  (engine.py:230)                */
+#define RL_W_SX 3       /* carried x delta  x(t) - x(t-dt);  vx itself while FRESH        */
+#define RL_W_SY 4       /* carried y delta;                  vy itself while FRESH        */
+#define RL_W_SANGLE 5   /* carried pre-wrap angle delta;     angular velocity while FRESH */
+#define RL_W_DRY 6      /* kg                                                             */
+#define RL_W_FUEL 7     /* kg                                                             */
+#define RL_W_META 8     /* int32 bits: [0,24) episode step count (lander.py:229),
+                           [24,27) signed count k of 360-degree wraps applied by the last
+                           normalisation (engine.py:226 stores the normalised angle as the
+                           next step's "previous" angle, base.py:171), bit 31 FRESH = just
+                           reset, Verlet bootstrap (base.py:65) not applied yet           */
+#define RL_W_EPRET 9    /* running episode return                                         */
+
+#define RL_META_STEP_MASK 0x00FFFFFFu
+#define RL_META_WRAP_SHIFT 24
+#define RL_META_FRESH 0x80000000u
+
+/* Slots of the statistics vector (float64 [16]) returned by rl_stats. */
+#define RL_STATS_WORDS 16
+#define RL_S_EPISODES 0     /* finished episodes                                   */
+#define RL_S_RETURN_SUM 1   /* sum of their returns                                */
+#define RL_S_LENGTH_SUM 2   /* sum of their lengths (steps)                        */
+#define RL_S_SAFE 3         /* landing class counts (utils.py:19-30)               */
+#define RL_S_GOOD 4
+#define RL_S_OK 5
+#define RL_S_UNSAFE 6
+#define RL_S_TIME_LIMIT 7   /* truncated by rl.max_episode_steps (lander.py:237)   */
+#define RL_S_OUT_OF_BOUNDS 8 /* truncated by position limits (reward.py:274)       */
+#define RL_S_TIP_STEPS 9    /* steps with |angle| > tip_over_angle (reward.py:278) */
+#define RL_S_NONFINITE 10   /* steps whose reward or altitude was NaN / Inf        */
+#define RL_S_ENV_STEPS 11   /* env steps executed                                  */
+#define RL_S_REWARD_SUM 12  /* sum of all step rewards                             */
+
+/* Constants of the environment: one field per config.yaml key the path reads
+ * (reference config.yaml; loaded there by backend/config.py:21-37). */
+typedef struct RlParams {
+    double time_step;                /* simulation.time_step            */
+    double gravity;                  /* environment.gravity             */
+    double air_density;              /* environment.air_density         */
+    double thrust_power;             /* rocket.thrust_power             */
+    double cold_gas_thrust_power;    /* rocket.cold_gas_thrust_power    */
+    double fuel_consumption_rate;    /* rocket.fuel_consumption_rate    */
+    double radius;                   /* rocket.radius                   */
+    double cold_gas_moment_arm;      /* rocket.cold_gas_moment_arm      */
+    double reference_area;           /* rocket.reference_area           */
+    double drag_coefficient;         /* rocket.drag_coefficient         */
+    double angular_damping;          /* rocket.angular_damping          */
+    /* reset distribution, draw order of simulation/config.py:26-40:
+     * x, y, vx, vy, ax, ay, angle, angular velocity, dry mass, fuel mass */
+    double reset_low[10];
+    double reset_high[10];
+    /* landing.thresholds.{perfect,good,ok}.{speed_vx,speed_vy,angle} */
+    double land_perfect[3];
+    double land_good[3];
+    double land_ok[3];
+    double max_horizontal_position;  /* rl.max_horizontal_position      */
+    double max_altitude;             /* rl.max_altitude                 */
+    double tip_over_angle;           /* rl.tip_over_angle               */
+    double landing_perfect;          /* rl.rewards.*                    */
+    double landing_good;
+    double landing_ok;
+    double crash_ground;
+    double out_of_bounds;
+    double tipped_over;
+    double throttle_descent_reward_scale;
+    double cold_gas_reward_scale;
+    double free_fall_penalty_scale;
+    double angle_aware_throttle_scale;
+    double correct_direction_bonus;
+    double gamma;
+    double obs_low[8];               /* observation Box bounds (lander.py:73-101) */
+    double obs_high[8];
+    int32_t max_episode_steps;       /* rl.max_episode_steps            */
+    int32_t reserved;
+} RlParams;
+
+typedef struct RlEnv RlEnv;          /* opaque handle */
+
+int rl_abi_version(void);
+const char *rl_last_error(void);
+
+/* Fill `p` with the reference's config.yaml defaults (config.yaml:16-91). */
+void rl_params_default(RlParams *p);
+
+/* Bytes of device memory holding the persistent state of n_envs rockets (40 B per rocket,
+ * padded to a whole number of 256-rocket tiles). */
+int64_t rl_state_bytes(int64_t n_envs);
+
+/* Create an environment batch of n_envs rockets on `device`.
+ *   env_id_offset : global id of rocket 0 of this shard; the Philox reset stream is keyed by
+ *                   (seed, global rocket id, launch epoch) so results do not depend on how
+ *                   rockets are sharded over GPUs.
+ *   state_buf     : caller-owned device buffer of rl_state_bytes(n_envs) bytes, 256-byte
+ *                   aligned (so the caller can checkpoint it), or NULL to let the library
+ *                   allocate and own it.
+ * Replaces: RocketLandingEnv.__init__ (lander.py:48) x n_envs + make_vec_env (train.py:83). */
+int rl_create(const RlParams *params, int64_t n_envs, int64_t env_id_offset, uint64_t seed,
+              int device, void *state_buf, RlEnv **out);
+int rl_destroy(RlEnv *env);
+
+int64_t rl_num_envs(const RlEnv *env);
+
+/* Launch epoch (counts rl_reset / rl_step launches; part of the Philox counter).  Saving
+ * it with the state buffer makes a checkpoint resume bit-identically. */
+uint64_t rl_get_epoch(const RlEnv *env);
+int rl_set_epoch(RlEnv *env, uint64_t epoch);
+
+/* Resample the initial state of every rocket (mask == NULL) or of the rockets with
+ * mask[i] != 0, and write their clipped reset observation (rows of unmasked rockets are
+ * left untouched).  obs may be NULL.
+ * Replaces: RocketLandingEnv.reset (lander.py:168) -> Rocket.reset (base.py:186) ->
+ * get_initial_state (simulation/config.py:26). */
+int rl_reset(RlEnv *env, const uint8_t *mask, float *obs, void *stream);
+
+/* One environment step for every rocket: `substeps` consecutive physics+reward steps with
+ * the same action (rewards summed, integration of a rocket stops at its first done), then
+ * -- if auto_reset != 0 -- rockets that are done are resampled and `obs` holds their reset
+ * observation (the SB3 VecEnv contract of scripts/train.py:82-88).
+ *   terminal_obs   [N,8] f32, nullable: rows of done rockets receive the terminal observation
+ *   episode_return [N] f32, nullable:   entries of done rockets receive the episode return
+ *   episode_length [N] i32, nullable:   entries of done rockets receive the episode length
+ *                                       (other rows / entries are left untouched)
+ *   landing        [N] i8,  nullable:   landing class of this step for EVERY rocket: 0 = no
+ *                                       touchdown, 1 safe, 2 good, 3 ok, 4 unsafe
+ *                                       (evaluate_landing, utils.py:1; codes of protocol.py:31-41)
+ * Replaces: RocketLandingEnv.step (lander.py:188) x n_envs. */
+int rl_step(RlEnv *env, const float *actions, float *obs, float *reward, uint8_t *terminated,
+            uint8_t *truncated, float *terminal_obs, float *episode_return,
+            int32_t *episode_length, int8_t *landing, int substeps, int auto_reset, void *stream);
+
+/* Inject / read back the persistent state in the public format (float32 [10][N], RL_W_*).
+ * rl_set_state writes only rockets with mask[i] != 0 (mask == NULL: all).  Used for
+ * deterministic replay against the reference and for checkpointing. */
+int rl_set_state(RlEnv *env, const float *state_soa, const uint8_t *mask, void *stream);
+int rl_get_state(RlEnv *env, float *state_soa, void *stream);
+
+/* Copy the float64[16] statistics vector (RL_S_*) to the DEVICE buffer `out16` (ready for an
+ * NCCL all-reduce on the same stream); reset_after != 0 zeroes the accumulators afterwards. */
+int rl_stats(RlEnv *env, double *out16, int reset_after, void *stream);
+
+/* Host-buffer variants (the reference-facing call with numpy arrays): copy `actions` to the
+ * device, step, copy obs / reward / flags back, synchronise.  Buffers are ordinary host
+ * memory (pinned memory makes the copies faster).  Nullable outputs as in rl_step. */
+int rl_step_host(RlEnv *env, const float *actions, float *obs, float *reward,
+                 uint8_t *terminated, uint8_t *truncated, float *terminal_obs,
+                 float *episode_return, int32_t *episode_length, int8_t *landing, int substeps,
+                 int auto_reset);
+int rl_reset_host(RlEnv *env, float *obs);
+
+/* Number of kernels this handle has launched so far (step / reset / state / stats). */
+int64_t rl_launch_count(const RlEnv *env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROCKET_LANDING_B200_H_ */

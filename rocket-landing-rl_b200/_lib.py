@@ -1,0 +1,74 @@
+"""ctypes loader of ``librocket_landing_b200.so`` (the C ABI in
+``include/rocket_landing_b200.h``).  No fallback: if the library is missing or the ABI
+version disagrees this raises, loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .config import RlParams
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_NAME = "librocket_landing_b200.so"
+LIB_PATH = os.path.join(_PKG_DIR, LIB_NAME)
+ABI_VERSION = 1
+
+# every symbol include/rocket_landing_b200.h declares
+EXPORTS = ("rl_abi_version", "rl_last_error", "rl_params_default", "rl_state_bytes", "rl_create",
+           "rl_destroy", "rl_num_envs", "rl_get_epoch", "rl_set_epoch", "rl_reset", "rl_step",
+           "rl_set_state", "rl_get_state", "rl_stats", "rl_step_host", "rl_reset_host",
+           "rl_launch_count")
+
+_lib = None
+
+
+class RocketLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise RocketLibraryError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built.  Run "
+            f"`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C "
+            f"rocket-landing-rl_b200/csrc`).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(L, name):
+            raise RocketLibraryError(f"{LIB_PATH} does not export {name}")
+    L.rl_abi_version.restype = C.c_int
+    if L.rl_abi_version() != ABI_VERSION:
+        raise RocketLibraryError(f"ABI mismatch: library {L.rl_abi_version()}, binding {ABI_VERSION}")
+    vp, i64, u64, i32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int
+    L.rl_last_error.restype = C.c_char_p
+    L.rl_params_default.argtypes = [C.POINTER(RlParams)]
+    L.rl_params_default.restype = None
+    L.rl_state_bytes.argtypes = [i64]
+    L.rl_state_bytes.restype = i64
+    L.rl_create.argtypes = [C.POINTER(RlParams), i64, i64, u64, i32, vp, C.POINTER(vp)]
+    L.rl_destroy.argtypes = [vp]
+    L.rl_num_envs.argtypes = [vp]
+    L.rl_num_envs.restype = i64
+    L.rl_get_epoch.argtypes = [vp]
+    L.rl_get_epoch.restype = u64
+    L.rl_set_epoch.argtypes = [vp, u64]
+    L.rl_reset.argtypes = [vp, vp, vp, vp]
+    L.rl_step.argtypes = [vp] + [vp] * 9 + [i32, i32, vp]
+    L.rl_set_state.argtypes = [vp, vp, vp, vp]
+    L.rl_get_state.argtypes = [vp, vp, vp]
+    L.rl_stats.argtypes = [vp, vp, i32, vp]
+    L.rl_step_host.argtypes = [vp] + [vp] * 9 + [i32, i32]
+    L.rl_reset_host.argtypes = [vp, vp]
+    L.rl_launch_count.argtypes = [vp]
+    L.rl_launch_count.restype = i64
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().rl_last_error().decode("utf-8", "replace")
+        raise RocketLibraryError(f"{what} failed (code {rc}): {msg}")

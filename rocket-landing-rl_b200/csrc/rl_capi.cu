@@ -1,0 +1,364 @@
+// C ABI of the batched environment step (include/rocket_landing_b200.h).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "rl_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define RL_CUDA(expr)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(RL_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                               \
+    } while (0)
+
+
+}  // namespace
+
+struct RlEnv {
+    rl::DevParams dev;
+    RlParams params;
+    rl::StatePlanes planes;
+    void* state_buf = nullptr;
+    bool owns_state = false;
+    double* stats = nullptr;          // device, RL_STATS_WORDS
+    int64_t n = 0;
+    int64_t gid0 = 0;
+    uint64_t seed = 0;
+    uint64_t epoch = 0;
+    int device = 0;
+    int grid_cap = 0;                 // persistent grid: SMs x resident CTAs of the step kernel
+    int64_t launches = 0;
+    // host-buffer path (rl_step_host): device staging, allocated on first use
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    cudaStream_t h_stream = nullptr;
+};
+
+namespace {
+
+int grid_for(const RlEnv* e, int64_t n) {
+    const int64_t tiles = (n + rl::kTile - 1) / rl::kTile;
+    return (int)(tiles < e->grid_cap ? (tiles > 0 ? tiles : 1) : e->grid_cap);
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8_t* terminated,
+                uint8_t* truncated, float* terminal_obs, float* episode_return, int32_t* episode_length,
+                int8_t* landing, int substeps, int auto_reset, cudaStream_t stream) {
+    rl::StepArgs a;
+    a.st = e->planes;
+    a.actions = reinterpret_cast<const float2*>(actions);
+    a.obs = reinterpret_cast<float4*>(obs);
+    a.reward = reward;
+    a.terminated = terminated;
+    a.truncated = truncated;
+    a.terminal_obs = reinterpret_cast<float4*>(terminal_obs);
+    a.episode_return = episode_return;
+    a.episode_length = episode_length;
+    a.landing = landing;
+    a.stats = e->stats;
+    a.n = e->n;
+    a.gid0 = e->gid0;
+    a.seed = e->seed;
+    a.epoch = e->epoch++;
+    a.substeps = substeps;
+    const int grid = grid_for(e, e->n);
+    if (auto_reset) rl::step_kernel<true><<<grid, rl::kTile, 0, stream>>>(e->dev, a);
+    else rl::step_kernel<false><<<grid, rl::kTile, 0, stream>>>(e->dev, a);
+    e->launches += 1;
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
+bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) != 0; }
+
+}  // namespace
+
+extern "C" {
+
+int rl_abi_version(void) { return RL_ABI_VERSION; }
+
+const char* rl_last_error(void) { return g_err; }
+
+void rl_params_default(RlParams* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->time_step = 0.1;
+    p->gravity = -9.81;
+    p->air_density = 1.225;
+    p->thrust_power = 1.0e7;
+    p->cold_gas_thrust_power = 7.0e4;
+    p->fuel_consumption_rate = 1700.0;
+    p->radius = 1.85;
+    p->cold_gas_moment_arm = 1.85;
+    p->reference_area = 10.8;
+    p->drag_coefficient = 0.8;
+    p->angular_damping = 0.05;
+    const double lo[10] = {-1500, 1800, -25, -200, -5, -5, -15, -10, 34000, 370000};
+    const double hi[10] = {1500, 2200, 25, -150, 5, 5, 15, 10, 38000, 410000};
+    memcpy(p->reset_low, lo, sizeof(lo));
+    memcpy(p->reset_high, hi, sizeof(hi));
+    const double perfect[3] = {30, 30, 5}, good[3] = {40, 40, 8}, ok[3] = {100, 100, 10};
+    memcpy(p->land_perfect, perfect, sizeof(perfect));
+    memcpy(p->land_good, good, sizeof(good));
+    memcpy(p->land_ok, ok, sizeof(ok));
+    p->max_horizontal_position = 50000.0;
+    p->max_altitude = 50000.0;
+    p->tip_over_angle = 90.0;
+    p->landing_perfect = 4000.0;
+    p->landing_good = 3000.0;
+    p->landing_ok = 2000.0;
+    p->crash_ground = -800.0;
+    p->out_of_bounds = -300.0;
+    p->tipped_over = -300.0;
+    p->throttle_descent_reward_scale = 0.3;
+    p->cold_gas_reward_scale = 0.7;
+    p->free_fall_penalty_scale = 0.2;
+    p->angle_aware_throttle_scale = 0.3;
+    p->correct_direction_bonus = 1.5;
+    p->gamma = 0.99;
+    // lander.py:73-101: [x, y, vx, vy, ax, ay, angle, omega]; y low is the literal 0.0
+    const int src[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+    for (int k = 0; k < 8; ++k) {
+        p->obs_low[k] = lo[src[k]];
+        p->obs_high[k] = hi[src[k]];
+    }
+    p->obs_low[1] = 0.0;
+    p->max_episode_steps = 1000;
+}
+
+int64_t rl_state_bytes(int64_t n_envs) { return n_envs > 0 ? 40 * rl::padded_envs(n_envs) : 0; }
+
+int rl_create(const RlParams* params, int64_t n_envs, int64_t env_id_offset, uint64_t seed, int device,
+              void* state_buf, RlEnv** out) {
+    if (!params || !out) return fail(RL_E_INVALID, "rl_create: null argument");
+    if (n_envs <= 0) return fail(RL_E_INVALID, "rl_create: n_envs must be positive (got %lld)", (long long)n_envs);
+    if (env_id_offset < 0) return fail(RL_E_INVALID, "rl_create: env_id_offset must be >= 0");
+    if (state_buf && misaligned(state_buf, 256)) return fail(RL_E_INVALID, "rl_create: state_buf must be 256-byte aligned");
+    RlEnv* e = new (std::nothrow) RlEnv();
+    if (!e) return fail(RL_E_NOMEM, "rl_create: out of host memory");
+    int rc = rl::derive_params(*params, e->dev, g_err, sizeof(g_err));
+    if (rc != RL_OK) { delete e; return rc; }
+    e->params = *params;
+    e->n = n_envs;
+    e->gid0 = env_id_offset;
+    e->seed = seed;
+    e->device = device;
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || device < 0 || device >= count) {
+        delete e;
+        return fail(RL_E_CUDA, "rl_create: CUDA device %d not available (%s)", device,
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "bad ordinal");
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) { delete e; return fail(RL_E_CUDA, "rl_create: cudaSetDevice(%d) failed", device); }
+    const size_t bytes = (size_t)rl_state_bytes(n_envs);
+    if (state_buf) {
+        e->state_buf = state_buf;
+    } else {
+        if (cudaMalloc(&e->state_buf, bytes) != cudaSuccess) {
+            delete e;
+            return fail(RL_E_NOMEM, "rl_create: cudaMalloc(%zu) failed", bytes);
+        }
+        e->owns_state = true;
+    }
+    e->planes = rl::carve_state(e->state_buf, n_envs);
+    if (cudaMalloc(&e->stats, RL_STATS_WORDS * sizeof(double)) != cudaSuccess ||
+        cudaMemset(e->stats, 0, RL_STATS_WORDS * sizeof(double)) != cudaSuccess ||
+        cudaMemset(e->state_buf, 0, bytes) != cudaSuccess) {
+        rl_destroy(e);
+        return fail(RL_E_CUDA, "rl_create: device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rl::step_kernel<true>, rl::kTile, 0);
+    if (sms <= 0 || per_sm <= 0) {
+        rl_destroy(e);
+        return fail(RL_E_CUDA, "rl_create: occupancy query failed (no sm_100a image for this device?): %s",
+                    cudaGetErrorString(cudaGetLastError()));
+    }
+    e->grid_cap = sms * per_sm;
+    *out = e;
+    return RL_OK;
+}
+
+int rl_destroy(RlEnv* e) {
+    if (!e) return RL_OK;
+    DeviceGuard guard(e->device);
+    if (e->owns_state && e->state_buf) cudaFree(e->state_buf);
+    if (e->stats) cudaFree(e->stats);
+    if (e->h_stage) cudaFree(e->h_stage);
+    if (e->h_stream) cudaStreamDestroy(e->h_stream);
+    delete e;
+    return RL_OK;
+}
+
+int64_t rl_num_envs(const RlEnv* e) { return e ? e->n : 0; }
+uint64_t rl_get_epoch(const RlEnv* e) { return e ? e->epoch : 0; }
+int rl_set_epoch(RlEnv* e, uint64_t epoch) {
+    if (!e) return fail(RL_E_INVALID, "rl_set_epoch: null handle");
+    e->epoch = epoch;
+    return RL_OK;
+}
+int64_t rl_launch_count(const RlEnv* e) { return e ? e->launches : 0; }
+
+int rl_reset(RlEnv* e, const uint8_t* mask, float* obs, void* stream) {
+    if (!e) return fail(RL_E_INVALID, "rl_reset: null handle");
+    if (obs && misaligned(obs, 16)) return fail(RL_E_INVALID, "rl_reset: obs must be 16-byte aligned");
+    DeviceGuard guard(e->device);
+    rl::reset_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(
+        e->dev, e->planes, mask, reinterpret_cast<float4*>(obs), e->n, e->gid0, e->seed, e->epoch++);
+    e->launches += 1;
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated,
+            float* terminal_obs, float* episode_return, int32_t* episode_length, int8_t* landing, int substeps,
+            int auto_reset, void* stream) {
+    if (!e) return fail(RL_E_INVALID, "rl_step: null handle");
+    if (!actions || !obs || !reward || !terminated || !truncated)
+        return fail(RL_E_INVALID, "rl_step: actions, obs, reward, terminated and truncated are required");
+    if (substeps < 1 || substeps > 4096) return fail(RL_E_INVALID, "rl_step: substeps must be in [1, 4096] (got %d)", substeps);
+    if (misaligned(actions, 8) || misaligned(obs, 16) || misaligned(reward, 4) ||
+        (terminal_obs && misaligned(terminal_obs, 16)))
+        return fail(RL_E_INVALID, "rl_step: actions need 8-byte, obs / terminal_obs 16-byte alignment");
+    DeviceGuard guard(e->device);
+    return launch_step(e, actions, obs, reward, terminated, truncated, terminal_obs, episode_return,
+                       episode_length, landing, substeps, auto_reset, (cudaStream_t)stream);
+}
+
+int rl_set_state(RlEnv* e, const float* state_soa, const uint8_t* mask, void* stream) {
+    if (!e || !state_soa) return fail(RL_E_INVALID, "rl_set_state: null argument");
+    DeviceGuard guard(e->device);
+    rl::set_state_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(e->planes, state_soa, mask, e->n);
+    e->launches += 1;
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_get_state(RlEnv* e, float* state_soa, void* stream) {
+    if (!e || !state_soa) return fail(RL_E_INVALID, "rl_get_state: null argument");
+    DeviceGuard guard(e->device);
+    rl::get_state_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(e->planes, state_soa, e->n);
+    e->launches += 1;
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
+int rl_stats(RlEnv* e, double* out16, int reset_after, void* stream) {
+    if (!e || !out16) return fail(RL_E_INVALID, "rl_stats: null argument");
+    DeviceGuard guard(e->device);
+    rl::stats_copy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(e->stats, out16, reset_after);
+    e->launches += 1;
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
+// ---- host-buffer path ------------------------------------------------------------------
+// Device staging for one full batch: actions | obs | reward | terminated | truncated |
+// terminal_obs | episode_return | episode_length, each 256-byte aligned.
+namespace {
+struct Stage {
+    float *actions, *obs, *reward, *terminal_obs, *episode_return;
+    uint8_t *terminated, *truncated;
+    int32_t* episode_length;
+    int8_t* landing;
+};
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+int ensure_stage(RlEnv* e, Stage& s) {
+    const size_t n = (size_t)e->n;
+    const size_t sz[9] = {align256(8 * n), align256(32 * n), align256(4 * n), align256(n), align256(n),
+                          align256(32 * n), align256(4 * n), align256(4 * n), align256(n)};
+    size_t total = 0;
+    for (size_t v : sz) total += v;
+    if (!e->h_stage) {
+        if (cudaMalloc(&e->h_stage, total) != cudaSuccess) return fail(RL_E_NOMEM, "host path: cudaMalloc(%zu) failed", total);
+        e->h_stage_bytes = total;
+        RL_CUDA(cudaStreamCreateWithFlags(&e->h_stream, cudaStreamNonBlocking));
+    }
+    char* p = static_cast<char*>(e->h_stage);
+    s.actions = (float*)p; p += sz[0];
+    s.obs = (float*)p; p += sz[1];
+    s.reward = (float*)p; p += sz[2];
+    s.terminated = (uint8_t*)p; p += sz[3];
+    s.truncated = (uint8_t*)p; p += sz[4];
+    s.terminal_obs = (float*)p; p += sz[5];
+    s.episode_return = (float*)p; p += sz[6];
+    s.episode_length = (int32_t*)p; p += sz[7];
+    s.landing = (int8_t*)p;
+    return RL_OK;
+}
+}  // namespace
+
+int rl_step_host(RlEnv* e, const float* actions, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated,
+                 float* terminal_obs, float* episode_return, int32_t* episode_length, int8_t* landing, int substeps,
+                 int auto_reset) {
+    if (!e) return fail(RL_E_INVALID, "rl_step_host: null handle");
+    if (!actions || !obs || !reward || !terminated || !truncated)
+        return fail(RL_E_INVALID, "rl_step_host: actions, obs, reward, terminated and truncated are required");
+    if (substeps < 1 || substeps > 4096) return fail(RL_E_INVALID, "rl_step_host: substeps must be in [1, 4096]");
+    DeviceGuard guard(e->device);
+    Stage s;
+    int rc = ensure_stage(e, s);
+    if (rc != RL_OK) return rc;
+    const size_t n = (size_t)e->n;
+    cudaStream_t st = e->h_stream;
+    RL_CUDA(cudaMemcpyAsync(s.actions, actions, 8 * n, cudaMemcpyHostToDevice, st));
+    rc = launch_step(e, s.actions, s.obs, s.reward, s.terminated, s.truncated,
+                     terminal_obs ? s.terminal_obs : nullptr, episode_return ? s.episode_return : nullptr,
+                     episode_length ? s.episode_length : nullptr, landing ? s.landing : nullptr, substeps,
+                     auto_reset, st);
+    if (rc != RL_OK) return rc;
+    RL_CUDA(cudaMemcpyAsync(obs, s.obs, 32 * n, cudaMemcpyDeviceToHost, st));
+    RL_CUDA(cudaMemcpyAsync(reward, s.reward, 4 * n, cudaMemcpyDeviceToHost, st));
+    RL_CUDA(cudaMemcpyAsync(terminated, s.terminated, n, cudaMemcpyDeviceToHost, st));
+    RL_CUDA(cudaMemcpyAsync(truncated, s.truncated, n, cudaMemcpyDeviceToHost, st));
+    if (terminal_obs) RL_CUDA(cudaMemcpyAsync(terminal_obs, s.terminal_obs, 32 * n, cudaMemcpyDeviceToHost, st));
+    if (episode_return) RL_CUDA(cudaMemcpyAsync(episode_return, s.episode_return, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (episode_length) RL_CUDA(cudaMemcpyAsync(episode_length, s.episode_length, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (landing) RL_CUDA(cudaMemcpyAsync(landing, s.landing, n, cudaMemcpyDeviceToHost, st));
+    RL_CUDA(cudaStreamSynchronize(st));
+    return RL_OK;
+}
+
+int rl_reset_host(RlEnv* e, float* obs) {
+    if (!e) return fail(RL_E_INVALID, "rl_reset_host: null handle");
+    DeviceGuard guard(e->device);
+    Stage s;
+    int rc = ensure_stage(e, s);
+    if (rc != RL_OK) return rc;
+    rc = rl_reset(e, nullptr, obs ? s.obs : nullptr, e->h_stream);
+    if (rc != RL_OK) return rc;
+    if (obs) RL_CUDA(cudaMemcpyAsync(obs, s.obs, 32 * (size_t)e->n, cudaMemcpyDeviceToHost, e->h_stream));
+    RL_CUDA(cudaStreamSynchronize(e->h_stream));
+    return RL_OK;
+}
+
+}  // extern "C"
