@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched rocket-landing environment step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 (N = 1)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json metric: "env-steps/sec at 1/2/4/8 B200 (64M rockets)"): 64 Mi rockets
+in total, sharded by contiguous global id over the N ranks (strong scaling; no data-path
+collective -- rockets never interact), one fresh random action per rocket per step, auto-reset
+on, K_sub = 1 substep per launch.  A "step" is one launch of the step kernel over a rank's
+whole shard.  The only collective is the NCCL all-reduce of the 16-word episode-statistics
+vector every --stats-interval steps and at the end of the timed region.
+
+Prints ONE JSON line (rank 0).  ``value`` = env-steps/s with everything resident in HBM;
+``e2e`` = the same metric through the host-buffer VecEnv call (pinned numpy in/out, H2D and
+D2H copies inside the timed region); ``roofline`` = algorithmic HBM bytes of the step kernel /
+its CUDA-event duration against the measured copy bandwidth; ``cpu_baseline`` = the oracle
+port on this box's host cores (N = 1 only).  ``--impl reference`` times the oracle port only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOTAL_ROCKETS = 64 * 1024 * 1024
+# algorithmic HBM bytes per env-step at one substep per launch (DESIGN.md "Roofline"):
+#   state read 40 (planes A, B 16+16, fuel 4, dry 4) + state write 36 (dry is written on reset only)
+#   + action read 8 + obs write 32 + reward write 4 + terminated/truncated 2 + landing class 1
+BYTES_PER_ENV_STEP = 40 + 36 + 8 + 32 + 4 + 2 + 1
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def _peaks() -> tuple[float, str]:
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:   # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:   # noqa: BLE001
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:   # noqa: BLE001
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_rate(seconds_budget: float = 12.0, threads: int | None = None) -> dict:
+    """The oracle port (oracle/rocket_oracle.c: scalar fp64 restatement of the reference's step,
+    random actions, auto-reset) on all host cores, on a bounded sample of the workload."""
+    from oracle import c_oracle
+    threads = threads or os.cpu_count() or 1
+    per_thread = 4096
+    probe = c_oracle.rollout_random(per_thread, 50, threads, seed=1)
+    steps = max(50, int(seconds_budget * probe["steps_per_s"] / (per_thread * threads)))
+    out = c_oracle.rollout_random(per_thread, steps, threads, seed=2)
+    return {"value": out["steps_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{per_thread * threads} rockets x {steps} steps, random actions, auto-reset, "
+                      f"C fp64 port of the reference step on {threads} host threads ({out['seconds']:.1f} s)"}
+
+
+def python_port_rate(steps: int = 20000) -> float:
+    """Single-core rate of the Python oracle (bit-identical restatement of the reference's
+    Python; the reference itself measured 14.3 k steps/s/core in the survey container)."""
+    import numpy as np
+    from oracle import rocket_oracle as ro
+    env = ro.OracleEnv()
+    rng = np.random.default_rng(0)
+    acts = rng.uniform([0, -1], [1, 1], (steps, 2)).astype(np.float32)
+    t0 = time.perf_counter()
+    for t in range(steps):
+        _, _, term, trunc, _ = env.step(acts[t])
+        if term or trunc:
+            env.reset()
+    return steps / (time.perf_counter() - t0)
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from oracle import c_oracle
+    c_oracle.build()
+    sample = 32768 * threads                      # rockets per step: bounded sample of the 64 Mi workload
+    per_thread = sample // threads
+    if args.warmup > 0:
+        c_oracle.rollout_random(per_thread, args.warmup, threads, seed=1)
+    out = c_oracle.rollout_random(per_thread, args.steps, threads, seed=2)
+    value = out["steps_per_s"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * out["seconds"] / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"64Mi rockets, random actions, auto-reset, 1 substep (timed on a {sample}-rocket sample per step)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{sample} rockets x {args.steps} steps on {threads} host threads, C fp64 port "
+                                   f"of the reference's Python step (oracle/rocket_oracle.c)",
+                         "python_port_steps_per_s_1core": python_port_rate(5000)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rockets", type=int, default=TOTAL_ROCKETS, help="total rockets over all ranks")
+    ap.add_argument("--substeps", type=int, default=1)
+    ap.add_argument("--stats-interval", type=int, default=100)
+    ap.add_argument("--e2e-steps", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from rocket_landing_rl_b200 import RocketLandingSB3VecEnv, RocketLandingVecEnv, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    start, count = shard_range(args.rockets, rank, world)
+    warmup = max(args.warmup, 3)
+
+    env = RocketLandingVecEnv(count, device=dev, seed=0, env_id_offset=start, substeps=args.substeps)
+    env.reset()
+    # a fresh random action per rocket per step: four pre-generated action sets, cycled
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    n_sets = 4
+    actions = []
+    for _ in range(n_sets):
+        a = torch.rand((count, 2), device=dev, generator=gen)
+        a[:, 1].mul_(2.0).sub_(1.0)
+        actions.append(a)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for t in range(warmup):
+        env.step(actions[t % n_sets])
+    env.stats(reset=True)
+    launches0 = env.launch_count
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    k1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev0.record()
+    for t in range(args.steps):
+        k0[t].record()
+        env.step(actions[t % n_sets])
+        k1[t].record()
+        if (t + 1) % args.stats_interval == 0:
+            env.stats()                              # 128-byte all-reduce (NCCL)
+    final = env.stats()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else {}
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in zip(k0, k1)) / max(args.steps, 1)
+    launches = env.launch_count - launches0
+    t_all = torch.tensor([elapsed_ms, kernel_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    elapsed_ms, kernel_ms = float(t_all[0]), float(t_all[1])
+    # env steps actually executed (counted by the kernel; with substeps > 1 a rocket stops at its
+    # first done, so this can be below rockets x steps x substeps)
+    env_steps_total = float(final.env_steps)
+    if args.substeps == 1:
+        assert env_steps_total == float(args.rockets) * args.steps, (env_steps_total, args.rockets, args.steps)
+    value = env_steps_total / (elapsed_ms * 1e-3)
+
+    peak, peak_src = _peaks()
+    bytes_per_launch = BYTES_PER_ENV_STEP * count / 1.0       # one launch = `count` rockets x substeps
+    achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "rl::step_kernel<true>", "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP / args.substeps, "peak_source": peak_src}
+    traffic_file = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as fh:
+                tj = json.load(fh)
+            roofline["traffic"] = tj["dram_bytes_per_rocket"] * count
+            roofline["traffic_source"] = tj.get("source")
+        except Exception:   # noqa: BLE001
+            pass
+    env.close()
+    del actions
+    torch.cuda.empty_cache()
+
+    # ---- e2e: the reference-facing VecEnv call with HOST buffers ----------------------------
+    e2e = None
+    if not args.no_e2e:
+        import numpy as np
+        henv = RocketLandingSB3VecEnv(count, device=local_rank, seed=0, env_id_offset=start,
+                                      substeps=args.substeps, build_infos=False)
+        henv.reset()
+        hact = torch.rand((count, 2)).pin_memory()
+        hact[:, 1].mul_(2.0).sub_(1.0)
+        hnp = hact.numpy()
+        henv.step_raw(hnp)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            obs, rew, term, trunc = henv.step_raw(hnp)
+            _ = float(rew[0])                                # the result is on the host
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        t_e = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        launches += 0                                         # e2e launches are outside the timed region of `value`
+        e2e = {"value": float(args.rockets) * args.e2e_steps * args.substeps / float(t_e[0]), "unit": UNIT,
+               "h2d_bytes_per_step": 8 * count, "d2h_bytes_per_step": (32 + 4 + 1 + 1) * count,
+               "steps": args.e2e_steps, "api": "RocketLandingSB3VecEnv.step_raw -> rl_step_host (pinned numpy in/out)"}
+        henv.close()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": elapsed_ms / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.rockets} rockets total ({count} on this rank), random actions "
+                                   f"(4 pre-generated sets cycled), auto-reset, {args.substeps} substep(s) per launch, "
+                                   f"stats all-reduce every {args.stats_interval} steps",
+                       "l2": "inputs larger than L2: %.1f GB of state+action+output per launch vs 126 MB"
+                             % (BYTES_PER_ENV_STEP * count / 1e9)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "episodes": final.episodes, "mean_episode_length": final.mean_length,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import c_oracle
+            c_oracle.build()
+            cb = cpu_port_rate()
+            cb["python_port_steps_per_s_1core"] = python_port_rate(5000)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -148,8 +148,10 @@ int rl_destroy(RlEnv *env);
 
 int64_t rl_num_envs(const RlEnv *env);
 
-/* Launch epoch (counts rl_reset / rl_step launches; part of the Philox counter).  Saving
- * it with the state buffer makes a checkpoint resume bit-identically. */
+/* Launch epoch: counts rl_reset / rl_step launches and is part of the Philox counter.  It
+ * lives in device memory and is advanced by the kernels themselves, so a CUDA-graph replay
+ * of rl_step advances the reset stream like an ordinary call.  Saving it with the state
+ * buffer makes a checkpoint resume bit-identically.  Both calls synchronise the device. */
 uint64_t rl_get_epoch(const RlEnv *env);
 int rl_set_epoch(RlEnv *env, uint64_t epoch);
 

@@ -40,7 +40,8 @@ struct RlEnv {
     int64_t n = 0;
     int64_t gid0 = 0;
     uint64_t seed = 0;
-    uint64_t epoch = 0;
+    unsigned long long* epoch = nullptr;   // device: {launch epoch}
+    unsigned int* ticket = nullptr;        // device
     int device = 0;
     int grid_cap = 0;                 // persistent grid: SMs x resident CTAs of the step kernel
     int64_t launches = 0;
@@ -85,7 +86,8 @@ int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8
     a.n = e->n;
     a.gid0 = e->gid0;
     a.seed = e->seed;
-    a.epoch = e->epoch++;
+    a.epoch = e->epoch;
+    a.ticket = e->ticket;
     a.substeps = substeps;
     const int grid = grid_for(e, e->n);
     if (auto_reset) rl::step_kernel<true><<<grid, rl::kTile, 0, stream>>>(e->dev, a);
@@ -191,6 +193,10 @@ int rl_create(const RlParams* params, int64_t n_envs, int64_t env_id_offset, uin
     e->planes = rl::carve_state(e->state_buf, n_envs);
     if (cudaMalloc(&e->stats, RL_STATS_WORDS * sizeof(double)) != cudaSuccess ||
         cudaMemset(e->stats, 0, RL_STATS_WORDS * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&e->epoch, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(e->epoch, 0, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc(&e->ticket, sizeof(unsigned int)) != cudaSuccess ||
+        cudaMemset(e->ticket, 0, sizeof(unsigned int)) != cudaSuccess ||
         cudaMemset(e->state_buf, 0, bytes) != cudaSuccess) {
         rl_destroy(e);
         return fail(RL_E_CUDA, "rl_create: device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -213,6 +219,8 @@ int rl_destroy(RlEnv* e) {
     DeviceGuard guard(e->device);
     if (e->owns_state && e->state_buf) cudaFree(e->state_buf);
     if (e->stats) cudaFree(e->stats);
+    if (e->epoch) cudaFree(e->epoch);
+    if (e->ticket) cudaFree(e->ticket);
     if (e->h_stage) cudaFree(e->h_stage);
     if (e->h_stream) cudaStreamDestroy(e->h_stream);
     delete e;
@@ -220,10 +228,23 @@ int rl_destroy(RlEnv* e) {
 }
 
 int64_t rl_num_envs(const RlEnv* e) { return e ? e->n : 0; }
-uint64_t rl_get_epoch(const RlEnv* e) { return e ? e->epoch : 0; }
+uint64_t rl_get_epoch(const RlEnv* e) {
+    if (!e) return 0;
+    DeviceGuard guard(e->device);
+    unsigned long long v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpy(&v, e->epoch, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fail(RL_E_CUDA, "rl_get_epoch: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    return (uint64_t)v;
+}
 int rl_set_epoch(RlEnv* e, uint64_t epoch) {
     if (!e) return fail(RL_E_INVALID, "rl_set_epoch: null handle");
-    e->epoch = epoch;
+    DeviceGuard guard(e->device);
+    const unsigned long long v = epoch;
+    RL_CUDA(cudaDeviceSynchronize());
+    RL_CUDA(cudaMemcpy(e->epoch, &v, sizeof(v), cudaMemcpyHostToDevice));
     return RL_OK;
 }
 int64_t rl_launch_count(const RlEnv* e) { return e ? e->launches : 0; }
@@ -233,7 +254,7 @@ int rl_reset(RlEnv* e, const uint8_t* mask, float* obs, void* stream) {
     if (obs && misaligned(obs, 16)) return fail(RL_E_INVALID, "rl_reset: obs must be 16-byte aligned");
     DeviceGuard guard(e->device);
     rl::reset_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(
-        e->dev, e->planes, mask, reinterpret_cast<float4*>(obs), e->n, e->gid0, e->seed, e->epoch++);
+        e->dev, e->planes, mask, reinterpret_cast<float4*>(obs), e->n, e->gid0, e->seed, e->epoch, e->ticket);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
     return RL_OK;

@@ -49,9 +49,25 @@ struct StepArgs {
     double* __restrict__ stats;           // [RL_STATS_WORDS]
     int64_t n;
     int64_t gid0;                         // global id of rocket 0 (Philox counter)
-    uint64_t seed, epoch;
+    uint64_t seed;
+    unsigned long long* __restrict__ epoch;   // device: launch epoch (Philox counter), bumped by the last CTA
+    unsigned int* __restrict__ ticket;        // device: CTAs finished in this launch
     int substeps;
 };
+
+// The launch epoch lives in device memory so that a CUDA-graph replay of the step advances the
+// Philox stream like an ordinary launch does.  Every CTA reads it on entry; the last CTA to
+// finish (ticket) bumps it for the next launch, which is stream-ordered after this one.
+__device__ __forceinline__ void epoch_bump(unsigned long long* epoch, unsigned int* ticket) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            *ticket = 0u;
+            *epoch += 1ull;
+        }
+    }
+}
 
 // ---- block-level statistics: rare events go to shared-memory atomics, one global atomic per
 // ---- slot per CTA at the end (grid is persistent, so that is a few thousand atomics per launch)
@@ -110,6 +126,7 @@ template <bool kAutoReset>
 __global__ void __launch_bounds__(kTile) step_kernel(const DevParams P, const StepArgs a) {
     __shared__ BlockStats bs;
     stats_init(bs);
+    const uint64_t epoch = *a.epoch;
     float reward_sum = 0.0f;
     int steps_done = 0;
 
@@ -144,7 +161,7 @@ __global__ void __launch_bounds__(kTile) step_kernel(const DevParams P, const St
             if (a.episode_length) a.episode_length[i] = ep_len;
             if (kAutoReset) {                    // SB3 VecEnv contract: return the reset observation
                 float ax0, ay0;
-                sample_reset(P, a.seed, (uint64_t)(a.gid0 + i), a.epoch, r, ax0, ay0);
+                sample_reset(P, a.seed, (uint64_t)(a.gid0 + i), epoch, r, ax0, ay0);
                 fresh_obs(P, r, ax0, ay0, o.obs);
                 write_dry = true;
             }
@@ -158,12 +175,15 @@ __global__ void __launch_bounds__(kTile) step_kernel(const DevParams P, const St
         if (a.landing) a.landing[i] = (int8_t)o.landing;
     }
     stats_flush(bs, a.stats, reward_sum, steps_done);
+    epoch_bump(a.epoch, a.ticket);
 }
 
 // RocketLandingEnv.reset (lander.py:168-186) for all / masked rockets.
 __global__ void __launch_bounds__(kTile) reset_kernel(const DevParams P, StatePlanes st, const uint8_t* __restrict__ mask,
                                                       float4* __restrict__ obs, int64_t n, int64_t gid0,
-                                                      uint64_t seed, uint64_t epoch) {
+                                                      uint64_t seed, unsigned long long* __restrict__ epoch_ctr,
+                                                      unsigned int* __restrict__ ticket) {
+    const uint64_t epoch = *epoch_ctr;
     for (int64_t i = (int64_t)blockIdx.x * kTile + threadIdx.x; i < n; i += (int64_t)gridDim.x * kTile) {
         if (mask && !mask[i]) continue;
         Rocket r;
@@ -176,6 +196,7 @@ __global__ void __launch_bounds__(kTile) reset_kernel(const DevParams P, StatePl
             obs[2 * i + 1] = make_float4(o[4], o[5], o[6], o[7]);
         }
     }
+    epoch_bump(epoch_ctr, ticket);
 }
 
 // Public state format <-> planes (rl_set_state / rl_get_state).

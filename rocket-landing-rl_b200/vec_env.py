@@ -68,10 +68,11 @@ class RocketLandingSB3VecEnv:
         self._rew = _pinned((n,), torch.float32)
         self._term = _pinned((n,), torch.uint8)
         self._trunc = _pinned((n,), torch.uint8)
-        self._tobs = _pinned((n, 8), torch.float32)
-        self._epr = _pinned((n,), torch.float32)
-        self._epl = _pinned((n,), torch.int32)
-        self._land = _pinned((n,), torch.int8)
+        if self.build_infos:      # per-episode records: only needed to build the SB3 info dicts
+            self._tobs = _pinned((n, 8), torch.float32)
+            self._epr = _pinned((n,), torch.float32)
+            self._epl = _pinned((n,), torch.int32)
+            self._land = _pinned((n,), torch.int8)
         self._pending = False
 
     # ---- SB3 VecEnv surface -------------------------------------------------------------
@@ -90,11 +91,14 @@ class RocketLandingSB3VecEnv:
         if not self._pending:
             raise RuntimeError("step_wait() without step_async()")
         self._pending = False
+        if self.build_infos:
+            extra = (self._tobs.ctypes.data, self._epr.ctypes.data, self._epl.ctypes.data,
+                     self._land.ctypes.data)
+        else:
+            extra = (None, None, None, None)
         _lib.check(self._L.rl_step_host(
             self._h, self._actions.ctypes.data, self._obs.ctypes.data, self._rew.ctypes.data,
-            self._term.ctypes.data, self._trunc.ctypes.data, self._tobs.ctypes.data,
-            self._epr.ctypes.data, self._epl.ctypes.data, self._land.ctypes.data, self.substeps, 1),
-            "rl_step_host")
+            self._term.ctypes.data, self._trunc.ctypes.data, *extra, self.substeps, 1), "rl_step_host")
         dones = (self._term | self._trunc).astype(bool)
         infos: List[Dict[str, Any]] = self._infos(dones) if self.build_infos else []
         return self._obs.copy(), self._rew.copy(), dones, infos

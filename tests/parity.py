@@ -349,6 +349,26 @@ def replay_golden_rollout(stepper, g: dict) -> ParityReport:
     return chk.rep
 
 
+def replay_edge_cases(stepper, g: dict) -> ParityReport:
+    """Teacher-forced wild states of ``ref_edge_cases.npz`` (outputs of the reference itself):
+    inject, step twice with the same action, compare both steps."""
+    n = g["init_state"].shape[0]
+    assert stepper.n == n
+    stepper.inject_fresh(g["init_state"], steps=g["init_step"])
+    chk = LockstepChecker(n)
+    y_before = g["init_state"][:, 1].copy()
+    before = stepper.view()
+    for k in range(2):
+        obs, rew, term, trunc, land = stepper.step(g["actions"])
+        after = stepper.view()
+        chk.teacher_forced(k, before, after, g["actions"], rew, term, trunc, land)
+        chk.compare(k, obs, rew, term, trunc, land, after, g["state"][k], g["obs"][k], g["reward"][k],
+                    g["terminated"][k], g["truncated"][k], g["landing"][k], y_before)
+        y_before = g["state"][k][:, 1].copy()
+        before = after
+    return chk.rep
+
+
 def sample_reset_states(rng: np.random.Generator, params: RlParams, n: int) -> np.ndarray:
     lo = np.array(list(params.reset_low))
     hi = np.array(list(params.reset_high))

@@ -1,0 +1,126 @@
+"""CPU tier: the DEVICE math (rocket-landing-rl_b200/csrc/rl_device.cuh) compiled for the host
+with shimmed intrinsics (tests/hostemu) against the reference's committed outputs and the C
+oracle.  This is a logic check of the fp32 formulation that runs without a GPU; the GPU tier
+(test_gpu_parity.py) runs the same harness on the real kernels."""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from oracle import c_oracle
+
+
+def test_reference_rollouts_replayed(golden_dir):
+    g = dict(np.load(os.path.join(golden_dir, "ref_rollout_batch8.npz")))
+    rep = parity.replay_golden_rollout(parity.HostEmuStepper(8), g)
+    rep.assert_ok(max_guard_events=1)
+    assert rep.steps_compared >= 7990 and rep.episodes >= 50
+
+
+def test_reference_single_env_trace_replayed(golden_dir):
+    g = dict(np.load(os.path.join(golden_dir, "ref_rollout_single.npz")))
+    g2 = {k: (v[:, None] if v.ndim >= 1 and k not in ("init_state", "init_obs") else v[None])
+          for k, v in g.items()}
+    rep = parity.replay_golden_rollout(parity.HostEmuStepper(1), g2)
+    rep.assert_ok(max_guard_events=0)
+    assert rep.episodes == 8
+
+
+def test_reference_edge_cases_replayed(golden_dir):
+    g = dict(np.load(os.path.join(golden_dir, "ref_edge_cases.npz")))
+    rep = parity.replay_edge_cases(parity.HostEmuStepper(g["init_state"].shape[0]), g)
+    rep.assert_ok(max_guard_events=2)
+    assert (rep.landing_counts[1:] > 0).all()
+
+
+@pytest.mark.parametrize("action_fn", [parity.random_actions, parity.braking_actions])
+def test_lockstep_against_c_oracle(action_fn):
+    n = 1024
+    rep = parity.lockstep_vs_oracle(parity.HostEmuStepper(n), c_oracle.BatchOracle(n), 400, seed=11,
+                                    action_fn=action_fn)
+    rep.assert_ok(max_guard_events=8)
+    assert rep.steps_compared > 0.999 * n * 400
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10."""
+    st = parity.HostEmuStepper(1)
+    assert st.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert st.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert st.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344],
+                     [0xa4093822, 0x299f31d0]) == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_reset_distribution_matches_config_ranges():
+    """get_initial_state (simulation/config.py:26-53): ten independent uniforms on the
+    config ranges.  Checks support, first two moments and pairwise independence."""
+    n = 200_000
+    st = parity.HostEmuStepper(n)
+    obs = st.philox_reset(gid0=0, seed=123, epoch=7)
+    v = st.view()
+    assert v["fresh"].all() and (v["steps"] == 0).all() and (v["ep_return"] == 0).all()
+    lo = np.array(list(st.params.reset_low))
+    hi = np.array(list(st.params.reset_high))
+    cols = [v["x"], v["y"], v["vx"], v["vy"], obs[:, 4].astype(np.float64), obs[:, 5].astype(np.float64),
+            v["angle"], v["ang_vel"], v["dry_mass"], v["fuel"]]
+    for k, c in enumerate(cols):
+        assert c.min() >= lo[k] and c.max() <= hi[k], k
+        span = hi[k] - lo[k]
+        assert abs(c.mean() - (lo[k] + hi[k]) / 2) < 4 * span / np.sqrt(12 * n), k
+        assert abs(c.std() - span / np.sqrt(12)) < 0.01 * span, k
+    corr = np.corrcoef(np.stack(cols))
+    assert np.abs(corr - np.eye(10)).max() < 0.015
+    # reset observation = clip(float32(state)) with the SAMPLED ax, ay (lander.py:182)
+    np.testing.assert_array_equal(obs[:, 0], v["x"].astype(np.float32))
+    np.testing.assert_array_equal(obs[:, 3], np.clip(v["vy"], -200, -150).astype(np.float32))
+    # counter-based: a different epoch / seed / id range gives different draws, same call the same
+    again = parity.HostEmuStepper(n)
+    again.philox_reset(gid0=0, seed=123, epoch=7)
+    np.testing.assert_array_equal(again.soa, st.soa)
+    other = parity.HostEmuStepper(n)
+    other.philox_reset(gid0=0, seed=123, epoch=8)
+    assert (other.soa[0] != st.soa[0]).mean() > 0.99
+    shifted = parity.HostEmuStepper(1000)
+    shifted.philox_reset(gid0=5000, seed=123, epoch=7)
+    np.testing.assert_array_equal(shifted.soa[:8], st.soa[:8, 5000:6000])
+
+
+def test_fused_substeps_equal_repeated_single_steps():
+    """K fused substeps == K single steps with the same action: rewards summed, integration
+    stops at the first done."""
+    n, K = 512, 8
+    rng = np.random.default_rng(5)
+    a_ = parity.HostEmuStepper(n)
+    b_ = parity.HostEmuStepper(n)
+    init = parity.sample_reset_states(rng, a_.params, n)
+    init[:, 1] = rng.uniform(5.0, 400.0, n)          # low enough that many touch down within K
+    a_.inject_fresh(init)
+    b_.inject_fresh(init)
+    for _ in range(6):
+        act = rng.uniform([0, -1], [1, 1], (n, 2)).astype(np.float32)
+        obs_k, rew_k, term_k, trunc_k, land_k = a_.step(act, substeps=K)
+        rew = np.zeros(n, np.float32)
+        done = np.zeros(n, bool)
+        term = np.zeros(n, bool)
+        obs = np.zeros((n, 8), np.float32)
+        keep = b_.soa.copy()
+        for k in range(K):
+            o, r, te, tr, la = b_.step(act)
+            live = ~done
+            # rockets that were already done must not advance: restore them
+            b_.soa[:, done] = keep[:, done]
+            rew[live] += r[live]
+            obs[live] = o[live]
+            term[live] = te[live]
+            done |= live & (te | tr)
+            keep = b_.soa.copy()
+        np.testing.assert_array_equal(term_k, term)
+        np.testing.assert_array_equal(a_.soa, b_.soa)
+        np.testing.assert_array_equal(obs_k, obs)
+        np.testing.assert_allclose(rew_k, rew, rtol=1e-6, atol=1e-6)
+        assert done.any()
+        fresh = parity.sample_reset_states(rng, a_.params, n)
+        fresh[:, 1] = rng.uniform(5.0, 400.0, n)
+        a_.inject_fresh(fresh, mask=done)
+        b_.inject_fresh(fresh, mask=done)
