@@ -160,6 +160,9 @@ def main() -> None:
     ap.add_argument("--rockets", type=int, default=TOTAL_ROCKETS, help="total rockets over all ranks")
     ap.add_argument("--substeps", type=int, default=1)
     ap.add_argument("--stats-interval", type=int, default=100)
+    ap.add_argument("--spinup", type=int, default=400,
+                    help="untimed env steps before the warm-up, so that episodes are desynchronised "
+                         "(steady state: ~1/113 of the rockets reset per step, as in a long rollout)")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -201,6 +204,10 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # All rockets start their first episode together; a long rollout does not look like that.
+    # Spin up (untimed) until episode phases are mixed, then do the W warm-up steps.
+    for t in range((args.spinup + args.substeps - 1) // args.substeps):
+        env.step(actions[t % n_sets])
     for t in range(warmup):
         env.step(actions[t % n_sets])
     env.stats(reset=True)
@@ -290,7 +297,8 @@ def main() -> None:
             "warmup": warmup, "ms_per_step": elapsed_ms / max(args.steps, 1), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.rockets} rockets total ({count} on this rank), random actions "
-                                   f"(4 pre-generated sets cycled), auto-reset, {args.substeps} substep(s) per launch, "
+                                   f"(4 pre-generated sets cycled), auto-reset (steady state after {args.spinup} "
+                                   f"untimed spin-up steps), {args.substeps} substep(s) per launch, "
                                    f"stats all-reduce every {args.stats_interval} steps",
                        "l2": "inputs larger than L2: %.1f GB of state+action+output per launch vs 126 MB"
                              % (BYTES_PER_ENV_STEP * count / 1e9)},

@@ -83,7 +83,7 @@ int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8
     a.episode_length = episode_length;
     a.landing = landing;
     a.stats = e->stats;
-    a.n = e->n;
+    a.n = (uint32_t)e->n;
     a.gid0 = e->gid0;
     a.seed = e->seed;
     a.epoch = e->epoch;
@@ -160,6 +160,8 @@ int rl_create(const RlParams* params, int64_t n_envs, int64_t env_id_offset, uin
               void* state_buf, RlEnv** out) {
     if (!params || !out) return fail(RL_E_INVALID, "rl_create: null argument");
     if (n_envs <= 0) return fail(RL_E_INVALID, "rl_create: n_envs must be positive (got %lld)", (long long)n_envs);
+    if (n_envs > 2147483392LL)    // 32-bit rocket index inside a shard (2^31 - 256); shard larger batches
+        return fail(RL_E_INVALID, "rl_create: at most 2147483392 rockets per handle (got %lld)", (long long)n_envs);
     if (env_id_offset < 0) return fail(RL_E_INVALID, "rl_create: env_id_offset must be >= 0");
     if (state_buf && misaligned(state_buf, 256)) return fail(RL_E_INVALID, "rl_create: state_buf must be 256-byte aligned");
     RlEnv* e = new (std::nothrow) RlEnv();
@@ -203,6 +205,10 @@ int rl_create(const RlParams* params, int64_t n_envs, int64_t env_id_offset, uin
     }
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    // the step kernel stages tiles in ~37 KiB of static shared memory per CTA: ask for the largest
+    // shared-memory carve-out so that registers, not shared memory, bound the resident CTAs
+    cudaFuncSetAttribute(rl::step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(rl::step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rl::step_kernel<true>, rl::kTile, 0);
     if (sms <= 0 || per_sm <= 0) {
         rl_destroy(e);
@@ -254,7 +260,7 @@ int rl_reset(RlEnv* e, const uint8_t* mask, float* obs, void* stream) {
     if (obs && misaligned(obs, 16)) return fail(RL_E_INVALID, "rl_reset: obs must be 16-byte aligned");
     DeviceGuard guard(e->device);
     rl::reset_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(
-        e->dev, e->planes, mask, reinterpret_cast<float4*>(obs), e->n, e->gid0, e->seed, e->epoch, e->ticket);
+        e->dev, e->planes, mask, reinterpret_cast<float4*>(obs), (uint32_t)e->n, e->gid0, e->seed, e->epoch, e->ticket);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
     return RL_OK;
@@ -278,7 +284,7 @@ int rl_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8_t* 
 int rl_set_state(RlEnv* e, const float* state_soa, const uint8_t* mask, void* stream) {
     if (!e || !state_soa) return fail(RL_E_INVALID, "rl_set_state: null argument");
     DeviceGuard guard(e->device);
-    rl::set_state_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(e->planes, state_soa, mask, e->n);
+    rl::set_state_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(e->planes, state_soa, mask, (uint32_t)e->n);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
     return RL_OK;
@@ -287,7 +293,7 @@ int rl_set_state(RlEnv* e, const float* state_soa, const uint8_t* mask, void* st
 int rl_get_state(RlEnv* e, float* state_soa, void* stream) {
     if (!e || !state_soa) return fail(RL_E_INVALID, "rl_get_state: null argument");
     DeviceGuard guard(e->device);
-    rl::get_state_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(e->planes, state_soa, e->n);
+    rl::get_state_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(e->planes, state_soa, (uint32_t)e->n);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
     return RL_OK;

@@ -14,6 +14,11 @@
 // where k is the number of 360-degree wraps the PREVIOUS normalisation applied: the reference
 // keeps the normalised angle as the next step's "previous" angle (base.py:171), so after a
 // wrap its (th - th_prev) contains a spurious -+360; subtracting 360 k reproduces that exactly.
+//
+// The always-executed path is written with selects instead of branches (the kernel is issue- as
+// much as bandwidth-limited, and BSSY/BSYNC/BRA around short divergent regions cost more than
+// the few flops they skip); only genuinely rare events branch: touchdown, an angle leaving
+// [-180, 180), a zero-mass rocket.
 #pragma once
 #ifndef RL_HOST_EMULATION
 #include <cuda_runtime.h>
@@ -23,7 +28,6 @@
 #include "rl_params.h"
 
 namespace rl {
-
 
 struct Rocket {                // the ten persistent words (RL_W_*)
     float x, y, ang;
@@ -40,6 +44,19 @@ struct StepResult {
     int landing;               // 0 none, 1 safe, 2 good, 3 ok, 4 unsafe (protocol.py:31-41)
 };
 
+// ---- small math helpers (shimmed in the host build of tests/hostemu) --------------------------
+#ifndef RL_HOST_EMULATION
+__device__ __forceinline__ float rl_rcp(float x) { return __frcp_rn(x); }          // correctly rounded 1/x
+__device__ __forceinline__ float rl_sqrt(float x) { return __fsqrt_rn(x); }
+__device__ __forceinline__ float rl_div_fast(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ uint32_t rl_f2u(float f) { return __float_as_uint(f); }
+#else
+inline float rl_rcp(float x) { return 1.0f / x; }
+inline float rl_sqrt(float x) { return std::sqrt(x); }
+inline float rl_div_fast(float a, float b) { return a / b; }
+inline uint32_t rl_f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+#endif
+
 // ---- Philox4x32-10 (Salmon et al., SC'11), counter-based: no per-rocket generator state ----
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
@@ -51,6 +68,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
         k.y += 0xBB67AE85u;
     }
     return c;
+}
+
+// Counter of Philox block `blk` (0..2) of the reset of global rocket `gid` at launch `epoch`.
+__device__ __forceinline__ uint4 reset_counter(uint64_t gid, uint64_t epoch, uint32_t blk) {
+    return make_uint4((uint32_t)gid, (uint32_t)(gid >> 32), (uint32_t)epoch, ((uint32_t)(epoch >> 32) << 2) | blk);
 }
 
 // 24 random bits -> [0, 1) exactly representable in fp32
@@ -72,28 +94,34 @@ __device__ __forceinline__ float normalize_angle(float a, int& k) {
 }
 
 // get_initial_state (simulation/config.py:26-53): ten independent uniforms lo + span u, in the
-// reference's draw order, from three Philox blocks keyed by (seed, global rocket id, epoch).
-// Returns the sampled ax, ay (they only ever appear in the reset observation, lander.py:182).
+// reference's draw order x, y, vx, vy, ax, ay, angle, angular velocity, dry mass, fuel mass, from
+// the ten random words w[0..9].  Returns the sampled ax, ay (they only ever appear in the reset
+// observation, lander.py:182).
+__device__ __forceinline__ void rocket_from_words(const DevParams& P, const uint32_t* w, Rocket& r,
+                                                  float& ax0, float& ay0) {
+    r.x = fmaf(P.reset_span[0], u01(w[0]), P.reset_lo[0]);
+    r.y = fmaf(P.reset_span[1], u01(w[1]), P.reset_lo[1]);
+    r.sx = fmaf(P.reset_span[2], u01(w[2]), P.reset_lo[2]);      // vx while FRESH
+    r.sy = fmaf(P.reset_span[3], u01(w[3]), P.reset_lo[3]);      // vy while FRESH
+    ax0 = fmaf(P.reset_span[4], u01(w[4]), P.reset_lo[4]);
+    ay0 = fmaf(P.reset_span[5], u01(w[5]), P.reset_lo[5]);
+    r.ang = fmaf(P.reset_span[6], u01(w[6]), P.reset_lo[6]);
+    r.sang = fmaf(P.reset_span[7], u01(w[7]), P.reset_lo[7]);    // angular velocity while FRESH
+    r.dry = fmaf(P.reset_span[8], u01(w[8]), P.reset_lo[8]);
+    r.fuel = fmaf(P.reset_span[9], u01(w[9]), P.reset_lo[9]);
+    r.ep_ret = 0.0f;
+    r.meta = RL_META_FRESH;                                      // current_step = 0 (lander.py:180)
+}
+
+// One thread draws all three Philox blocks keyed by (seed, global rocket id, epoch).
 __device__ __forceinline__ void sample_reset(const DevParams& P, uint64_t seed, uint64_t gid,
                                              uint64_t epoch, Rocket& r, float& ax0, float& ay0) {
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    const uint32_t c0 = (uint32_t)gid, c1 = (uint32_t)(gid >> 32), c2 = (uint32_t)epoch;
-    const uint32_t c3 = (uint32_t)(epoch >> 32) << 2;
-    const uint4 a = philox4x32_10(make_uint4(c0, c1, c2, c3 | 0u), key);
-    const uint4 b = philox4x32_10(make_uint4(c0, c1, c2, c3 | 1u), key);
-    const uint4 c = philox4x32_10(make_uint4(c0, c1, c2, c3 | 2u), key);
-    r.x = fmaf(P.reset_span[0], u01(a.x), P.reset_lo[0]);
-    r.y = fmaf(P.reset_span[1], u01(a.y), P.reset_lo[1]);
-    r.sx = fmaf(P.reset_span[2], u01(a.z), P.reset_lo[2]);      // vx while FRESH
-    r.sy = fmaf(P.reset_span[3], u01(a.w), P.reset_lo[3]);      // vy while FRESH
-    ax0 = fmaf(P.reset_span[4], u01(b.x), P.reset_lo[4]);
-    ay0 = fmaf(P.reset_span[5], u01(b.y), P.reset_lo[5]);
-    r.ang = fmaf(P.reset_span[6], u01(b.z), P.reset_lo[6]);
-    r.sang = fmaf(P.reset_span[7], u01(b.w), P.reset_lo[7]);    // angular velocity while FRESH
-    r.dry = fmaf(P.reset_span[8], u01(c.x), P.reset_lo[8]);
-    r.fuel = fmaf(P.reset_span[9], u01(c.y), P.reset_lo[9]);
-    r.ep_ret = 0.0f;
-    r.meta = RL_META_FRESH;                                      // current_step = 0 (lander.py:180)
+    const uint4 a = philox4x32_10(reset_counter(gid, epoch, 0u), key);
+    const uint4 b = philox4x32_10(reset_counter(gid, epoch, 1u), key);
+    const uint4 c = philox4x32_10(reset_counter(gid, epoch, 2u), key);
+    const uint32_t w[10] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
+    rocket_from_words(P, w, r, ax0, ay0);
 }
 
 __device__ __forceinline__ float clipf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
@@ -121,8 +149,21 @@ __device__ __forceinline__ void fresh_obs(const DevParams& P, const Rocket& r, f
 __device__ __forceinline__ float potential(float y, float vx, float vy, float ang, float om) {
     const float yp = fmaxf(0.0f, y);
     const float w = 2.0f - fminf(1.0f, yp * (1.0f / 2000.0f));
-    return -0.005f * yp - (0.015f * w) * fabsf(vy) - 0.005f * fabsf(vx) - (0.01f * w) * fabsf(ang) -
-           (0.05f * w) * fabsf(om);
+    const float near_ground = fmaf(0.015f, fabsf(vy), fmaf(0.01f, fabsf(ang), 0.05f * fabsf(om)));
+    return -fmaf(w, near_ground, fmaf(0.005f, yp, 0.005f * fabsf(vx)));
+}
+
+// Landing step (rare): evaluate_landing (utils.py:1-37) + landing reward (reward.py:77-100).
+__device__ __noinline__ float landing_reward(const DevParams& P, float avx, float avy, float aa, int& cls) {
+    cls = 4;
+    if (avx < P.land_lt[2][0] && avy < P.land_lt[2][1] && aa < P.land_lt[2][2]) cls = 3;
+    if (avx < P.land_lt[1][0] && avy < P.land_lt[1][1] && aa < P.land_lt[1][2]) cls = 2;
+    if (avx < P.land_lt[0][0] && avy < P.land_lt[0][1] && aa < P.land_lt[0][2]) cls = 1;
+    const float q = 0.6f * fmaxf(0.0f, 1.0f - aa * 0.1f) + 0.4f * fmaxf(0.0f, 1.0f - avy * 0.2f);
+    if (cls == 1) return P.r_perfect * (1.0f + 0.5f * q);
+    if (cls == 2) return P.r_good * (0.8f + 0.2f * q);
+    if (cls == 3) return P.r_ok;
+    return P.r_crash * (0.7f + 0.3f * fminf(1.0f, (avy * 0.05f + aa * (1.0f / 45.0f)) * 0.5f));
 }
 
 // One env step (lander.py:188-255) of one rocket, no reset.  th_raw / cg_raw are the raw
@@ -130,56 +171,48 @@ __device__ __forceinline__ float potential(float y, float vx, float vy, float an
 __device__ __forceinline__ void rocket_step(const DevParams& P, Rocket& r, float th_raw, float cg_raw,
                                             StepResult& o) {
     const bool fresh = (r.meta & RL_META_FRESH) != 0u;
-    int steps = (int)(r.meta & RL_META_STEP_MASK);
+    const int steps = min((int)(r.meta & RL_META_STEP_MASK) + 1, (int)RL_META_STEP_MASK);   // lander.py:229
     const int k_prev = ((int)(r.meta << 5)) >> 29;             // bits [24,27) sign-extended
 
     // ---- state before the action (Rocket.get_state, base.py:220) --------------------------
     const float y_b = r.y, ang_b = r.ang;
-    const float vx_b = fresh ? r.sx : r.sx * P.inv_dt;
-    const float vy_b = fresh ? r.sy : r.sy * P.inv_dt;
-    const float om_b = fresh ? r.sang : r.sang * P.inv_dt;
+    const float vscale = fresh ? 1.0f : P.inv_dt;               // slots hold v while FRESH, deltas after
+    const float vx_b = r.sx * vscale, vy_b = r.sy * vscale, om_b = r.sang * vscale;
 
     // ---- Rocket.apply_action (base.py:132-184) -----------------------------------------------
-    float th = clipf(th_raw, 0.0f, 1.0f);
-    const float cg = clipf(cg_raw, -1.0f, 1.0f);
     const float fuel_now = r.fuel;
-    if (fuel_now <= 0.0f) th = 0.0f;                           // base.py:138-141
+    const float th = (fuel_now <= 0.0f) ? 0.0f : clipf(th_raw, 0.0f, 1.0f);       // base.py:135-141
+    const float cg = clipf(cg_raw, -1.0f, 1.0f);
     const float m = r.dry + fuel_now;                          // pre-burn mass, base.py:143-144
 
     float ax = 0.0f, ay = 0.0f, vx_a = vx_b, vy_a = vy_b, om_a = om_b;
     if (m > P.mass_gate) {                                     // base.py:145-147: else no-op
-        const float inv_m = 1.0f / m;
+        const float inv_m = rl_rcp(m);
         // drag (engine.py:78-98): 0.5 rho Cd A v^2 (-v/|v|) = -drag_k |v| v
         const float v2 = fmaf(vx_b, vx_b, vy_b * vy_b);
-        const float kd = (v2 > P.speed2_gate) ? P.drag_k * sqrtf(v2) * inv_m : 0.0f;
+        const float kd = (v2 > P.speed2_gate) ? P.drag_k * rl_sqrt(v2) * inv_m : 0.0f;
         // zero-control acceleration: gravity + drag (engine.py:48-52, :117-123)
         const float a0x = -kd * vx_b;
         const float a0y = fmaf(-kd, vy_b, P.gravity);
-        ax = a0x;
-        ay = a0y;
-        if (th > P.throttle_gate) {                            // thrust, engine.py:63-74
-            float s, c;
-            sincospif(ang_b * (1.0f / 180.0f), &s, &c);
-            const float t = th * P.thrust_power * inv_m;
-            ax = fmaf(t, s, ax);
-            ay = fmaf(t, c, ay);
-        }
+        // thrust along the rocket axis, only above the throttle gate (engine.py:63-74)
+        float s, c;
+        sincospif(ang_b * (1.0f / 180.0f), &s, &c);
+        const float t = (th > P.throttle_gate) ? th * P.thrust_power * inv_m : 0.0f;
+        ax = fmaf(t, s, a0x);
+        ay = fmaf(t, c, a0y);
         const float alpha = (m >= P.alpha_min_mass) ? cg * P.alpha_k * inv_m : 0.0f;  // engine.py:125-155
 
-        float dx, dy, dang;
-        if (fresh) {
-            // Verlet bootstrap (base.py:65-130): x - x_prev = v dt - a0 dt^2 / 2, alpha0 = 0
-            dx = fmaf(-P.half_dt2, a0x, vx_b * P.dt);
-            dy = fmaf(-P.half_dt2, a0y, vy_b * P.dt);
-            const float back = om_b * P.dt;
-            int kp;
-            (void)normalize_angle(ang_b - back, kp);          // base.py:117: previous angle is normalised
-            dang = fmaf(360.0f, (float)kp, back);
-        } else {
-            dx = r.sx;
-            dy = r.sy;
-            dang = fmaf(-360.0f, (float)k_prev, r.sang);       // (angle - previous angle), base.py:171
-        }
+        // carried deltas; a FRESH rocket gets the Verlet bootstrap (base.py:65-130):
+        // x - x_prev = v dt - a0 dt^2 / 2 and, alpha0 being 0, angle - angle_prev = omega dt
+        const float boot_x = fmaf(-P.half_dt2, a0x, vx_b * P.dt);
+        const float boot_y = fmaf(-P.half_dt2, a0y, vy_b * P.dt);
+        const float back = om_b * P.dt;
+        int kp = 0;
+        if (fresh) (void)normalize_angle(ang_b - back, kp);    // base.py:117 normalises the previous angle
+        const float dx = fresh ? boot_x : r.sx;
+        const float dy = fresh ? boot_y : r.sy;
+        // (angle - previous angle) with both angles normalised (base.py:171)
+        const float dang = fresh ? fmaf(360.0f, (float)kp, back) : fmaf(-360.0f, (float)k_prev, r.sang);
         // engine.py:181-222
         const float ndx = fmaf(ax, P.dt2, dx);
         const float ndy = fmaf(ay, P.dt2, dy);
@@ -195,86 +228,65 @@ __device__ __forceinline__ void rocket_step(const DevParams& P, Rocket& r, float
         r.sy = ndy;
         r.sang = ndang;
         r.fuel = fmaxf(0.0f, fuel_now - fmaxf(0.0f, th * P.burn_per_step));   // engine.py:239-243, base.py:174-175
-        r.meta = ((uint32_t)k & 7u) << RL_META_WRAP_SHIFT;     // FRESH cleared; step count set below
+        r.meta = (((uint32_t)k & 7u) << RL_META_WRAP_SHIFT) | (uint32_t)steps;   // FRESH cleared
     } else {
         r.fuel = fmaxf(0.0f, fuel_now);
-        r.meta &= ~RL_META_STEP_MASK;
+        r.meta = (r.meta & ~RL_META_STEP_MASK) | (uint32_t)steps;
     }
-    steps = min(steps + 1, (int)RL_META_STEP_MASK);            // lander.py:229
-    r.meta |= (uint32_t)steps;
 
     const float x_a = r.x, y_a = r.y, ang_a = r.ang;
     const float aa = fabsf(ang_a), avy = fabsf(vy_a);
 
-    // ---- calculate_reward (reward.py:27-281) -----------------------------------------------
-    float total = 0.0f;
-    o.terminated = (y_a <= P.ground_y) && (y_b > P.ground_y);  // reward.py:73
-    o.truncated = false;
-    o.out_of_bounds = false;
-    o.tipped = false;
-    o.landing = 0;
-    if (o.terminated) {
-        // evaluate_landing (utils.py:1-37)
-        const float avx = fabsf(vx_a);
-        int cls = 4;
-        if (avx < P.land_lt[2][0] && avy < P.land_lt[2][1] && aa < P.land_lt[2][2]) cls = 3;
-        if (avx < P.land_lt[1][0] && avy < P.land_lt[1][1] && aa < P.land_lt[1][2]) cls = 2;
-        if (avx < P.land_lt[0][0] && avy < P.land_lt[0][1] && aa < P.land_lt[0][2]) cls = 1;
-        o.landing = cls;
-        const float q = 0.6f * fmaxf(0.0f, 1.0f - aa * 0.1f) + 0.4f * fmaxf(0.0f, 1.0f - avy * 0.2f);
-        if (cls == 1) total = P.r_perfect * (1.0f + 0.5f * q);
-        else if (cls == 2) total = P.r_good * (0.8f + 0.2f * q);
-        else if (cls == 3) total = P.r_ok;
-        else total = P.r_crash * (0.7f + 0.3f * fminf(1.0f, (avy * 0.05f + aa * (1.0f / 45.0f)) * 0.5f));
-        // reward.py:102 returns here: no bounds / tip-over check on the landing step
-    } else {
-        const float ab = fabsf(ang_b), wb = fabsf(om_b), wa = fabsf(om_a);
-        // 1. angular control (reward.py:108-124)
-        total = -(aa - ab) * 0.5f - (wa - wb) * 0.1f;
-        // cold-gas direction term (reward.py:130-167); cold gas is the RAW action
-        const float acg = fabsf(cg_raw);
-        if (ab > P.dead_band || wb > P.dead_band) {
-            const bool correct = (ang_b > 0.0f && cg_raw < 0.0f) || (ang_b < 0.0f && cg_raw > 0.0f);
-            const float effect = (ab - aa) + (wb - wa);
-            float cgr = acg * (ab + wb) * (correct ? P.k_direction : -P.k_direction) * P.k_cold_gas;
-            if (effect > 0.0f) cgr *= fmaf(effect, effect, 1.0f);
-            total += cgr;
-        } else {
-            total -= acg * 0.3f * P.k_cold_gas;
-        }
-        const bool airborne = y_a > P.ground_y;
-        if (airborne && vy_a < 0.0f) {
-            // 2. throttle while descending (reward.py:171-186)
-            const float af = fmaxf(0.0f, 1.0f - aa * (1.0f / 45.0f));
-            total += th_raw * (-vy_a) * af * (1.0f + fminf(1.0f, avy * 0.1f)) * P.k_throttle_descent;
-            // 3. free fall (reward.py:190-201)
-            if (th_raw < P.throttle_lo_lt) {
-                const float prox = 1.0f + __fdividef(8.0f, fmaxf(y_a, 1.0f));
-                total -= P.k_free_fall * (-vy_a) * prox * (1.0f + fminf(1.0f, avy * (1.0f / 15.0f)));
-            }
-        }
-        // 4. throttle while tilted (reward.py:205-219)
-        if (th_raw > P.throttle_lo_gt && airborne) {
-            if (aa > 10.0f) total -= th_raw * (aa * (1.0f / 90.0f)) * P.k_angle_throttle;
-            else if (aa > 5.0f) total -= th_raw * ((aa - 5.0f) * 0.2f) * P.k_angle_throttle * 0.5f;
-        }
-        // 5. climbing (reward.py:222-227)
-        if (airborne && vy_a > 0.0f)
-            total -= vy_a * 0.5f * fminf(1.0f, y_a * 1e-3f) * (1.0f + fminf(1.0f, vy_a * 0.2f));
-        // 6. potential shaping (reward.py:267-270)
-        total += fmaf(P.gamma, potential(y_a, vx_a, vy_a, ang_a, om_a), -potential(y_b, vx_b, vy_b, ang_b, om_b));
-        // truncation penalties (reward.py:274-279); tip-over never ends the episode
-        if (fabsf(x_a) > P.max_x || y_a > P.max_y) {
-            total += P.r_oob;
-            o.truncated = true;
-            o.out_of_bounds = true;
-        }
-        if (aa > P.tip_angle) {
-            total += P.r_tip;
-            o.tipped = true;
-        }
+    // ---- calculate_reward (reward.py:27-281), shaping path ------------------------------------
+    const float ab = fabsf(ang_b), wb = fabsf(om_b), wa = fabsf(om_a);
+    const float d_ang = ab - aa, d_om = wb - wa;
+    // 1. angular control (reward.py:108-124)
+    float total = fmaf(d_ang, 0.5f, d_om * 0.1f);
+    // cold-gas direction term (reward.py:130-167); cold gas is the RAW action
+    const bool need = (ab > P.dead_band) || (wb > P.dead_band);
+    // (angle > 0 and cg < 0) or (angle < 0 and cg > 0): both non-zero with opposite signs
+    const bool correct = (ang_b != 0.0f) && (cg_raw != 0.0f) && ((int32_t)(rl_f2u(ang_b) ^ rl_f2u(cg_raw)) < 0);
+    const float effect = d_ang + d_om;
+    const float amp = (need && effect > 0.0f) ? fmaf(effect, effect, 1.0f) : 1.0f;
+    const float gain = need ? (ab + wb) * (correct ? P.k_direction : -P.k_direction) : -0.3f;
+    total = fmaf(fabsf(cg_raw) * gain * P.k_cold_gas, amp, total);
+    const bool airborne = y_a > P.ground_y;
+    const bool descending = airborne && (vy_a < 0.0f);
+    // 2. throttle while descending (reward.py:171-186)
+    const float af = fmaxf(0.0f, fmaf(aa, -1.0f / 45.0f, 1.0f));
+    const float t2 = th_raw * (-vy_a) * af * (1.0f + fminf(1.0f, avy * 0.1f)) * P.k_throttle_descent;
+    total += descending ? t2 : 0.0f;
+    // 3. free fall (reward.py:190-201)
+    const float prox = 1.0f + rl_div_fast(8.0f, fmaxf(y_a, 1.0f));
+    const float t3 = P.k_free_fall * (-vy_a) * prox * (1.0f + fminf(1.0f, avy * (1.0f / 15.0f)));
+    total -= (descending && th_raw < P.throttle_lo_lt) ? t3 : 0.0f;
+    // 4. throttle while tilted (reward.py:205-219)
+    const float tilt = (aa > 10.0f) ? aa * (1.0f / 90.0f) : ((aa > 5.0f) ? (aa - 5.0f) * 0.1f : 0.0f);
+    total -= (airborne && th_raw > P.throttle_lo_gt) ? th_raw * tilt * P.k_angle_throttle : 0.0f;
+    // 5. climbing (reward.py:222-227)
+    const float t5 = vy_a * 0.5f * fminf(1.0f, y_a * 1e-3f) * (1.0f + fminf(1.0f, vy_a * 0.2f));
+    total -= (airborne && vy_a > 0.0f) ? t5 : 0.0f;
+    // 6. potential shaping (reward.py:267-270)
+    total += fmaf(P.gamma, potential(y_a, vx_a, vy_a, ang_a, om_a), -potential(y_b, vx_b, vy_b, ang_b, om_b));
+    // truncation penalties (reward.py:274-279); tip-over never ends the episode
+    bool oob = (fabsf(x_a) > P.max_x) || (y_a > P.max_y);
+    bool tipped = aa > P.tip_angle;
+    total += oob ? P.r_oob : 0.0f;
+    total += tipped ? P.r_tip : 0.0f;
+
+    // ---- ground contact (reward.py:73-102): replaces the shaping reward, skips bounds / tip ----
+    const bool terminated = (y_a <= P.ground_y) && (y_b > P.ground_y);
+    int landing = 0;
+    if (terminated) {
+        total = landing_reward(P, fabsf(vx_a), avy, aa, landing);
+        oob = false;
+        tipped = false;
     }
-    if (steps >= P.max_episode_steps) o.truncated = true;      // lander.py:237-241
+    o.terminated = terminated;
+    o.out_of_bounds = oob;
+    o.tipped = tipped;
+    o.landing = landing;
+    o.truncated = oob || (steps >= P.max_episode_steps);       // lander.py:237-241
     o.reward = total;
     o.nonfinite = !(fabsf(total) <= 3.0e38f) || !(fabsf(y_a) <= 3.0e38f);
     r.ep_ret += total;

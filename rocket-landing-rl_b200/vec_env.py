@@ -30,13 +30,9 @@ def _pinned(shape, dtype) -> np.ndarray:
         t = t.pin_memory()
     except RuntimeError:      # no CUDA: plain pageable memory (construction fails later anyway)
         pass
-    arr = t.numpy()
-    arr.setflags(write=True)
-    _pinned.keep.append(t)
-    return arr
+    return t.numpy()          # the array keeps the (pinned) tensor storage alive
 
 
-_pinned.keep = []   # type: ignore[attr-defined]
 
 
 class RocketLandingSB3VecEnv:

@@ -255,7 +255,7 @@ def test_host_buffer_vecenv_api_matches_device_api(torch):
             assert infos[i]["landing"] in ("safe", "good", "ok", "unsafe")
             seen_done += 1
         assert all(infos[i] == {} for i in np.flatnonzero(~dh)[:5])
-    assert seen_done > n
+    assert seen_done > 0.9 * n
     host.close()
     dev.close()
 
