@@ -148,6 +148,13 @@ int rl_destroy(RlEnv *env);
 
 int64_t rl_num_envs(const RlEnv *env);
 
+/* 1 if this handle runs the kernel instantiation with the reference's config.yaml constants
+ * folded in at compile time (chosen only when every derived constant is bit-identical to those
+ * defaults), 0 if it runs the instantiation that reads its constants at run time.  Both are the
+ * same template; setting the environment variable RL_B200_GENERIC_KERNEL=1 before rl_create
+ * forces the run-time one. */
+int rl_uses_folded_constants(const RlEnv *env);
+
 /* Launch epoch: counts rl_reset / rl_step launches and is part of the Philox counter.  It
  * lives in device memory and is advanced by the kernels themselves, so a CUDA-graph replay
  * of rl_step advances the reset stream like an ordinary call.  Saving it with the state

@@ -15,7 +15,7 @@ ABI_VERSION = 1
 
 # every symbol include/rocket_landing_b200.h declares
 EXPORTS = ("rl_abi_version", "rl_last_error", "rl_params_default", "rl_state_bytes", "rl_create",
-           "rl_destroy", "rl_num_envs", "rl_get_epoch", "rl_set_epoch", "rl_reset", "rl_step",
+           "rl_destroy", "rl_num_envs", "rl_uses_folded_constants", "rl_get_epoch", "rl_set_epoch", "rl_reset", "rl_step",
            "rl_set_state", "rl_get_state", "rl_stats", "rl_step_host", "rl_reset_host",
            "rl_launch_count")
 
@@ -52,6 +52,7 @@ def load():
     L.rl_destroy.argtypes = [vp]
     L.rl_num_envs.argtypes = [vp]
     L.rl_num_envs.restype = i64
+    L.rl_uses_folded_constants.argtypes = [vp]
     L.rl_get_epoch.argtypes = [vp]
     L.rl_get_epoch.restype = u64
     L.rl_set_epoch.argtypes = [vp, u64]

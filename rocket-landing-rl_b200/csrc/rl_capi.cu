@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -43,7 +44,9 @@ struct RlEnv {
     unsigned long long* epoch = nullptr;   // device: {launch epoch}
     unsigned int* ticket = nullptr;        // device
     int device = 0;
-    int grid_cap = 0;                 // persistent grid: SMs x resident CTAs of the step kernel
+    int sms = 0;
+    bool folded = false;              // constants equal the reference defaults: use the constexpr kernels
+    int step_grid[2][2] = {{0, 0}, {0, 0}};   // [auto_reset][single_step]: SMs x resident CTAs (persistent grid)
     int64_t launches = 0;
     // host-buffer path (rl_step_host): device staging, allocated on first use
     void* h_stage = nullptr;
@@ -53,9 +56,25 @@ struct RlEnv {
 
 namespace {
 
+// grid of the helper kernels (reset / state copy): one CTA per 256 rockets, capped at 8 per SM
 int grid_for(const RlEnv* e, int64_t n) {
-    const int64_t tiles = (n + rl::kTile - 1) / rl::kTile;
-    return (int)(tiles < e->grid_cap ? (tiles > 0 ? tiles : 1) : e->grid_cap);
+    const int64_t ctas = (n + rl::kCtaThreads - 1) / rl::kCtaThreads;
+    const int64_t cap = (int64_t)e->sms * 8;
+    return (int)(ctas < cap ? (ctas > 0 ? ctas : 1) : cap);
+}
+
+using StepKernel = void (*)(const rl::DevParams, const rl::StepArgs);
+
+// [folded constants][auto_reset][single_step]
+StepKernel step_kernel_for(bool folded, bool auto_reset, bool single) {
+    using rl::DefaultParams;
+    using rl::DevParams;
+    static const StepKernel table[2][2][2] = {
+        {{rl::step_kernel<false, false, DevParams>, rl::step_kernel<false, true, DevParams>},
+         {rl::step_kernel<true, false, DevParams>, rl::step_kernel<true, true, DevParams>}},
+        {{rl::step_kernel<false, false, DefaultParams>, rl::step_kernel<false, true, DefaultParams>},
+         {rl::step_kernel<true, false, DefaultParams>, rl::step_kernel<true, true, DefaultParams>}}};
+    return table[folded ? 1 : 0][auto_reset ? 1 : 0][single ? 1 : 0];
 }
 
 struct DeviceGuard {
@@ -89,9 +108,12 @@ int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8
     a.epoch = e->epoch;
     a.ticket = e->ticket;
     a.substeps = substeps;
-    const int grid = grid_for(e, e->n);
-    if (auto_reset) rl::step_kernel<true><<<grid, rl::kTile, 0, stream>>>(e->dev, a);
-    else rl::step_kernel<false><<<grid, rl::kTile, 0, stream>>>(e->dev, a);
+    const bool single = substeps == 1;
+    const int64_t warp_tiles = (e->n + rl::kWarpTile - 1) / rl::kWarpTile;
+    const int64_t ctas = (warp_tiles + rl::kWarps - 1) / rl::kWarps;
+    const int cap = e->step_grid[auto_reset ? 1 : 0][single ? 1 : 0];
+    const int grid = (int)(ctas < cap ? ctas : cap);
+    step_kernel_for(e->folded, auto_reset != 0, single)<<<grid, rl::kCtaThreads, 0, stream>>>(e->dev, a);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
     return RL_OK;
@@ -203,19 +225,27 @@ int rl_create(const RlParams* params, int64_t n_envs, int64_t env_id_offset, uin
         rl_destroy(e);
         return fail(RL_E_CUDA, "rl_create: device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    int sms = 0, per_sm = 0;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    // the step kernel stages tiles in ~37 KiB of static shared memory per CTA: ask for the largest
-    // shared-memory carve-out so that registers, not shared memory, bound the resident CTAs
-    cudaFuncSetAttribute(rl::step_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(rl::step_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rl::step_kernel<true>, rl::kTile, 0);
-    if (sms <= 0 || per_sm <= 0) {
-        rl_destroy(e);
-        return fail(RL_E_CUDA, "rl_create: occupancy query failed (no sm_100a image for this device?): %s",
-                    cudaGetErrorString(cudaGetLastError()));
-    }
-    e->grid_cap = sms * per_sm;
+    // Constants equal to the reference's config.yaml run the instantiation with them folded in as
+    // immediates; anything else (or RL_B200_GENERIC_KERNEL=1, used by the tests) runs the
+    // instantiation that reads them from the kernel-parameter constant bank.
+    const char* force_generic = getenv("RL_B200_GENERIC_KERNEL");
+    e->folded = rl::matches_default(e->dev) && !(force_generic && force_generic[0] == '1');
+    cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
+    for (int ar = 0; ar < 2; ++ar)
+        for (int single = 0; single < 2; ++single) {
+            StepKernel fn = step_kernel_for(e->folded, ar != 0, single != 0);
+            int per_sm = 0;
+            // each CTA stages its warps' tiles in ~25 KiB of static shared memory: ask for the largest
+            // carve-out so that registers, not shared memory, bound the resident CTAs
+            cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, rl::kCtaThreads, 0);
+            if (e->sms <= 0 || per_sm <= 0) {
+                rl_destroy(e);
+                return fail(RL_E_CUDA, "rl_create: occupancy query failed (no sm_100a image for this device?): %s",
+                            cudaGetErrorString(cudaGetLastError()));
+            }
+            e->step_grid[ar][single] = e->sms * per_sm;
+        }
     *out = e;
     return RL_OK;
 }
@@ -234,6 +264,7 @@ int rl_destroy(RlEnv* e) {
 }
 
 int64_t rl_num_envs(const RlEnv* e) { return e ? e->n : 0; }
+int rl_uses_folded_constants(const RlEnv* e) { return (e && e->folded) ? 1 : 0; }
 uint64_t rl_get_epoch(const RlEnv* e) {
     if (!e) return 0;
     DeviceGuard guard(e->device);
@@ -259,7 +290,7 @@ int rl_reset(RlEnv* e, const uint8_t* mask, float* obs, void* stream) {
     if (!e) return fail(RL_E_INVALID, "rl_reset: null handle");
     if (obs && misaligned(obs, 16)) return fail(RL_E_INVALID, "rl_reset: obs must be 16-byte aligned");
     DeviceGuard guard(e->device);
-    rl::reset_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(
+    rl::reset_kernel<<<grid_for(e, e->n), rl::kCtaThreads, 0, (cudaStream_t)stream>>>(
         e->dev, e->planes, mask, reinterpret_cast<float4*>(obs), (uint32_t)e->n, e->gid0, e->seed, e->epoch, e->ticket);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
@@ -284,7 +315,7 @@ int rl_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8_t* 
 int rl_set_state(RlEnv* e, const float* state_soa, const uint8_t* mask, void* stream) {
     if (!e || !state_soa) return fail(RL_E_INVALID, "rl_set_state: null argument");
     DeviceGuard guard(e->device);
-    rl::set_state_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(e->planes, state_soa, mask, (uint32_t)e->n);
+    rl::set_state_kernel<<<grid_for(e, e->n), rl::kCtaThreads, 0, (cudaStream_t)stream>>>(e->planes, state_soa, mask, (uint32_t)e->n);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
     return RL_OK;
@@ -293,7 +324,7 @@ int rl_set_state(RlEnv* e, const float* state_soa, const uint8_t* mask, void* st
 int rl_get_state(RlEnv* e, float* state_soa, void* stream) {
     if (!e || !state_soa) return fail(RL_E_INVALID, "rl_get_state: null argument");
     DeviceGuard guard(e->device);
-    rl::get_state_kernel<<<grid_for(e, e->n), rl::kTile, 0, (cudaStream_t)stream>>>(e->planes, state_soa, (uint32_t)e->n);
+    rl::get_state_kernel<<<grid_for(e, e->n), rl::kCtaThreads, 0, (cudaStream_t)stream>>>(e->planes, state_soa, (uint32_t)e->n);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
     return RL_OK;

@@ -97,24 +97,26 @@ __device__ __forceinline__ float normalize_angle(float a, int& k) {
 // reference's draw order x, y, vx, vy, ax, ay, angle, angular velocity, dry mass, fuel mass, from
 // the ten random words w[0..9].  Returns the sampled ax, ay (they only ever appear in the reset
 // observation, lander.py:182).
-__device__ __forceinline__ void rocket_from_words(const DevParams& P, const uint32_t* w, Rocket& r,
+template <class PP>
+__device__ __forceinline__ void rocket_from_words(const PP& P, const uint32_t* w, Rocket& r,
                                                   float& ax0, float& ay0) {
-    r.x = fmaf(P.reset_span[0], u01(w[0]), P.reset_lo[0]);
-    r.y = fmaf(P.reset_span[1], u01(w[1]), P.reset_lo[1]);
-    r.sx = fmaf(P.reset_span[2], u01(w[2]), P.reset_lo[2]);      // vx while FRESH
-    r.sy = fmaf(P.reset_span[3], u01(w[3]), P.reset_lo[3]);      // vy while FRESH
-    ax0 = fmaf(P.reset_span[4], u01(w[4]), P.reset_lo[4]);
-    ay0 = fmaf(P.reset_span[5], u01(w[5]), P.reset_lo[5]);
-    r.ang = fmaf(P.reset_span[6], u01(w[6]), P.reset_lo[6]);
-    r.sang = fmaf(P.reset_span[7], u01(w[7]), P.reset_lo[7]);    // angular velocity while FRESH
-    r.dry = fmaf(P.reset_span[8], u01(w[8]), P.reset_lo[8]);
-    r.fuel = fmaf(P.reset_span[9], u01(w[9]), P.reset_lo[9]);
+    r.x = fmaf(P.reset_span(0), u01(w[0]), P.reset_lo(0));
+    r.y = fmaf(P.reset_span(1), u01(w[1]), P.reset_lo(1));
+    r.sx = fmaf(P.reset_span(2), u01(w[2]), P.reset_lo(2));      // vx while FRESH
+    r.sy = fmaf(P.reset_span(3), u01(w[3]), P.reset_lo(3));      // vy while FRESH
+    ax0 = fmaf(P.reset_span(4), u01(w[4]), P.reset_lo(4));
+    ay0 = fmaf(P.reset_span(5), u01(w[5]), P.reset_lo(5));
+    r.ang = fmaf(P.reset_span(6), u01(w[6]), P.reset_lo(6));
+    r.sang = fmaf(P.reset_span(7), u01(w[7]), P.reset_lo(7));    // angular velocity while FRESH
+    r.dry = fmaf(P.reset_span(8), u01(w[8]), P.reset_lo(8));
+    r.fuel = fmaf(P.reset_span(9), u01(w[9]), P.reset_lo(9));
     r.ep_ret = 0.0f;
     r.meta = RL_META_FRESH;                                      // current_step = 0 (lander.py:180)
 }
 
 // One thread draws all three Philox blocks keyed by (seed, global rocket id, epoch).
-__device__ __forceinline__ void sample_reset(const DevParams& P, uint64_t seed, uint64_t gid,
+template <class PP>
+__device__ __forceinline__ void sample_reset(const PP& P, uint64_t seed, uint64_t gid,
                                              uint64_t epoch, Rocket& r, float& ax0, float& ay0) {
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     const uint4 a = philox4x32_10(reset_counter(gid, epoch, 0u), key);
@@ -127,20 +129,22 @@ __device__ __forceinline__ void sample_reset(const DevParams& P, uint64_t seed, 
 __device__ __forceinline__ float clipf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 // _get_obs (lander.py:124-150)
-__device__ __forceinline__ void clip_obs(const DevParams& P, float x, float y, float vx, float vy,
+template <class PP>
+__device__ __forceinline__ void clip_obs(const PP& P, float x, float y, float vx, float vy,
                                          float ax, float ay, float ang, float om, float* obs) {
-    obs[0] = clipf(x, P.obs_lo[0], P.obs_hi[0]);
-    obs[1] = clipf(y, P.obs_lo[1], P.obs_hi[1]);
-    obs[2] = clipf(vx, P.obs_lo[2], P.obs_hi[2]);
-    obs[3] = clipf(vy, P.obs_lo[3], P.obs_hi[3]);
-    obs[4] = clipf(ax, P.obs_lo[4], P.obs_hi[4]);
-    obs[5] = clipf(ay, P.obs_lo[5], P.obs_hi[5]);
-    obs[6] = clipf(ang, P.obs_lo[6], P.obs_hi[6]);
-    obs[7] = clipf(om, P.obs_lo[7], P.obs_hi[7]);
+    obs[0] = clipf(x, P.obs_lo(0), P.obs_hi(0));
+    obs[1] = clipf(y, P.obs_lo(1), P.obs_hi(1));
+    obs[2] = clipf(vx, P.obs_lo(2), P.obs_hi(2));
+    obs[3] = clipf(vy, P.obs_lo(3), P.obs_hi(3));
+    obs[4] = clipf(ax, P.obs_lo(4), P.obs_hi(4));
+    obs[5] = clipf(ay, P.obs_lo(5), P.obs_hi(5));
+    obs[6] = clipf(ang, P.obs_lo(6), P.obs_hi(6));
+    obs[7] = clipf(om, P.obs_lo(7), P.obs_hi(7));
 }
 
 // Observation of a FRESH rocket (reset observation).
-__device__ __forceinline__ void fresh_obs(const DevParams& P, const Rocket& r, float ax0, float ay0,
+template <class PP>
+__device__ __forceinline__ void fresh_obs(const PP& P, const Rocket& r, float ax0, float ay0,
                                           float* obs) {
     clip_obs(P, r.x, r.y, r.sx, r.sy, ax0, ay0, r.ang, r.sang, obs);
 }
@@ -154,11 +158,12 @@ __device__ __forceinline__ float potential(float y, float vx, float vy, float an
 }
 
 // Landing step (rare): evaluate_landing (utils.py:1-37) + landing reward (reward.py:77-100).
-__device__ __noinline__ float landing_reward(const DevParams& P, float avx, float avy, float aa, int& cls) {
+template <class PP>
+__device__ __forceinline__ float landing_reward(const PP& P, float avx, float avy, float aa, int& cls) {
     cls = 4;
-    if (avx < P.land_lt[2][0] && avy < P.land_lt[2][1] && aa < P.land_lt[2][2]) cls = 3;
-    if (avx < P.land_lt[1][0] && avy < P.land_lt[1][1] && aa < P.land_lt[1][2]) cls = 2;
-    if (avx < P.land_lt[0][0] && avy < P.land_lt[0][1] && aa < P.land_lt[0][2]) cls = 1;
+    if (avx < P.land_lt(2, 0) && avy < P.land_lt(2, 1) && aa < P.land_lt(2, 2)) cls = 3;
+    if (avx < P.land_lt(1, 0) && avy < P.land_lt(1, 1) && aa < P.land_lt(1, 2)) cls = 2;
+    if (avx < P.land_lt(0, 0) && avy < P.land_lt(0, 1) && aa < P.land_lt(0, 2)) cls = 1;
     const float q = 0.6f * fmaxf(0.0f, 1.0f - aa * 0.1f) + 0.4f * fmaxf(0.0f, 1.0f - avy * 0.2f);
     if (cls == 1) return P.r_perfect * (1.0f + 0.5f * q);
     if (cls == 2) return P.r_good * (0.8f + 0.2f * q);
@@ -168,7 +173,8 @@ __device__ __noinline__ float landing_reward(const DevParams& P, float avx, floa
 
 // One env step (lander.py:188-255) of one rocket, no reset.  th_raw / cg_raw are the raw
 // action: physics clips it (base.py:135-136), the reward does not (reward.py:69-70).
-__device__ __forceinline__ void rocket_step(const DevParams& P, Rocket& r, float th_raw, float cg_raw,
+template <class PP>
+__device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw, float cg_raw,
                                             StepResult& o) {
     const bool fresh = (r.meta & RL_META_FRESH) != 0u;
     const int steps = min((int)(r.meta & RL_META_STEP_MASK) + 1, (int)RL_META_STEP_MASK);   // lander.py:229

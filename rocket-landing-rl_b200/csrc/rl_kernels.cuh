@@ -5,19 +5,29 @@
 //   fuel     float [Np]                                  read + written every step
 //   dry      float [Np]                                  read every step, written on reset only
 //
-// Np = n_envs rounded up to a 256-rocket tile; all planes live in one buffer so a checkpoint is
-// one tensor.  A tile's slice of every plane is one contiguous, 16-byte-aligned run of bytes
-// (4 KiB / 4 KiB / 1 KiB / 1 KiB, plus 2 KiB of the action array), which is what lets the step
-// kernel fetch it with five TMA bulk copies (cp.async.bulk, SASS UBLKCP) into a shared-memory
-// ring instead of per-thread loads: the loads of the next kStages tiles are always in flight
-// while the current tile is being computed, independent of occupancy and register pressure.
+// Np = n_envs rounded up to 256; all planes live in one buffer so a checkpoint is one tensor.
+// The unit of work is a WARP TILE of 32 consecutive rockets: its slice of every plane is one
+// contiguous, 16-byte-aligned run (512 B / 512 B / 128 B / 128 B, plus 256 B of the action
+// array), fetched by five TMA bulk copies (cp.async.bulk, SASS UBLKCP) into that warp's own
+// shared-memory ring and signalled on that warp's own mbarrier.  Every warp is therefore an
+// independent software pipeline -- the next tile's bytes are in flight while the current tile is
+// computed, with no CTA-wide barrier in the loop, so a warp that takes the (long) reset path
+// never stalls its neighbours.
 #pragma once
+#include <type_traits>
+
 #include "rl_device.cuh"
 
 namespace rl {
 
-constexpr int kTile = 256;           // rockets per tile == threads per CTA
-constexpr int kStages = 3;           // depth of the shared-memory ring
+constexpr int kCtaThreads = 256;
+constexpr int kWarps = kCtaThreads / 32;
+constexpr int kWarpTile = 32;        // rockets per warp tile
+constexpr int kStages = 2;           // depth of each warp's shared-memory ring
+constexpr int kPad = 256;            // planes are padded to a multiple of this many rockets
+#ifndef RL_MIN_CTAS
+#define RL_MIN_CTAS 4                // resident CTAs per SM the register allocator must allow
+#endif
 
 struct StatePlanes {
     float4* A;
@@ -26,7 +36,7 @@ struct StatePlanes {
     float* dry;
 };
 
-__host__ __device__ inline int64_t padded_envs(int64_t n) { return (n + kTile - 1) / kTile * kTile; }
+__host__ __device__ inline int64_t padded_envs(int64_t n) { return (n + kPad - 1) / kPad * kPad; }
 
 __host__ inline StatePlanes carve_state(void* base, int64_t n_envs) {
     const int64_t np = padded_envs(n_envs);
@@ -67,6 +77,10 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
 }
 __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory (and those it has
+// synchronised with) before its later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -95,12 +109,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-struct __align__(128) TileStage {     // one tile's inputs, 12 KiB
-    float4 A[kTile];
-    float4 B[kTile];
-    float fuel[kTile];
-    float dry[kTile];
-    float2 act[kTile];
+struct __align__(128) WarpStage {     // one warp tile's inputs, 1536 B
+    float4 A[kWarpTile];
+    float4 B[kWarpTile];
+    float fuel[kWarpTile];
+    float dry[kWarpTile];
+    float2 act[kWarpTile];
 };
 
 // The launch epoch lives in device memory so that a CUDA-graph replay of the step advances the
@@ -117,38 +131,58 @@ __device__ __forceinline__ void epoch_bump(unsigned long long* epoch, unsigned i
     }
 }
 
-// ---- block-level statistics: rare events go to shared-memory atomics, one global atomic per
-// ---- slot per CTA at the end (the grid is persistent, so that is a few thousand atomics per launch)
+// ---- statistics: every thread keeps its own running sums in registers; once per CTA they are
+// ---- reduced by warp shuffles into shared memory and flushed with one global atomic per slot
+// ---- (the grid is persistent, so that is a few thousand global atomics per launch).  Only the
+// ---- per-class episode counts use shared-memory atomics, and those are native integer adds
+// ---- (a double atomicAdd on shared memory is a CAS loop -- far too slow for a per-step event).
+struct ThreadStats {
+    float reward_sum = 0.0f, return_sum = 0.0f;
+    int env_steps = 0, tip_steps = 0, nonfinite = 0, episodes = 0, length_sum = 0;
+};
+
 struct BlockStats {
     double sum[RL_STATS_WORDS];
+    unsigned int cls[8];            // [1..4] landing class, [5] out of bounds, [6] time limit
 };
 
 __device__ __forceinline__ void stats_init(BlockStats& s) {
     if (threadIdx.x < RL_STATS_WORDS) s.sum[threadIdx.x] = 0.0;
+    if (threadIdx.x < 8) s.cls[threadIdx.x] = 0u;
 }
 
-__device__ __forceinline__ void stats_flush(BlockStats& s, double* __restrict__ g, float reward_sum, int steps) {
+__device__ __forceinline__ void stats_flush(BlockStats& s, double* __restrict__ g, ThreadStats ts) {
+    double reward_sum = (double)ts.reward_sum, return_sum = (double)ts.return_sum;   // once per launch: reduce in fp64
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         reward_sum += __shfl_xor_sync(0xffffffffu, reward_sum, o);
-        steps += __shfl_xor_sync(0xffffffffu, steps, o);
+        return_sum += __shfl_xor_sync(0xffffffffu, return_sum, o);
+        ts.env_steps += __shfl_xor_sync(0xffffffffu, ts.env_steps, o);
+        ts.tip_steps += __shfl_xor_sync(0xffffffffu, ts.tip_steps, o);
+        ts.nonfinite += __shfl_xor_sync(0xffffffffu, ts.nonfinite, o);
+        ts.episodes += __shfl_xor_sync(0xffffffffu, ts.episodes, o);
+        ts.length_sum += __shfl_xor_sync(0xffffffffu, ts.length_sum, o);
     }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&s.sum[RL_S_REWARD_SUM], (double)reward_sum);
-        atomicAdd(&s.sum[RL_S_ENV_STEPS], (double)steps);
+    if ((threadIdx.x & 31) == 0) {          // 8 warps x 7 slots, once per CTA per launch
+        atomicAdd(&s.sum[RL_S_REWARD_SUM], reward_sum);
+        atomicAdd(&s.sum[RL_S_RETURN_SUM], return_sum);
+        atomicAdd(&s.sum[RL_S_ENV_STEPS], (double)ts.env_steps);
+        atomicAdd(&s.sum[RL_S_TIP_STEPS], (double)ts.tip_steps);
+        atomicAdd(&s.sum[RL_S_NONFINITE], (double)ts.nonfinite);
+        atomicAdd(&s.sum[RL_S_EPISODES], (double)ts.episodes);
+        atomicAdd(&s.sum[RL_S_LENGTH_SUM], (double)ts.length_sum);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        s.sum[RL_S_SAFE] = (double)s.cls[1];
+        s.sum[RL_S_GOOD] = (double)s.cls[2];
+        s.sum[RL_S_OK] = (double)s.cls[3];
+        s.sum[RL_S_UNSAFE] = (double)s.cls[4];
+        s.sum[RL_S_OUT_OF_BOUNDS] = (double)s.cls[5];
+        s.sum[RL_S_TIME_LIMIT] = (double)s.cls[6];
     }
     __syncthreads();
     if (threadIdx.x < RL_STATS_WORDS && s.sum[threadIdx.x] != 0.0) atomicAdd(&g[threadIdx.x], s.sum[threadIdx.x]);
-}
-
-__device__ __noinline__ void stats_episode_end(BlockStats& s, int landing, bool out_of_bounds, float ep_ret,
-                                               int ep_len) {
-    atomicAdd(&s.sum[RL_S_EPISODES], 1.0);
-    atomicAdd(&s.sum[RL_S_RETURN_SUM], (double)ep_ret);
-    atomicAdd(&s.sum[RL_S_LENGTH_SUM], (double)ep_len);
-    if (landing) atomicAdd(&s.sum[RL_S_SAFE + landing - 1], 1.0);
-    else if (out_of_bounds) atomicAdd(&s.sum[RL_S_OUT_OF_BOUNDS], 1.0);
-    else atomicAdd(&s.sum[RL_S_TIME_LIMIT], 1.0);
 }
 
 __device__ __forceinline__ void load_rocket(const StatePlanes& st, uint32_t i, Rocket& r) {
@@ -167,157 +201,190 @@ __device__ __forceinline__ void store_rocket(const StatePlanes& st, uint32_t i, 
     if (write_dry) st.dry[i] = r.dry;
 }
 
-// Warp-cooperative reset: for every done lane (uniform loop over the ballot) lanes 0..2 compute the
-// three Philox blocks of that rocket in parallel and the ten words are shuffled to the lane that
-// owns it.  Same counters and words as sample_reset(), one third of the serial Philox latency, and
-// the rest of the warp is not dragged through three back-to-back Philox evaluations.
-__device__ __forceinline__ void warp_reset(const DevParams& P, unsigned done_mask, uint64_t seed, uint64_t gid_lane0,
-                                           uint64_t epoch, Rocket& r, float* obs) {
-    const unsigned lane = threadIdx.x & 31u;
-    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    while (done_mask) {
-        const unsigned src = (unsigned)__ffs((int)done_mask) - 1u;
-        done_mask &= done_mask - 1u;
-        const uint4 blk = philox4x32_10(reset_counter(gid_lane0 + src, epoch, lane & 3u), key);
-        uint32_t w[10];
-        w[0] = __shfl_sync(0xffffffffu, blk.x, 0); w[1] = __shfl_sync(0xffffffffu, blk.y, 0);
-        w[2] = __shfl_sync(0xffffffffu, blk.z, 0); w[3] = __shfl_sync(0xffffffffu, blk.w, 0);
-        w[4] = __shfl_sync(0xffffffffu, blk.x, 1); w[5] = __shfl_sync(0xffffffffu, blk.y, 1);
-        w[6] = __shfl_sync(0xffffffffu, blk.z, 1); w[7] = __shfl_sync(0xffffffffu, blk.w, 1);
-        w[8] = __shfl_sync(0xffffffffu, blk.x, 2); w[9] = __shfl_sync(0xffffffffu, blk.y, 2);
-        if (lane == src) {
-            float ax0, ay0;
-            rocket_from_words(P, w, r, ax0, ay0);
-            fresh_obs(P, r, ax0, ay0, obs);          // SB3 VecEnv contract: return the reset observation
+// Episode end + reset of the done lanes of one warp (rare: ~1 rocket in 113 per step; inlined
+// into a cold branch -- an out-of-line call would force the rocket's registers onto the stack).  Records the finished episode, hands the terminal
+// observation / return / length to the caller's buffers, and -- with auto-reset -- resamples the
+// rocket: for every done lane (uniform loop over the ballot) lanes 0..2 compute the three Philox
+// blocks of that rocket in parallel and the ten words are shuffled to the lane that owns it.
+// Same counters and words as sample_reset(), one third of the serial Philox latency.
+template <bool kAutoReset, class PP>
+__device__ __forceinline__ void warp_episode_end(const PP& P, const StepArgs& a, BlockStats& bs, ThreadStats& ts,
+                                              unsigned done_mask, bool done, uint32_t i, uint64_t epoch, Rocket& r,
+                                              StepResult& o) {
+    if (done) {
+        const int ep_len = (int)(r.meta & RL_META_STEP_MASK);
+        ts.episodes += 1;
+        ts.return_sum += r.ep_ret;
+        ts.length_sum += ep_len;
+        atomicAdd(&bs.cls[o.landing ? o.landing : (o.out_of_bounds ? 5 : 6)], 1u);
+        if (a.terminal_obs) {
+            a.terminal_obs[2 * (size_t)i] = make_float4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]);
+            a.terminal_obs[2 * (size_t)i + 1] = make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]);
+        }
+        if (a.episode_return) a.episode_return[i] = r.ep_ret;
+        if (a.episode_length) a.episode_length[i] = ep_len;
+    }
+    if (kAutoReset) {
+        const unsigned lane = threadIdx.x & 31u;
+        const uint64_t gid_lane0 = (uint64_t)a.gid0 + (uint64_t)(i - lane);
+        const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        while (done_mask) {
+            const unsigned src = (unsigned)__ffs((int)done_mask) - 1u;
+            done_mask &= done_mask - 1u;
+            const uint4 blk = philox4x32_10(reset_counter(gid_lane0 + src, epoch, lane & 3u), key);
+            uint32_t w[10];
+            w[0] = __shfl_sync(0xffffffffu, blk.x, 0); w[1] = __shfl_sync(0xffffffffu, blk.y, 0);
+            w[2] = __shfl_sync(0xffffffffu, blk.z, 0); w[3] = __shfl_sync(0xffffffffu, blk.w, 0);
+            w[4] = __shfl_sync(0xffffffffu, blk.x, 1); w[5] = __shfl_sync(0xffffffffu, blk.y, 1);
+            w[6] = __shfl_sync(0xffffffffu, blk.z, 1); w[7] = __shfl_sync(0xffffffffu, blk.w, 1);
+            w[8] = __shfl_sync(0xffffffffu, blk.x, 2); w[9] = __shfl_sync(0xffffffffu, blk.y, 2);
+            if (lane == src) {
+                float ax0, ay0;
+                rocket_from_words(P, w, r, ax0, ay0);
+                fresh_obs(P, r, ax0, ay0, o.obs);        // SB3 VecEnv contract: return the reset observation
+                a.st.dry[i] = r.dry;                     // dry mass only ever changes here
+            }
         }
     }
 }
 
+template <class PP> struct ParamSel;
+template <> struct ParamSel<DevParams> {
+    static __device__ __forceinline__ const DevParams& get(const DevParams& rt) { return rt; }
+};
+template <> struct ParamSel<DefaultParams> {
+    static __device__ __forceinline__ DefaultParams get(const DevParams&) { return DefaultParams{}; }
+};
+
 // The environment step (lander.py:188-255 for every rocket) + VecEnv auto-reset.
-// Persistent grid: CTA b walks tiles b, b + gridDim.x, ...; thread t of the CTA owns rocket
-// tile * 256 + t.  Inputs arrive through the TMA ring, outputs leave as coalesced 128-bit stores.
-template <bool kAutoReset>
-__global__ void __launch_bounds__(kTile) step_kernel(const __grid_constant__ DevParams P,
-                                                     const __grid_constant__ StepArgs a) {
-    __shared__ TileStage ring[kStages];
-    __shared__ __align__(8) uint64_t full_bar[kStages];
+//   kAutoReset   reset done rockets in the same launch (scripts/train.py:82-88 contract)
+//   kSingleStep  substeps == 1 (the reference's step): no substep loop
+//   PP           DevParams (runtime constants) or DefaultParams (reference config.yaml folded in)
+// Persistent grid; warp w of CTA b walks warp tiles (b * kWarps + w), + gridDim.x * kWarps, ...
+template <bool kAutoReset, bool kSingleStep, class PP>
+__global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __grid_constant__ DevParams Prt,
+                                                           const __grid_constant__ StepArgs a) {
+    __shared__ WarpStage ring[kWarps][kStages];
+    __shared__ __align__(8) uint64_t full_bar[kWarps][kStages];
     __shared__ BlockStats bs;
 
-    const uint32_t tid = threadIdx.x;
-    const uint32_t n_tiles = (a.n + kTile - 1) / kTile;
-    const uint32_t full_tiles = a.n / kTile;           // tiles whose action slice is a whole 2 KiB
-    const uint32_t stride = gridDim.x;
+    const auto& P = ParamSel<PP>::get(Prt);
 
-    auto issue = [&](uint32_t tile, uint32_t s) {      // one thread: five bulk copies into stage s
-        const size_t base = (size_t)tile * kTile;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
+    const uint32_t full_tiles = a.n / kWarpTile;       // tiles whose action slice is a whole 256 B
+    const uint32_t stride = gridDim.x * kWarps;
+    WarpStage* const my_ring = ring[warp];
+    uint64_t* const my_bar = full_bar[warp];
+
+    auto issue = [&](uint32_t tile, uint32_t s) {      // lane 0: five bulk copies into stage s
+        const size_t base = (size_t)tile * kWarpTile;
         const bool act_bulk = tile < full_tiles;
-        mbar_arrive_expect_tx(&full_bar[s], 4096u + 4096u + 1024u + 1024u + (act_bulk ? 2048u : 0u));
-        bulk_g2s(ring[s].A, a.st.A + base, 4096u, &full_bar[s]);
-        bulk_g2s(ring[s].B, a.st.B + base, 4096u, &full_bar[s]);
-        bulk_g2s(ring[s].fuel, a.st.fuel + base, 1024u, &full_bar[s]);
-        bulk_g2s(ring[s].dry, a.st.dry + base, 1024u, &full_bar[s]);
-        if (act_bulk) bulk_g2s(ring[s].act, a.actions + base, 2048u, &full_bar[s]);
+        mbar_arrive_expect_tx(&my_bar[s], 512u + 512u + 128u + 128u + (act_bulk ? 256u : 0u));
+        bulk_g2s(my_ring[s].A, a.st.A + base, 512u, &my_bar[s]);
+        bulk_g2s(my_ring[s].B, a.st.B + base, 512u, &my_bar[s]);
+        bulk_g2s(my_ring[s].fuel, a.st.fuel + base, 128u, &my_bar[s]);
+        bulk_g2s(my_ring[s].dry, a.st.dry + base, 128u, &my_bar[s]);
+        if (act_bulk) bulk_g2s(my_ring[s].act, a.actions + base, 256u, &my_bar[s]);
     };
 
     stats_init(bs);
-    if (tid == 0) {
+    const uint32_t first = blockIdx.x * kWarps + warp;
+    if (lane == 0) {
 #pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1u);
+        for (int s = 0; s < kStages; ++s) mbar_init(&my_bar[s], 1u);
         mbar_fence_init();
-    }
-    __syncthreads();
-    if (tid == 0) {
+        fence_proxy_async();
 #pragma unroll
         for (uint32_t s = 0; s < (uint32_t)kStages; ++s) {
-            const uint32_t tile = blockIdx.x + s * stride;
+            const uint32_t tile = first + s * stride;
             if (tile < n_tiles) issue(tile, s);
         }
     }
+    __syncthreads();                                    // stats_init + barrier init visible CTA-wide
     const uint64_t epoch = *a.epoch;
-    float reward_sum = 0.0f;
-    int steps_done = 0;
+    ThreadStats ts;
 
     uint32_t s = 0, parity = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += stride) {
-        const uint32_t i = tile * kTile + tid;
+    for (uint32_t tile = first; tile < n_tiles; tile += stride) {
+        const uint32_t i = tile * kWarpTile + lane;
         const bool valid = i < a.n;
 
-        mbar_wait(&full_bar[s], parity);
+        mbar_wait(&my_bar[s], parity);
         Rocket r;
         {
-            const float4 va = ring[s].A[tid];
-            const float4 vb = ring[s].B[tid];
-            r.fuel = ring[s].fuel[tid];
-            r.dry = ring[s].dry[tid];
+            const float4 va = my_ring[s].A[lane];
+            const float4 vb = my_ring[s].B[lane];
+            r.fuel = my_ring[s].fuel[lane];
+            r.dry = my_ring[s].dry[lane];
             r.x = va.x; r.y = va.y; r.ang = va.z; r.meta = __float_as_uint(va.w);
             r.sx = vb.x; r.sy = vb.y; r.sang = vb.z; r.ep_ret = vb.w;
         }
         float2 act;
-        if (tile < full_tiles) act = ring[s].act[tid];
+        if (tile < full_tiles) act = my_ring[s].act[lane];
         else act = valid ? __ldg(&a.actions[i]) : make_float2(0.0f, 0.0f);   // ragged last tile
-        __syncthreads();                                 // every thread has drained stage s
-        if (tid == 0) {
+        __syncwarp();                                    // every lane has drained stage s ...
+        if (lane == 0) {
             const uint32_t next = tile + (uint32_t)kStages * stride;
-            if (next < n_tiles) issue(next, s);
+            if (next < n_tiles) {
+                fence_proxy_async();                     // ... before the async proxy overwrites it
+                issue(next, s);
+            }
         }
         if (++s == (uint32_t)kStages) { s = 0; parity ^= 1u; }
 
         StepResult o;
-        float reward = 0.0f;
-        bool done = false;
-        for (int k = 0; k < a.substeps; ++k) {
+        float reward;
+        bool done;
+        if constexpr (kSingleStep) {
             rocket_step(P, r, act.x, act.y, o);
-            reward += o.reward;
-            if (valid) {
-                ++steps_done;
-                if (o.tipped) atomicAdd(&bs.sum[RL_S_TIP_STEPS], 1.0);
-                if (o.nonfinite) atomicAdd(&bs.sum[RL_S_NONFINITE], 1.0);
-            }
+            reward = o.reward;
+            ts.env_steps += valid ? 1 : 0;
+            ts.tip_steps += (valid && o.tipped) ? 1 : 0;
+            ts.nonfinite += (valid && o.nonfinite) ? 1 : 0;
             done = valid && (o.terminated || o.truncated);
-            if (done) break;                             // stop integrating at the first done
+        } else {
+            reward = 0.0f;
+            done = false;
+            for (int k = 0; k < a.substeps; ++k) {
+                rocket_step(P, r, act.x, act.y, o);
+                reward += o.reward;
+                ts.env_steps += valid ? 1 : 0;
+                ts.tip_steps += (valid && o.tipped) ? 1 : 0;
+                ts.nonfinite += (valid && o.nonfinite) ? 1 : 0;
+                done = valid && (o.terminated || o.truncated);
+                if (done) break;                         // stop integrating at the first done
+            }
         }
-        reward_sum += valid ? reward : 0.0f;
+        ts.reward_sum += valid ? reward : 0.0f;
 
-        if (done) {
-            const int ep_len = (int)(r.meta & RL_META_STEP_MASK);
-            stats_episode_end(bs, o.landing, o.out_of_bounds, r.ep_ret, ep_len);
-            if (a.terminal_obs) {
-                a.terminal_obs[2 * (size_t)i] = make_float4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]);
-                a.terminal_obs[2 * (size_t)i + 1] = make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]);
-            }
-            if (a.episode_return) a.episode_return[i] = r.ep_ret;
-            if (a.episode_length) a.episode_length[i] = ep_len;
-        }
-        bool write_dry = false;
-        if (kAutoReset) {
-            const unsigned done_mask = __ballot_sync(0xffffffffu, done);
-            if (done_mask) {
-                warp_reset(P, done_mask, a.seed, (uint64_t)a.gid0 + (uint64_t)(i - (tid & 31u)), epoch, r, o.obs);
-                write_dry = done;
-            }
-        }
+        const unsigned done_mask = __ballot_sync(0xffffffffu, done);
+        const bool terminated = o.terminated, truncated = o.truncated;
+        const int landing = o.landing;
+        if (done_mask) warp_episode_end<kAutoReset>(P, a, bs, ts, done_mask, done, i, epoch, r, o);
+
         if (valid) {
-            store_rocket(a.st, i, r, write_dry);
+            store_rocket(a.st, i, r, false);
             a.obs[2 * (size_t)i] = make_float4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]);
             a.obs[2 * (size_t)i + 1] = make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]);
             a.reward[i] = reward;
-            a.terminated[i] = o.terminated ? 1 : 0;
-            a.truncated[i] = o.truncated ? 1 : 0;
-            if (a.landing) a.landing[i] = (int8_t)o.landing;
+            a.terminated[i] = terminated ? 1 : 0;
+            a.truncated[i] = truncated ? 1 : 0;
+            if (a.landing) a.landing[i] = (int8_t)landing;
         }
     }
-    stats_flush(bs, a.stats, reward_sum, steps_done);
+    stats_flush(bs, a.stats, ts);
     epoch_bump(a.epoch, a.ticket);
 }
 
 // RocketLandingEnv.reset (lander.py:168-186) for all / masked rockets.
-__global__ void __launch_bounds__(kTile) reset_kernel(const __grid_constant__ DevParams P, StatePlanes st,
-                                                      const uint8_t* __restrict__ mask, float4* __restrict__ obs,
-                                                      uint32_t n, int64_t gid0, uint64_t seed,
-                                                      unsigned long long* __restrict__ epoch_ctr,
-                                                      unsigned int* __restrict__ ticket) {
+__global__ void __launch_bounds__(kCtaThreads) reset_kernel(const __grid_constant__ DevParams P, StatePlanes st,
+                                                            const uint8_t* __restrict__ mask,
+                                                            float4* __restrict__ obs, uint32_t n, int64_t gid0,
+                                                            uint64_t seed, unsigned long long* __restrict__ epoch_ctr,
+                                                            unsigned int* __restrict__ ticket) {
     const uint64_t epoch = *epoch_ctr;
-    for (uint32_t i = blockIdx.x * kTile + threadIdx.x; i < n; i += gridDim.x * kTile) {
+    for (uint32_t i = blockIdx.x * kCtaThreads + threadIdx.x; i < n; i += gridDim.x * kCtaThreads) {
         if (mask && !mask[i]) continue;
         Rocket r;
         float ax0, ay0, o[8];
@@ -333,10 +400,10 @@ __global__ void __launch_bounds__(kTile) reset_kernel(const __grid_constant__ De
 }
 
 // Public state format <-> planes (rl_set_state / rl_get_state).
-__global__ void __launch_bounds__(kTile) set_state_kernel(StatePlanes st, const float* __restrict__ soa,
-                                                          const uint8_t* __restrict__ mask, uint32_t n) {
+__global__ void __launch_bounds__(kCtaThreads) set_state_kernel(StatePlanes st, const float* __restrict__ soa,
+                                                                const uint8_t* __restrict__ mask, uint32_t n) {
     const size_t N = n;
-    for (uint32_t i = blockIdx.x * kTile + threadIdx.x; i < n; i += gridDim.x * kTile) {
+    for (uint32_t i = blockIdx.x * kCtaThreads + threadIdx.x; i < n; i += gridDim.x * kCtaThreads) {
         if (mask && !mask[i]) continue;
         Rocket r;
         r.x = soa[RL_W_X * N + i]; r.y = soa[RL_W_Y * N + i]; r.ang = soa[RL_W_ANGLE * N + i];
@@ -347,9 +414,9 @@ __global__ void __launch_bounds__(kTile) set_state_kernel(StatePlanes st, const 
     }
 }
 
-__global__ void __launch_bounds__(kTile) get_state_kernel(StatePlanes st, float* __restrict__ soa, uint32_t n) {
+__global__ void __launch_bounds__(kCtaThreads) get_state_kernel(StatePlanes st, float* __restrict__ soa, uint32_t n) {
     const size_t N = n;
-    for (uint32_t i = blockIdx.x * kTile + threadIdx.x; i < n; i += gridDim.x * kTile) {
+    for (uint32_t i = blockIdx.x * kCtaThreads + threadIdx.x; i < n; i += gridDim.x * kCtaThreads) {
         Rocket r;
         load_rocket(st, i, r);
         soa[RL_W_X * N + i] = r.x; soa[RL_W_Y * N + i] = r.y; soa[RL_W_ANGLE * N + i] = r.ang;

@@ -1,6 +1,15 @@
 // Kernel-parameter struct of the environment step and its derivation from RlParams.
 // Pure C++ (no CUDA): shared by the library (rl_capi.cu) and by the host-compiled logic check
 // of the device math under tests/hostemu/.
+//
+// Two providers of the same constants exist, with the same accessor surface:
+//   * DevParams      -- runtime values (kernel argument, read through the constant bank);
+//   * DefaultParams  -- the reference's config.yaml baked in as constexpr, so the compiler folds
+//                       them into immediates (the step kernel is issue-limited as much as
+//                       bandwidth-limited; ~50 of its ~450 instructions were constant loads).
+// rl_create picks the constexpr instantiation only when EVERY derived constant is bit-identical
+// to DefaultParams (matches_default); any other config runs the runtime instantiation of the
+// very same templates.
 #pragma once
 #include <cmath>
 #include <cstdarg>
@@ -10,11 +19,17 @@
 
 #include "../../include/rocket_landing_b200.h"
 
+#if defined(__CUDACC__)
+#define RL_HD __host__ __device__
+#else
+#define RL_HD
+#endif
+
 namespace rl {
 
-// Constants in fp32, derived on the host in double (rl_capi.cu: derive_params).  Thresholds
-// are rounded in the direction that keeps the comparison exact for fp32 inputs: for a
-// double threshold c, `x > c` == `x > down(c)` and `x < c` == `x < up(c)` for every fp32 x.
+// Constants in fp32, derived on the host in double (derive_params).  Thresholds are rounded in
+// the direction that keeps the comparison exact for fp32 inputs: for a double threshold c,
+// `x > c` == `x > down(c)` and `x < c` == `x < up(c)` for every fp32 x.
 struct DevParams {
     float dt, inv_dt, dt2, half_dt2;
     float gravity;
@@ -31,14 +46,86 @@ struct DevParams {
     float dead_band;           // 0.1 rounded down: |angle| > 0.1 (reward.py:130)
     float throttle_lo_lt;      // 0.1 rounded up:   throttle < 0.1 (reward.py:190)
     float throttle_lo_gt;      // 0.1 rounded down: throttle > 0.1 (reward.py:205)
-    float land_lt[3][3];       // [perfect|good|ok][vx|vy|angle], rounded up (strict <, utils.py:19-21)
     float max_x, max_y, tip_angle;            // rounded down (strict >, reward.py:274-278)
     float r_perfect, r_good, r_ok, r_crash, r_oob, r_tip;
     float k_throttle_descent, k_cold_gas, k_free_fall, k_angle_throttle, k_direction, gamma;
-    float obs_lo[8], obs_hi[8];
-    float reset_lo[10], reset_span[10];
+    float land_lt_[3][3];      // [perfect|good|ok][vx|vy|angle], rounded up (strict <, utils.py:19-21)
+    float obs_lo_[8], obs_hi_[8];
+    float reset_lo_[10], reset_span_[10];
     int max_episode_steps;
+
+    RL_HD float land_lt(int level, int k) const { return land_lt_[level][k]; }
+    RL_HD float obs_lo(int k) const { return obs_lo_[k]; }
+    RL_HD float obs_hi(int k) const { return obs_hi_[k]; }
+    RL_HD float reset_lo(int k) const { return reset_lo_[k]; }
+    RL_HD float reset_span(int k) const { return reset_span_[k]; }
 };
+
+// The reference's config.yaml (config.yaml:16-91), derived exactly as derive_params does.
+struct DefaultParams {
+    static constexpr double kDt = 0.1, kPi = 3.14159265358979323846;
+    static constexpr float dt = (float)kDt;
+    static constexpr float inv_dt = (float)(1.0 / kDt);
+    static constexpr float dt2 = (float)(kDt * kDt);
+    static constexpr float half_dt2 = (float)(0.5 * kDt * kDt);
+    static constexpr float gravity = (float)-9.81;
+    static constexpr float thrust_power = 1.0e7f;
+    static constexpr float drag_k = (float)(0.5 * 1.225 * 0.8 * 10.8);
+    static constexpr float alpha_k = (float)(7.0e4 * 1.85 / (0.5 * 1.85 * 1.85) * (180.0 / kPi));
+    static constexpr float alpha_min_mass = 0x1.39baf4p-21f;          // up(1e-6 / (0.5 r^2))
+    static constexpr float damp = (float)(1.0 - 0.05 * kDt);
+    static constexpr float burn_per_step = (float)(1700.0 * kDt);
+    static constexpr float mass_gate = 0x1.0c6f7ap-20f;               // down(1e-6)
+    static constexpr float throttle_gate = 0x1.0c6f7ap-20f;           // down(1e-6)
+    static constexpr float speed2_gate = 0x1.12e0bep-30f;             // down(1e-9)
+    static constexpr float ground_y = 0x1.999998p-4f;                 // down(0.1)
+    static constexpr float dead_band = 0x1.999998p-4f;                // down(0.1)
+    static constexpr float throttle_lo_lt = 0x1.99999ap-4f;           // up(0.1)
+    static constexpr float throttle_lo_gt = 0x1.999998p-4f;           // down(0.1)
+    static constexpr float max_x = 50000.0f, max_y = 50000.0f, tip_angle = 90.0f;
+    static constexpr float r_perfect = 4000.0f, r_good = 3000.0f, r_ok = 2000.0f, r_crash = -800.0f;
+    static constexpr float r_oob = -300.0f, r_tip = -300.0f;
+    static constexpr float k_throttle_descent = (float)0.3, k_cold_gas = (float)0.7, k_free_fall = (float)0.2;
+    static constexpr float k_angle_throttle = (float)0.3, k_direction = 1.5f, gamma = (float)0.99;
+    static constexpr int max_episode_steps = 1000;
+
+    RL_HD static constexpr float land_lt(int level, int k) {
+        return level == 0 ? (k == 2 ? 5.0f : 30.0f) : level == 1 ? (k == 2 ? 8.0f : 40.0f) : (k == 2 ? 10.0f : 100.0f);
+    }
+    RL_HD static constexpr float reset_lo(int k) {
+        return k == 0 ? -1500.0f : k == 1 ? 1800.0f : k == 2 ? -25.0f : k == 3 ? -200.0f : k == 4 ? -5.0f
+             : k == 5 ? -5.0f : k == 6 ? -15.0f : k == 7 ? -10.0f : k == 8 ? 34000.0f : 370000.0f;
+    }
+    RL_HD static constexpr float reset_hi(int k) {
+        return k == 0 ? 1500.0f : k == 1 ? 2200.0f : k == 2 ? 25.0f : k == 3 ? -150.0f : k == 4 ? 5.0f
+             : k == 5 ? 5.0f : k == 6 ? 15.0f : k == 7 ? 10.0f : k == 8 ? 38000.0f : 410000.0f;
+    }
+    RL_HD static constexpr float reset_span(int k) { return (float)((double)reset_hi(k) - (double)reset_lo(k)); }
+    RL_HD static constexpr float obs_lo(int k) { return k == 1 ? 0.0f : reset_lo(k); }     // lander.py:76
+    RL_HD static constexpr float obs_hi(int k) { return reset_hi(k); }
+};
+
+inline bool matches_default(const DevParams& d) {
+    using D = DefaultParams;
+    bool ok = d.dt == D::dt && d.inv_dt == D::inv_dt && d.dt2 == D::dt2 && d.half_dt2 == D::half_dt2 &&
+              d.gravity == D::gravity && d.thrust_power == D::thrust_power && d.drag_k == D::drag_k &&
+              d.alpha_k == D::alpha_k && d.alpha_min_mass == D::alpha_min_mass && d.damp == D::damp &&
+              d.burn_per_step == D::burn_per_step && d.mass_gate == D::mass_gate &&
+              d.throttle_gate == D::throttle_gate && d.speed2_gate == D::speed2_gate && d.ground_y == D::ground_y &&
+              d.dead_band == D::dead_band && d.throttle_lo_lt == D::throttle_lo_lt &&
+              d.throttle_lo_gt == D::throttle_lo_gt && d.max_x == D::max_x && d.max_y == D::max_y &&
+              d.tip_angle == D::tip_angle && d.r_perfect == D::r_perfect && d.r_good == D::r_good &&
+              d.r_ok == D::r_ok && d.r_crash == D::r_crash && d.r_oob == D::r_oob && d.r_tip == D::r_tip &&
+              d.k_throttle_descent == D::k_throttle_descent && d.k_cold_gas == D::k_cold_gas &&
+              d.k_free_fall == D::k_free_fall && d.k_angle_throttle == D::k_angle_throttle &&
+              d.k_direction == D::k_direction && d.gamma == D::gamma &&
+              d.max_episode_steps == D::max_episode_steps;
+    for (int l = 0; l < 3 && ok; ++l)
+        for (int k = 0; k < 3; ++k) ok = ok && d.land_lt_[l][k] == D::land_lt(l, k);
+    for (int k = 0; k < 8 && ok; ++k) ok = d.obs_lo_[k] == D::obs_lo(k) && d.obs_hi_[k] == D::obs_hi(k);
+    for (int k = 0; k < 10 && ok; ++k) ok = d.reset_lo_[k] == D::reset_lo(k) && d.reset_span_[k] == D::reset_span(k);
+    return ok;
+}
 
 inline int derive_fail(char* err, size_t err_len, const char* fmt, ...) {
     if (err && err_len) {
@@ -93,9 +180,9 @@ inline int derive_params(const RlParams& p, DevParams& d, char* err, size_t err_
     d.throttle_lo_lt = f32_up(0.1);
     d.throttle_lo_gt = f32_down(0.1);
     for (int k = 0; k < 3; ++k) {
-        d.land_lt[0][k] = f32_up(p.land_perfect[k]);
-        d.land_lt[1][k] = f32_up(p.land_good[k]);
-        d.land_lt[2][k] = f32_up(p.land_ok[k]);
+        d.land_lt_[0][k] = f32_up(p.land_perfect[k]);
+        d.land_lt_[1][k] = f32_up(p.land_good[k]);
+        d.land_lt_[2][k] = f32_up(p.land_ok[k]);
     }
     d.max_x = f32_down(p.max_horizontal_position);
     d.max_y = f32_down(p.max_altitude);
@@ -113,14 +200,14 @@ inline int derive_params(const RlParams& p, DevParams& d, char* err, size_t err_
     d.k_direction = (float)p.correct_direction_bonus;
     d.gamma = (float)p.gamma;
     for (int k = 0; k < 8; ++k) {
-        d.obs_lo[k] = (float)p.obs_low[k];       // np.array(..., dtype=float32), lander.py:73-101
-        d.obs_hi[k] = (float)p.obs_high[k];
-        if (!(d.obs_lo[k] <= d.obs_hi[k])) return derive_fail(err, err_len, "obs_low[%d] > obs_high[%d]", k, k);
+        d.obs_lo_[k] = (float)p.obs_low[k];       // np.array(..., dtype=float32), lander.py:73-101
+        d.obs_hi_[k] = (float)p.obs_high[k];
+        if (!(d.obs_lo_[k] <= d.obs_hi_[k])) return derive_fail(err, err_len, "obs_low[%d] > obs_high[%d]", k, k);
     }
     for (int k = 0; k < 10; ++k) {
         if (!(p.reset_low[k] <= p.reset_high[k])) return derive_fail(err, err_len, "reset_low[%d] > reset_high[%d]", k, k);
-        d.reset_lo[k] = (float)p.reset_low[k];
-        d.reset_span[k] = (float)(p.reset_high[k] - p.reset_low[k]);
+        d.reset_lo_[k] = (float)p.reset_low[k];
+        d.reset_span_[k] = (float)(p.reset_high[k] - p.reset_low[k]);
     }
     d.max_episode_steps = p.max_episode_steps;
     return RL_OK;

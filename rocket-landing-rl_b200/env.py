@@ -196,5 +196,10 @@ class RocketLandingVecEnv:
         return EpisodeStats.from_vector(vec.cpu().tolist())
 
     @property
+    def uses_folded_constants(self) -> bool:
+        """True when the kernels with the reference's default constants folded in are used."""
+        return bool(self._L.rl_uses_folded_constants(self._h))
+
+    @property
     def launch_count(self) -> int:
         return int(self._L.rl_launch_count(self._h))

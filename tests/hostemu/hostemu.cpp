@@ -32,14 +32,12 @@ using std::min;
 
 #include "../../rocket-landing-rl_b200/csrc/rl_device.cuh"
 
-extern "C" {
-
 // soa: float32 [10][n] public state format, updated in place.  Outputs as rl_step (no reset).
-int emu_step(const RlParams* p, float* soa, int64_t n, const float* actions, float* obs, float* reward,
-             uint8_t* terminated, uint8_t* truncated, int8_t* landing, int substeps) {
-    rl::DevParams P;
-    char err[256];
-    if (rl::derive_params(*p, P, err, sizeof(err)) != RL_OK) return -1;
+// folded != 0 runs the instantiation with the reference's default constants folded in
+// (rl::DefaultParams), which the library only selects when matches_default() holds.
+template <class PP>
+static void emu_step_impl(const PP& P, float* soa, int64_t n, const float* actions, float* obs, float* reward,
+                          uint8_t* terminated, uint8_t* truncated, int8_t* landing, int substeps) {
     for (int64_t i = 0; i < n; ++i) {
         rl::Rocket r;
         r.x = soa[RL_W_X * n + i]; r.y = soa[RL_W_Y * n + i]; r.ang = soa[RL_W_ANGLE * n + i];
@@ -61,7 +59,29 @@ int emu_step(const RlParams* p, float* soa, int64_t n, const float* actions, flo
         reward[i] = rew;
         terminated[i] = o.terminated; truncated[i] = o.truncated; landing[i] = (int8_t)o.landing;
     }
+}
+
+extern "C" {
+
+int emu_step(const RlParams* p, float* soa, int64_t n, const float* actions, float* obs, float* reward,
+             uint8_t* terminated, uint8_t* truncated, int8_t* landing, int substeps, int folded) {
+    rl::DevParams P;
+    char err[256];
+    if (rl::derive_params(*p, P, err, sizeof(err)) != RL_OK) return -1;
+    if (folded) {
+        if (!rl::matches_default(P)) return -2;
+        emu_step_impl(rl::DefaultParams{}, soa, n, actions, obs, reward, terminated, truncated, landing, substeps);
+    } else {
+        emu_step_impl(P, soa, n, actions, obs, reward, terminated, truncated, landing, substeps);
+    }
     return 0;
+}
+
+int emu_matches_default(const RlParams* p) {
+    rl::DevParams P;
+    char err[256];
+    if (rl::derive_params(*p, P, err, sizeof(err)) != RL_OK) return -1;
+    return rl::matches_default(P) ? 1 : 0;
 }
 
 // Philox reset of n rockets with global ids gid0.. at `epoch`; writes soa [10][n] and obs [n][8].

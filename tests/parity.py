@@ -68,8 +68,9 @@ def _fresh_soa(states: np.ndarray, steps=0) -> np.ndarray:
 class HostEmuStepper:
     """Host build of rl_device.cuh (tests/hostemu) -- CPU logic check only, never shipped."""
 
-    def __init__(self, n: int, params: RlParams | None = None):
+    def __init__(self, n: int, params: RlParams | None = None, folded: bool = False):
         import subprocess
+        self.folded = folded
         here = os.path.join(_ROOT, "tests", "hostemu")
         so, src = os.path.join(here, "libhostemu.so"), os.path.join(here, "hostemu.cpp")
         deps = [src] + [os.path.join(_ROOT, "rocket-landing-rl_b200", "csrc", f)
@@ -79,7 +80,8 @@ class HostEmuStepper:
                                    "-ffp-contract=off", "-o", so, src])
         self.L = C.CDLL(so)
         vp = C.c_void_p
-        self.L.emu_step.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int]
+        self.L.emu_step.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int]
+        self.L.emu_matches_default.argtypes = [vp]
         self.L.emu_reset.argtypes = [vp, vp, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, vp]
         self.L.emu_philox.argtypes = [vp, vp, vp]
         self.n = n
@@ -106,8 +108,8 @@ class HostEmuStepper:
         land = np.zeros(self.n, np.int8)
         rc = self.L.emu_step(C.addressof(self.params), self.soa.ctypes.data, self.n,
                              a.ctypes.data, obs.ctypes.data, rew.ctypes.data, term.ctypes.data,
-                             trunc.ctypes.data, land.ctypes.data, substeps)
-        assert rc == 0
+                             trunc.ctypes.data, land.ctypes.data, substeps, int(self.folded))
+        assert rc == 0, rc
         return obs, rew, term.astype(bool), trunc.astype(bool), land
 
     def view(self) -> dict:

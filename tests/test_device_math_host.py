@@ -124,3 +124,32 @@ def test_fused_substeps_equal_repeated_single_steps():
         fresh[:, 1] = rng.uniform(5.0, 400.0, n)
         a_.inject_fresh(fresh, mask=done)
         b_.inject_fresh(fresh, mask=done)
+
+
+def test_folded_constants_instantiation_is_bitwise_identical():
+    """rl::DefaultParams (reference config.yaml folded in at compile time) must be the same
+    function as the runtime-constant instantiation -- the library only selects it when every
+    derived constant matches bit for bit (rl_params.h: matches_default)."""
+    import ctypes as C
+    from rocket_landing_rl_b200.config import load_params
+    n = 4096
+    a_, b_ = parity.HostEmuStepper(n), parity.HostEmuStepper(n, folded=True)
+    assert a_.L.emu_matches_default(C.addressof(a_.params)) == 1
+    other = load_params()
+    other.max_episode_steps = 999
+    assert a_.L.emu_matches_default(C.addressof(other)) == 0
+    other = load_params()
+    other.gravity = -9.80
+    assert a_.L.emu_matches_default(C.addressof(other)) == 0
+    rng = np.random.default_rng(0)
+    init = parity.sample_reset_states(rng, a_.params, n)
+    a_.inject_fresh(init)
+    b_.inject_fresh(init)
+    for t in range(200):
+        act = rng.uniform([0, -1], [1, 1], (n, 2)).astype(np.float32)
+        for x, y in zip(a_.step(act), b_.step(act)):
+            np.testing.assert_array_equal(x, y)
+        np.testing.assert_array_equal(a_.soa, b_.soa)
+        if t == 120:           # second episode for everybody
+            a_.inject_fresh(init)
+            b_.inject_fresh(init)
