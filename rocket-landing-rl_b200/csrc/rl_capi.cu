@@ -109,8 +109,7 @@ int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8
     a.ticket = e->ticket;
     a.substeps = substeps;
     const bool single = substeps == 1;
-    const int64_t warp_tiles = (e->n + rl::kWarpTile - 1) / rl::kWarpTile;
-    const int64_t ctas = (warp_tiles + rl::kWarps - 1) / rl::kWarps;
+    const int64_t ctas = (e->n + rl::kCtaThreads - 1) / rl::kCtaThreads;     // one tile of 256 rockets each
     const int cap = e->step_grid[auto_reset ? 1 : 0][single ? 1 : 0];
     const int grid = (int)(ctas < cap ? ctas : cap);
     step_kernel_for(e->folded, auto_reset != 0, single)<<<grid, rl::kCtaThreads, 0, stream>>>(e->dev, a);

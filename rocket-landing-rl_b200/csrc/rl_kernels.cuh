@@ -6,13 +6,18 @@
 //   dry      float [Np]                                  read every step, written on reset only
 //
 // Np = n_envs rounded up to 256; all planes live in one buffer so a checkpoint is one tensor.
-// The unit of work is a WARP TILE of 32 consecutive rockets: its slice of every plane is one
-// contiguous, 16-byte-aligned run (512 B / 512 B / 128 B / 128 B, plus 256 B of the action
-// array), fetched by five TMA bulk copies (cp.async.bulk, SASS UBLKCP) into that warp's own
-// shared-memory ring and signalled on that warp's own mbarrier.  Every warp is therefore an
-// independent software pipeline -- the next tile's bytes are in flight while the current tile is
-// computed, with no CTA-wide barrier in the loop, so a warp that takes the (long) reset path
-// never stalls its neighbours.
+// Thread t of a CTA owns rocket tile * 256 + t of the tile the CTA is working on, so every
+// warp-wide access is one contiguous run (512 B in planes A / B, 128 B in fuel / dry, 256 B of
+// actions, 1 KiB of observations).
+//
+// Inputs are STAGED THROUGH SHARED MEMORY BY ASYNCHRONOUS COPIES (cp.async, SASS LDGSTS): at the
+// top of an iteration each thread issues the copies of ITS OWN rocket of the NEXT tile into the
+// other half of a two-stage ring, then waits only for the current tile's group.  The next tile's
+// bytes are therefore always in flight while the current one is computed, without holding
+// registers for them.  Because a thread only ever reads back what it copied itself there is no
+// barrier, mbarrier or proxy fence in the loop, and warps never wait for one another (a warp on
+// the long reset path does not stall its CTA).  profiles/README.md records why this replaced the
+// two TMA (cp.async.bulk) designs tried first.
 #pragma once
 #include <type_traits>
 
@@ -20,10 +25,8 @@
 
 namespace rl {
 
-constexpr int kCtaThreads = 256;
-constexpr int kWarps = kCtaThreads / 32;
-constexpr int kWarpTile = 32;        // rockets per warp tile
-constexpr int kStages = 2;           // depth of each warp's shared-memory ring
+constexpr int kCtaThreads = 256;     // rockets per tile == threads per CTA
+constexpr int kStages = 2;           // depth of the shared-memory ring
 constexpr int kPad = 256;            // planes are padded to a multiple of this many rockets
 #ifndef RL_MIN_CTAS
 #define RL_MIN_CTAS 4                // resident CTAs per SM the register allocator must allow
@@ -69,52 +72,29 @@ struct StepArgs {
     int substeps;
 };
 
-// ---- TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) ----------------------------------------
+// ---- asynchronous global -> shared copies (PTX cp.async; SASS LDGSTS) ---------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t arrivals) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals) : "memory");
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {      // L2 only (.cg): streamed once
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_fence_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+__device__ __forceinline__ void cp_async_4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-// orders this thread's earlier generic-proxy accesses to shared memory (and those it has
-// synchronised with) before its later async-proxy (TMA) accesses
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+// copies src_bytes (0 or 8) and zero-fills the rest of the 8 bytes
+__device__ __forceinline__ void cp_async_8_zfill(void* dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0u;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    while (!mbar_try_wait(bar, parity)) {
-    }
-}
-// global -> shared bulk copy (1-D TMA); completion is signalled on `bar` as transaction bytes
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
-struct __align__(128) WarpStage {     // one warp tile's inputs, 1536 B
-    float4 A[kWarpTile];
-    float4 B[kWarpTile];
-    float fuel[kWarpTile];
-    float dry[kWarpTile];
-    float2 act[kWarpTile];
+struct __align__(16) Stage {          // one tile's inputs, 12 KiB; thread t uses element t of every array
+    float4 A[kCtaThreads];
+    float4 B[kCtaThreads];
+    float2 act[kCtaThreads];
+    float fuel[kCtaThreads];
+    float dry[kCtaThreads];
 };
 
 // The launch epoch lives in device memory so that a CUDA-graph replay of the step advances the
@@ -202,15 +182,16 @@ __device__ __forceinline__ void store_rocket(const StatePlanes& st, uint32_t i, 
 }
 
 // Episode end + reset of the done lanes of one warp (rare: ~1 rocket in 113 per step; inlined
-// into a cold branch -- an out-of-line call would force the rocket's registers onto the stack).  Records the finished episode, hands the terminal
-// observation / return / length to the caller's buffers, and -- with auto-reset -- resamples the
-// rocket: for every done lane (uniform loop over the ballot) lanes 0..2 compute the three Philox
-// blocks of that rocket in parallel and the ten words are shuffled to the lane that owns it.
-// Same counters and words as sample_reset(), one third of the serial Philox latency.
+// into a cold branch -- an out-of-line call would force the rocket's registers onto the stack).
+// Records the finished episode, hands the terminal observation / return / length to the
+// caller's buffers, and -- with auto-reset -- resamples the rocket: for every done lane (uniform
+// loop over the ballot) lanes 0..2 compute the three Philox blocks of that rocket in parallel
+// and the ten words are shuffled to the lane that owns it.  Same counters and words as
+// sample_reset(), one third of the serial Philox latency.
 template <bool kAutoReset, class PP>
 __device__ __forceinline__ void warp_episode_end(const PP& P, const StepArgs& a, BlockStats& bs, ThreadStats& ts,
-                                              unsigned done_mask, bool done, uint32_t i, uint64_t epoch, Rocket& r,
-                                              StepResult& o) {
+                                                 unsigned done_mask, bool done, uint32_t i, uint64_t epoch,
+                                                 Rocket& r, StepResult& o) {
     if (done) {
         const int ep_len = (int)(r.meta & RL_META_STEP_MASK);
         ts.episodes += 1;
@@ -260,78 +241,58 @@ template <> struct ParamSel<DefaultParams> {
 //   kAutoReset   reset done rockets in the same launch (scripts/train.py:82-88 contract)
 //   kSingleStep  substeps == 1 (the reference's step): no substep loop
 //   PP           DevParams (runtime constants) or DefaultParams (reference config.yaml folded in)
-// Persistent grid; warp w of CTA b walks warp tiles (b * kWarps + w), + gridDim.x * kWarps, ...
+// Persistent grid: CTA b walks tiles b, b + gridDim.x, ... of 256 rockets.
 template <bool kAutoReset, bool kSingleStep, class PP>
 __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __grid_constant__ DevParams Prt,
-                                                           const __grid_constant__ StepArgs a) {
-    __shared__ WarpStage ring[kWarps][kStages];
-    __shared__ __align__(8) uint64_t full_bar[kWarps][kStages];
+                                                                        const __grid_constant__ StepArgs a) {
+    __shared__ Stage ring[kStages];
     __shared__ BlockStats bs;
 
     const auto& P = ParamSel<PP>::get(Prt);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t n_tiles = (a.n + kCtaThreads - 1) / kCtaThreads;
+    const uint32_t stride = gridDim.x;
 
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t n_tiles = (a.n + kWarpTile - 1) / kWarpTile;
-    const uint32_t full_tiles = a.n / kWarpTile;       // tiles whose action slice is a whole 256 B
-    const uint32_t stride = gridDim.x * kWarps;
-    WarpStage* const my_ring = ring[warp];
-    uint64_t* const my_bar = full_bar[warp];
-
-    auto issue = [&](uint32_t tile, uint32_t s) {      // lane 0: five bulk copies into stage s
-        const size_t base = (size_t)tile * kWarpTile;
-        const bool act_bulk = tile < full_tiles;
-        mbar_arrive_expect_tx(&my_bar[s], 512u + 512u + 128u + 128u + (act_bulk ? 256u : 0u));
-        bulk_g2s(my_ring[s].A, a.st.A + base, 512u, &my_bar[s]);
-        bulk_g2s(my_ring[s].B, a.st.B + base, 512u, &my_bar[s]);
-        bulk_g2s(my_ring[s].fuel, a.st.fuel + base, 128u, &my_bar[s]);
-        bulk_g2s(my_ring[s].dry, a.st.dry + base, 128u, &my_bar[s]);
-        if (act_bulk) bulk_g2s(my_ring[s].act, a.actions + base, 256u, &my_bar[s]);
+    // this thread's rocket of `tile` -> stage s (state planes are padded, so only the caller's
+    // action array needs a bounds guard: out-of-range rockets get a zero action)
+    auto prefetch = [&](uint32_t tile, uint32_t s) {
+        const uint32_t j = tile * kCtaThreads + tid;
+        cp_async_16(&ring[s].A[tid], a.st.A + j);
+        cp_async_16(&ring[s].B[tid], a.st.B + j);
+        cp_async_4(&ring[s].fuel[tid], a.st.fuel + j);
+        cp_async_4(&ring[s].dry[tid], a.st.dry + j);
+        const bool in = j < a.n;
+        cp_async_8_zfill(&ring[s].act[tid], a.actions + (in ? j : 0u), in ? 8u : 0u);
     };
 
     stats_init(bs);
-    const uint32_t first = blockIdx.x * kWarps + warp;
-    if (lane == 0) {
-#pragma unroll
-        for (int s = 0; s < kStages; ++s) mbar_init(&my_bar[s], 1u);
-        mbar_fence_init();
-        fence_proxy_async();
-#pragma unroll
-        for (uint32_t s = 0; s < (uint32_t)kStages; ++s) {
-            const uint32_t tile = first + s * stride;
-            if (tile < n_tiles) issue(tile, s);
-        }
-    }
-    __syncthreads();                                    // stats_init + barrier init visible CTA-wide
+    if (blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
+    cp_async_commit();
+    __syncthreads();                                    // stats_init visible CTA-wide
     const uint64_t epoch = *a.epoch;
     ThreadStats ts;
 
-    uint32_t s = 0, parity = 0;
-    for (uint32_t tile = first; tile < n_tiles; tile += stride) {
-        const uint32_t i = tile * kWarpTile + lane;
+    uint32_t s = 0;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += stride) {
+        const uint32_t i = tile * kCtaThreads + tid;
         const bool valid = i < a.n;
 
-        mbar_wait(&my_bar[s], parity);
+        const uint32_t next = tile + stride;
+        if (next < n_tiles) prefetch(next, s ^ 1u);     // next tile in flight while this one is computed
+        cp_async_commit();                              // (possibly empty) keeps the group count uniform
+        cp_async_wait<1>();                             // everything but the newest group has landed
+
         Rocket r;
         {
-            const float4 va = my_ring[s].A[lane];
-            const float4 vb = my_ring[s].B[lane];
-            r.fuel = my_ring[s].fuel[lane];
-            r.dry = my_ring[s].dry[lane];
+            const float4 va = ring[s].A[tid];
+            const float4 vb = ring[s].B[tid];
+            r.fuel = ring[s].fuel[tid];
+            r.dry = ring[s].dry[tid];
             r.x = va.x; r.y = va.y; r.ang = va.z; r.meta = __float_as_uint(va.w);
             r.sx = vb.x; r.sy = vb.y; r.sang = vb.z; r.ep_ret = vb.w;
         }
-        float2 act;
-        if (tile < full_tiles) act = my_ring[s].act[lane];
-        else act = valid ? __ldg(&a.actions[i]) : make_float2(0.0f, 0.0f);   // ragged last tile
-        __syncwarp();                                    // every lane has drained stage s ...
-        if (lane == 0) {
-            const uint32_t next = tile + (uint32_t)kStages * stride;
-            if (next < n_tiles) {
-                fence_proxy_async();                     // ... before the async proxy overwrites it
-                issue(next, s);
-            }
-        }
-        if (++s == (uint32_t)kStages) { s = 0; parity ^= 1u; }
+        const float2 act = ring[s].act[tid];
+        s ^= 1u;
 
         StepResult o;
         float reward;
@@ -373,6 +334,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
             if (a.landing) a.landing[i] = (int8_t)landing;
         }
     }
+    cp_async_wait<0>();
     stats_flush(bs, a.stats, ts);
     epoch_bump(a.epoch, a.ticket);
 }

@@ -23,11 +23,6 @@ static inline uint2 make_uint2(uint32_t x, uint32_t y) { return {x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return {x, y, z, w}; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline float __fdividef(float a, float b) { return a / b; }
-static inline void sincospif(float x, float* s, float* c) {
-    const double t = 3.14159265358979323846 * (double)x;
-    *s = (float)std::sin(t);
-    *c = (float)std::cos(t);
-}
 using std::min;
 
 #include "../../rocket-landing-rl_b200/csrc/rl_device.cuh"

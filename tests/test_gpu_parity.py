@@ -427,7 +427,10 @@ def test_generic_and_folded_kernels_are_bitwise_identical(torch, substeps):
         for key in ("terminal_observation", "episode_return", "episode_length", "landing"):
             assert torch.equal(rf[4][key], rg[4][key]), (t, key)
     assert torch.equal(folded.get_state(), generic.get_state())
-    assert torch.equal(folded.stats_tensor(), generic.stats_tensor())
+    sf, sg = folded.stats_tensor().clone(), generic.stats_tensor().clone()
+    exact = [0, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11]            # integer-valued slots
+    assert torch.equal(sf[exact], sg[exact]) and sf[0] > 0
+    assert torch.allclose(sf, sg, rtol=1e-9)               # float sums: atomics order differs
     folded.close()
     generic.close()
 
