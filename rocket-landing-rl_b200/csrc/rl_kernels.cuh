@@ -26,7 +26,10 @@
 namespace rl {
 
 constexpr int kCtaThreads = 256;     // rockets per tile == threads per CTA
-constexpr int kStages = 2;           // depth of the shared-memory ring
+#ifndef RL_STAGES
+#define RL_STAGES 2
+#endif
+constexpr int kStages = RL_STAGES;   // depth of the shared-memory ring (tiles in flight = kStages - 1)
 constexpr int kPad = 256;            // planes are padded to a multiple of this many rockets
 #ifndef RL_MIN_CTAS
 #define RL_MIN_CTAS 4                // resident CTAs per SM the register allocator must allow
@@ -266,8 +269,12 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
     };
 
     stats_init(bs);
-    if (blockIdx.x < n_tiles) prefetch(blockIdx.x, 0);
-    cp_async_commit();
+#pragma unroll
+    for (uint32_t d = 0; d + 1 < (uint32_t)kStages; ++d) {   // prologue: the first kStages - 1 tiles
+        const uint32_t tile = blockIdx.x + d * stride;
+        if (tile < n_tiles) prefetch(tile, d);
+        cp_async_commit();
+    }
     __syncthreads();                                    // stats_init visible CTA-wide
     const uint64_t epoch = *a.epoch;
     ThreadStats ts;
@@ -277,10 +284,11 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
         const uint32_t i = tile * kCtaThreads + tid;
         const bool valid = i < a.n;
 
-        const uint32_t next = tile + stride;
-        if (next < n_tiles) prefetch(next, s ^ 1u);     // next tile in flight while this one is computed
+        const uint32_t next = tile + (uint32_t)(kStages - 1) * stride;
+        const uint32_t s_next = (s == 0u) ? (uint32_t)(kStages - 1) : s - 1u;   // the stage drained last iteration
+        if (next < n_tiles) prefetch(next, s_next);     // kStages - 1 tiles in flight while this one is computed
         cp_async_commit();                              // (possibly empty) keeps the group count uniform
-        cp_async_wait<1>();                             // everything but the newest group has landed
+        cp_async_wait<kStages - 1>();                   // everything but the newest kStages - 1 groups has landed
 
         Rocket r;
         {
@@ -292,7 +300,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
             r.sx = vb.x; r.sy = vb.y; r.sang = vb.z; r.ep_ret = vb.w;
         }
         const float2 act = ring[s].act[tid];
-        s ^= 1u;
+        s = (s + 1u == (uint32_t)kStages) ? 0u : s + 1u;
 
         StepResult o;
         float reward;
