@@ -160,7 +160,7 @@ def main() -> None:
     ap.add_argument("--rockets", type=int, default=TOTAL_ROCKETS, help="total rockets over all ranks")
     ap.add_argument("--substeps", type=int, default=1)
     ap.add_argument("--stats-interval", type=int, default=100)
-    ap.add_argument("--spinup", type=int, default=400,
+    ap.add_argument("--spinup", type=int, default=2000,
                     help="untimed env steps before the warm-up, so that episodes are desynchronised "
                          "(steady state: ~1/113 of the rockets reset per step, as in a long rollout)")
     ap.add_argument("--e2e-steps", type=int, default=4)
