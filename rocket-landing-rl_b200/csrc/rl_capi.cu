@@ -51,7 +51,9 @@ struct RlEnv {
     // host-buffer path (rl_step_host): device staging, allocated on first use
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
-    cudaStream_t h_stream = nullptr;
+    unsigned long long* h_epoch_snapshot = nullptr;    // inside h_stage
+    cudaStream_t h_streams[2] = {nullptr, nullptr};
+    cudaEvent_t h_events[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -87,10 +89,21 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Enqueue the step of tiles [tile_begin, tile_end) of the handle's rockets (a tile = 256 rockets;
+// all buffer pointers are those of rocket 0).  `epoch_src` is the epoch the launch reads; the launch
+// advances the handle's epoch when it ends iff `bump`.  rl_step passes the whole range, the handle's
+// epoch and bump = true; the pipelined host path steps chunks against a snapshot of the epoch and
+// lets only the last chunk advance it, so that it draws exactly the resets rl_step would.
 int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8_t* terminated,
                 uint8_t* truncated, float* terminal_obs, float* episode_return, int32_t* episode_length,
-                int8_t* landing, int substeps, int auto_reset, cudaStream_t stream) {
+                int8_t* landing, int substeps, int auto_reset, cudaStream_t stream, int64_t tile_begin = 0,
+                int64_t tile_end = -1, const unsigned long long* epoch_src = nullptr, bool bump = true) {
     rl::StepArgs a;
+    const int64_t all_tiles = (e->n + rl::kCtaThreads - 1) / rl::kCtaThreads;
+    if (tile_end < 0) tile_end = all_tiles;
+    a.tile_begin = (uint32_t)tile_begin;
+    a.tile_end = (uint32_t)tile_end;
+    a.epoch_bump = bump ? e->epoch : nullptr;
     a.st = e->planes;
     a.actions = reinterpret_cast<const float2*>(actions);
     a.obs = reinterpret_cast<float4*>(obs);
@@ -105,11 +118,12 @@ int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8
     a.n = (uint32_t)e->n;
     a.gid0 = e->gid0;
     a.seed = e->seed;
-    a.epoch = e->epoch;
+    a.epoch = epoch_src ? epoch_src : e->epoch;
     a.ticket = e->ticket;
     a.substeps = substeps;
     const bool single = substeps == 1;
-    const int64_t ctas = (e->n + rl::kCtaThreads - 1) / rl::kCtaThreads;     // one tile of 256 rockets each
+    const int64_t ctas = tile_end - tile_begin;                              // one tile of 256 rockets each
+    if (ctas <= 0) return RL_OK;
     const int cap = e->step_grid[auto_reset ? 1 : 0][single ? 1 : 0];
     const int grid = (int)(ctas < cap ? ctas : cap);
     step_kernel_for(e->folded, auto_reset != 0, single)<<<grid, rl::kCtaThreads, 0, stream>>>(e->dev, a);
@@ -257,7 +271,10 @@ int rl_destroy(RlEnv* e) {
     if (e->epoch) cudaFree(e->epoch);
     if (e->ticket) cudaFree(e->ticket);
     if (e->h_stage) cudaFree(e->h_stage);
-    if (e->h_stream) cudaStreamDestroy(e->h_stream);
+    for (int k = 0; k < 2; ++k) {
+        if (e->h_streams[k]) cudaStreamDestroy(e->h_streams[k]);
+        if (e->h_events[k]) cudaEventDestroy(e->h_events[k]);
+    }
     delete e;
     return RL_OK;
 }
@@ -340,7 +357,12 @@ int rl_stats(RlEnv* e, double* out16, int reset_after, void* stream) {
 
 // ---- host-buffer path ------------------------------------------------------------------
 // Device staging for one full batch: actions | obs | reward | terminated | truncated |
-// terminal_obs | episode_return | episode_length, each 256-byte aligned.
+// terminal_obs | episode_return | episode_length | landing, each 256-byte aligned.
+// rl_step_host cuts the batch into chunks and runs them as a two-stream software pipeline:
+//   chunk c:  H2D(actions[c]) -> step(tiles of c) -> D2H(obs[c], reward[c], flags[c], ...)
+// so that the (dominant) device-to-host copy of chunk c overlaps the host-to-device copy and the
+// kernel of chunk c + 1 (PCIe is full duplex).  Every chunk reads the same SNAPSHOT of the launch
+// epoch and only the last one advances it: the call draws exactly the resets one rl_step would.
 namespace {
 struct Stage {
     float *actions, *obs, *reward, *terminal_obs, *episode_return;
@@ -353,14 +375,18 @@ int ensure_stage(RlEnv* e, Stage& s) {
     const size_t n = (size_t)e->n;
     const size_t sz[9] = {align256(8 * n), align256(32 * n), align256(4 * n), align256(n), align256(n),
                           align256(32 * n), align256(4 * n), align256(4 * n), align256(n)};
-    size_t total = 0;
+    size_t total = 256;                                   // + the epoch snapshot
     for (size_t v : sz) total += v;
     if (!e->h_stage) {
         if (cudaMalloc(&e->h_stage, total) != cudaSuccess) return fail(RL_E_NOMEM, "host path: cudaMalloc(%zu) failed", total);
         e->h_stage_bytes = total;
-        RL_CUDA(cudaStreamCreateWithFlags(&e->h_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            RL_CUDA(cudaStreamCreateWithFlags(&e->h_streams[k], cudaStreamNonBlocking));
+            RL_CUDA(cudaEventCreateWithFlags(&e->h_events[k], cudaEventDisableTiming));
+        }
     }
     char* p = static_cast<char*>(e->h_stage);
+    e->h_epoch_snapshot = reinterpret_cast<unsigned long long*>(p); p += 256;
     s.actions = (float*)p; p += sz[0];
     s.obs = (float*)p; p += sz[1];
     s.reward = (float*)p; p += sz[2];
@@ -385,23 +411,42 @@ int rl_step_host(RlEnv* e, const float* actions, float* obs, float* reward, uint
     Stage s;
     int rc = ensure_stage(e, s);
     if (rc != RL_OK) return rc;
-    const size_t n = (size_t)e->n;
-    cudaStream_t st = e->h_stream;
-    RL_CUDA(cudaMemcpyAsync(s.actions, actions, 8 * n, cudaMemcpyHostToDevice, st));
-    rc = launch_step(e, s.actions, s.obs, s.reward, s.terminated, s.truncated,
-                     terminal_obs ? s.terminal_obs : nullptr, episode_return ? s.episode_return : nullptr,
-                     episode_length ? s.episode_length : nullptr, landing ? s.landing : nullptr, substeps,
-                     auto_reset, st);
-    if (rc != RL_OK) return rc;
-    RL_CUDA(cudaMemcpyAsync(obs, s.obs, 32 * n, cudaMemcpyDeviceToHost, st));
-    RL_CUDA(cudaMemcpyAsync(reward, s.reward, 4 * n, cudaMemcpyDeviceToHost, st));
-    RL_CUDA(cudaMemcpyAsync(terminated, s.terminated, n, cudaMemcpyDeviceToHost, st));
-    RL_CUDA(cudaMemcpyAsync(truncated, s.truncated, n, cudaMemcpyDeviceToHost, st));
-    if (terminal_obs) RL_CUDA(cudaMemcpyAsync(terminal_obs, s.terminal_obs, 32 * n, cudaMemcpyDeviceToHost, st));
-    if (episode_return) RL_CUDA(cudaMemcpyAsync(episode_return, s.episode_return, 4 * n, cudaMemcpyDeviceToHost, st));
-    if (episode_length) RL_CUDA(cudaMemcpyAsync(episode_length, s.episode_length, 4 * n, cudaMemcpyDeviceToHost, st));
-    if (landing) RL_CUDA(cudaMemcpyAsync(landing, s.landing, n, cudaMemcpyDeviceToHost, st));
-    RL_CUDA(cudaStreamSynchronize(st));
+    const int64_t n = e->n;
+    const int64_t tiles = (n + rl::kCtaThreads - 1) / rl::kCtaThreads;
+    // chunks of >= 1 Mi rockets (PCIe-efficient, and a full persistent grid), at most 16 of them
+    int64_t chunks = tiles / 4096;
+    chunks = chunks < 1 ? 1 : (chunks > 16 ? 16 : chunks);
+    const int64_t tiles_per_chunk = (tiles + chunks - 1) / chunks;
+    // snapshot of the launch epoch, ordered before every chunk
+    RL_CUDA(cudaMemcpyAsync(e->h_epoch_snapshot, e->epoch, sizeof(unsigned long long), cudaMemcpyDeviceToDevice,
+                            e->h_streams[0]));
+    RL_CUDA(cudaEventRecord(e->h_events[0], e->h_streams[0]));
+    RL_CUDA(cudaStreamWaitEvent(e->h_streams[1], e->h_events[0], 0));
+    for (int64_t c = 0; c < chunks; ++c) {
+        const int64_t t0 = c * tiles_per_chunk, t1 = (t0 + tiles_per_chunk < tiles) ? t0 + tiles_per_chunk : tiles;
+        if (t0 >= t1) break;
+        const size_t lo = (size_t)t0 * rl::kCtaThreads;
+        const size_t hi = (size_t)t1 * rl::kCtaThreads < (size_t)n ? (size_t)t1 * rl::kCtaThreads : (size_t)n;
+        const size_t m = hi - lo;
+        cudaStream_t st = e->h_streams[c & 1];
+        const bool last = (t1 == tiles);
+        RL_CUDA(cudaMemcpyAsync(s.actions + 2 * lo, actions + 2 * lo, 8 * m, cudaMemcpyHostToDevice, st));
+        rc = launch_step(e, s.actions, s.obs, s.reward, s.terminated, s.truncated,
+                         terminal_obs ? s.terminal_obs : nullptr, episode_return ? s.episode_return : nullptr,
+                         episode_length ? s.episode_length : nullptr, landing ? s.landing : nullptr, substeps,
+                         auto_reset, st, t0, t1, e->h_epoch_snapshot, last);
+        if (rc != RL_OK) return rc;
+        RL_CUDA(cudaMemcpyAsync(obs + 8 * lo, s.obs + 8 * lo, 32 * m, cudaMemcpyDeviceToHost, st));
+        RL_CUDA(cudaMemcpyAsync(reward + lo, s.reward + lo, 4 * m, cudaMemcpyDeviceToHost, st));
+        RL_CUDA(cudaMemcpyAsync(terminated + lo, s.terminated + lo, m, cudaMemcpyDeviceToHost, st));
+        RL_CUDA(cudaMemcpyAsync(truncated + lo, s.truncated + lo, m, cudaMemcpyDeviceToHost, st));
+        if (terminal_obs) RL_CUDA(cudaMemcpyAsync(terminal_obs + 8 * lo, s.terminal_obs + 8 * lo, 32 * m, cudaMemcpyDeviceToHost, st));
+        if (episode_return) RL_CUDA(cudaMemcpyAsync(episode_return + lo, s.episode_return + lo, 4 * m, cudaMemcpyDeviceToHost, st));
+        if (episode_length) RL_CUDA(cudaMemcpyAsync(episode_length + lo, s.episode_length + lo, 4 * m, cudaMemcpyDeviceToHost, st));
+        if (landing) RL_CUDA(cudaMemcpyAsync(landing + lo, s.landing + lo, m, cudaMemcpyDeviceToHost, st));
+    }
+    RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
+    RL_CUDA(cudaStreamSynchronize(e->h_streams[1]));
     return RL_OK;
 }
 
@@ -411,10 +456,10 @@ int rl_reset_host(RlEnv* e, float* obs) {
     Stage s;
     int rc = ensure_stage(e, s);
     if (rc != RL_OK) return rc;
-    rc = rl_reset(e, nullptr, obs ? s.obs : nullptr, e->h_stream);
+    rc = rl_reset(e, nullptr, obs ? s.obs : nullptr, e->h_streams[0]);
     if (rc != RL_OK) return rc;
-    if (obs) RL_CUDA(cudaMemcpyAsync(obs, s.obs, 32 * (size_t)e->n, cudaMemcpyDeviceToHost, e->h_stream));
-    RL_CUDA(cudaStreamSynchronize(e->h_stream));
+    if (obs) RL_CUDA(cudaMemcpyAsync(obs, s.obs, 32 * (size_t)e->n, cudaMemcpyDeviceToHost, e->h_streams[0]));
+    RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
     return RL_OK;
 }
 

@@ -70,8 +70,10 @@ struct StepArgs {
     uint32_t n;                           // rockets on this shard (< 2^31)
     int64_t gid0;                         // global id of rocket 0 (Philox counter)
     uint64_t seed;
-    unsigned long long* __restrict__ epoch;   // device: launch epoch (Philox counter), bumped by the last CTA
-    unsigned int* __restrict__ ticket;        // device: CTAs finished in this launch
+    const unsigned long long* __restrict__ epoch;   // device: launch epoch to READ (Philox counter)
+    unsigned long long* __restrict__ epoch_bump;    // device: epoch to advance when the launch ends, or null
+    unsigned int* __restrict__ ticket;              // device: CTAs finished in this launch
+    uint32_t tile_begin, tile_end;                  // tiles of 256 rockets this launch steps ([0, ceil(n/256)) = all)
     int substeps;
 };
 
@@ -253,7 +255,8 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
 
     const auto& P = ParamSel<PP>::get(Prt);
     const uint32_t tid = threadIdx.x;
-    const uint32_t n_tiles = (a.n + kCtaThreads - 1) / kCtaThreads;
+    const uint32_t n_tiles = a.tile_end;                // one past the last tile of this launch
+    const uint32_t tile0 = a.tile_begin + blockIdx.x;   // this CTA's first tile
     const uint32_t stride = gridDim.x;
 
     // this thread's rocket of `tile` -> stage s (state planes are padded, so only the caller's
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
     stats_init(bs);
 #pragma unroll
     for (uint32_t d = 0; d + 1 < (uint32_t)kStages; ++d) {   // prologue: the first kStages - 1 tiles
-        const uint32_t tile = blockIdx.x + d * stride;
+        const uint32_t tile = tile0 + d * stride;
         if (tile < n_tiles) prefetch(tile, d);
         cp_async_commit();
     }
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
     ThreadStats ts;
 
     uint32_t s = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += stride) {
+    for (uint32_t tile = tile0; tile < n_tiles; tile += stride) {
         const uint32_t i = tile * kCtaThreads + tid;
         const bool valid = i < a.n;
 
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
     }
     cp_async_wait<0>();
     stats_flush(bs, a.stats, ts);
-    epoch_bump(a.epoch, a.ticket);
+    if (a.epoch_bump) epoch_bump(a.epoch_bump, a.ticket);   // uniform over the grid
 }
 
 // RocketLandingEnv.reset (lander.py:168-186) for all / masked rockets.

@@ -468,3 +468,33 @@ def test_ragged_batch_sizes(torch):
                 assert torch.equal(x, y[:n]), (n, k)
         assert bool((canary[n:] == -7.0).all()), n
         env.close()
+
+
+def test_pipelined_host_path_equals_device_path_across_chunks(torch):
+    """rl_step_host cuts large batches into chunks on two streams; every chunk reads the same
+    epoch snapshot, so resets -- and everything else -- equal one rl_step over the whole batch."""
+    from rocket_landing_rl_b200 import RocketLandingSB3VecEnv, RocketLandingVecEnv
+    n = 3 * 4096 * 256 + 77                      # three chunks, ragged tail
+    host = RocketLandingSB3VecEnv(n, seed=17, build_infos=False)
+    dev = RocketLandingVecEnv(n, seed=17)
+    assert np.array_equal(host.reset(), dev.reset()[0].cpu().numpy())
+    a = torch.rand((n, 2), generator=torch.Generator().manual_seed(0))
+    a[:, 1] = a[:, 1] * 2 - 1
+    a_np = a.numpy()
+    a_dev = a.cuda()
+    resets = 0
+    for t in range(112):
+        oh, rh, th, trh = host.step_raw(a_np)
+        od, rd, td, trd, _ = dev.step(a_dev)
+        if t % 8 == 0 or t > 95:
+            assert np.array_equal(oh, od.cpu().numpy()), t
+            assert np.array_equal(rh, rd.cpu().numpy()), t
+            assert np.array_equal(th.astype(bool), td.cpu().numpy()), t
+        resets += int(th.sum()) + int(trh.sum())
+    assert resets > 0.5 * n
+    host.close()
+    dev.close()
+    torch.cuda.synchronize()
+    sh = RocketLandingSB3VecEnv(64, seed=1)
+    assert sh.launch_count == 0
+    sh.close()
