@@ -207,6 +207,44 @@ int rl_reset_host(RlEnv *env, float *obs);
 /* Number of kernels this handle has launched so far (step / reset / state / stats). */
 int64_t rl_launch_count(const RlEnv *env);
 
+/* ---------------------------------------------------------------------------------------------
+ * On-device VecNormalize -- the wrapper the reference puts around its vectorised environment
+ * (scripts/train.py:86-88; statistics re-loaded for inference at backend/rl/agent.py:73-80,181).
+ * Semantics of stable-baselines3 2.3.2 (running mean / variance of the observations, clip to
+ * +-clip_obs; reward divided by the running std of the discounted return, clip to +-clip_reward).
+ * All buffers are DEVICE pointers; calls only enqueue on `stream`; outputs may alias inputs. */
+typedef struct RlVecNorm RlVecNorm;
+
+const char *rl_vecnorm_last_error(void);
+int rl_vecnorm_create(int64_t n_envs, double gamma, double epsilon, double clip_obs, double clip_reward,
+                      int device, RlVecNorm **out);
+int rl_vecnorm_destroy(RlVecNorm *vn);
+/* VecNormalize.reset() on the observations returned by rl_reset. */
+int rl_vecnorm_reset(RlVecNorm *vn, const float *obs_in, float *obs_out, int training, int norm_obs, void *stream);
+/* VecNormalize.step_wait() on the outputs of rl_step; terminal_obs (nullable) is normalised in
+ * place for done rockets (SB3 normalises infos[i]["terminal_observation"]). */
+int rl_vecnorm_step(RlVecNorm *vn, const float *obs_in, const float *reward_in, const uint8_t *terminated,
+                    const uint8_t *truncated, float *terminal_obs, float *obs_out, float *reward_out,
+                    int training, int norm_obs, int norm_reward, void *stream);
+/* normalize_obs of `rows` observations with the current statistics (evaluation / inference). */
+int rl_vecnorm_normalize_obs(RlVecNorm *vn, const float *obs_in, float *obs_out, int64_t rows, void *stream);
+/* Statistics as 20 doubles in HOST memory: obs mean[8], obs var[8], obs count, return mean, var,
+ * count (what SB3 pickles as vecnormalize.pkl).  Both calls synchronise the device. */
+int rl_vecnorm_get_stats(RlVecNorm *vn, double *out20);
+int rl_vecnorm_set_stats(RlVecNorm *vn, const double *in20);
+int64_t rl_vecnorm_launch_count(const RlVecNorm *vn);
+
+/* ---------------------------------------------------------------------------------------------
+ * Generalised advantage estimation over a device-resident rollout buffer: what SB3's
+ * RolloutBuffer.compute_returns_and_advantage does for the reference's PPO (scripts/train.py:
+ * 119-134, gamma / gae_lambda of config.yaml:100-104).  DEVICE pointers; rewards, values,
+ * advantages, returns are float32 [T][N]; episode_starts uint8 [T][N]; last_values float32 [N],
+ * last_dones uint8 [N] describe the state after the last step.  Enqueue only. */
+const char *rl_rollout_last_error(void);
+int rl_gae(const float *rewards, const float *values, const uint8_t *episode_starts,
+           const float *last_values, const uint8_t *last_dones, float *advantages, float *returns, int T,
+           int64_t n_envs, double gamma, double gae_lambda, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,9 @@ ABI_VERSION = 1
 EXPORTS = ("rl_abi_version", "rl_last_error", "rl_params_default", "rl_state_bytes", "rl_create",
            "rl_destroy", "rl_num_envs", "rl_uses_folded_constants", "rl_get_epoch", "rl_set_epoch", "rl_reset", "rl_step",
            "rl_set_state", "rl_get_state", "rl_stats", "rl_step_host", "rl_reset_host",
-           "rl_launch_count")
+           "rl_launch_count", "rl_vecnorm_last_error", "rl_vecnorm_create", "rl_vecnorm_destroy",
+           "rl_vecnorm_reset", "rl_vecnorm_step", "rl_vecnorm_normalize_obs", "rl_vecnorm_get_stats",
+           "rl_vecnorm_set_stats", "rl_vecnorm_launch_count", "rl_rollout_last_error", "rl_gae")
 
 _lib = None
 
@@ -65,6 +67,19 @@ def load():
     L.rl_reset_host.argtypes = [vp, vp]
     L.rl_launch_count.argtypes = [vp]
     L.rl_launch_count.restype = i64
+    f64 = C.c_double
+    L.rl_vecnorm_last_error.restype = C.c_char_p
+    L.rl_vecnorm_create.argtypes = [i64, f64, f64, f64, f64, i32, C.POINTER(vp)]
+    L.rl_vecnorm_destroy.argtypes = [vp]
+    L.rl_vecnorm_reset.argtypes = [vp, vp, vp, i32, i32, vp]
+    L.rl_vecnorm_step.argtypes = [vp] + [vp] * 7 + [i32, i32, i32, vp]
+    L.rl_vecnorm_normalize_obs.argtypes = [vp, vp, vp, i64, vp]
+    L.rl_vecnorm_get_stats.argtypes = [vp, vp]
+    L.rl_vecnorm_set_stats.argtypes = [vp, vp]
+    L.rl_vecnorm_launch_count.argtypes = [vp]
+    L.rl_vecnorm_launch_count.restype = i64
+    L.rl_rollout_last_error.restype = C.c_char_p
+    L.rl_gae.argtypes = [vp] * 7 + [i32, i64, f64, f64, vp]
     _lib = L
     return L
 

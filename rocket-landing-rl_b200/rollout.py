@@ -1,0 +1,116 @@
+"""Device-resident PPO rollout collection (BASELINE.json configs[4]).
+
+The reference collects rollouts with stable-baselines3: ``PPO("MlpPolicy", ...,
+policy_kwargs=dict(net_arch=dict(pi=[256, 256], vf=[256, 256])))`` (``scripts/train.py:117-134``)
+steps ``SubprocVecEnv`` workers over pipes and fills a host ``RolloutBuffer``.  Here the
+environments, the (optional) ``VecNormalize`` statistics, the policy and the buffer all live on one
+GPU: nothing crosses PCIe during collection.
+
+* ``ActorCriticMLP`` is the SB3 ``MlpPolicy`` the shipped checkpoints use: separate tanh MLPs
+  8 -> 256 -> 256 for the policy and the value function, a linear action-mean head, a
+  state-independent log-std, a linear value head -- 136 965 parameters, as
+  ``assets/model/v3/best_model.zip``.  It is plain PyTorch (cuBLAS
+  GEMMs): the MLP is a neighbour of the hot path, not the path.
+* ``collect_rollout`` mirrors ``OnPolicyAlgorithm.collect_rollouts``: sample, clip the action to
+  the Box (SB3 clips before ``env.step``), step, bootstrap time-limit truncations with the value
+  of the terminal observation, store, and finally compute GAE with the ``rl_gae`` CUDA kernel.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+class ActorCriticMLP(nn.Module):
+    def __init__(self, obs_dim: int = 8, act_dim: int = 2, hidden=(256, 256), log_std_init: float = 0.0):
+        super().__init__()
+
+        def mlp():
+            layers, d = [], obs_dim
+            for h in hidden:
+                layers += [nn.Linear(d, h), nn.Tanh()]
+                d = h
+            return nn.Sequential(*layers)
+
+        self.policy_net, self.value_net_body = mlp(), mlp()
+        self.action_net = nn.Linear(hidden[-1], act_dim)
+        self.value_net = nn.Linear(hidden[-1], 1)
+        self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
+
+    def forward(self, obs: torch.Tensor, generator: Optional[torch.Generator] = None):
+        """actions ~ N(mean, exp(log_std)), values, log-probabilities (SB3 ``policy.forward``)."""
+        mean = self.action_net(self.policy_net(obs))
+        values = self.value_net(self.value_net_body(obs)).squeeze(-1)
+        std = self.log_std.exp()
+        noise = torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
+        actions = mean + std * noise
+        log_prob = (-0.5 * noise.pow(2) - self.log_std - 0.5 * math.log(2.0 * math.pi)).sum(-1)
+        return actions, values, log_prob
+
+    def predict_values(self, obs: torch.Tensor) -> torch.Tensor:
+        return self.value_net(self.value_net_body(obs)).squeeze(-1)
+
+
+class DeviceRolloutBuffer:
+    """Pre-allocated ``[T, N, ...]`` device tensors (SB3 ``RolloutBuffer`` fields)."""
+
+    def __init__(self, n_steps: int, num_envs: int, device, obs_dim: int = 8, act_dim: int = 2):
+        f32 = dict(dtype=torch.float32, device=device)
+        self.n_steps, self.num_envs = n_steps, num_envs
+        self.observations = torch.zeros((n_steps, num_envs, obs_dim), **f32)
+        self.actions = torch.zeros((n_steps, num_envs, act_dim), **f32)
+        self.rewards = torch.zeros((n_steps, num_envs), **f32)
+        self.values = torch.zeros((n_steps, num_envs), **f32)
+        self.log_probs = torch.zeros((n_steps, num_envs), **f32)
+        self.episode_starts = torch.zeros((n_steps, num_envs), dtype=torch.bool, device=device)
+        self.advantages = torch.zeros((n_steps, num_envs), **f32)
+        self.returns = torch.zeros((n_steps, num_envs), **f32)
+
+    def compute_returns_and_advantage(self, last_values: torch.Tensor, dones: torch.Tensor, gamma: float,
+                                      gae_lambda: float) -> None:
+        L = _lib.load()
+        last_values = last_values.to(torch.float32).contiguous()
+        dones = dones.to(torch.bool).contiguous()
+        rc = L.rl_gae(self.rewards.data_ptr(), self.values.data_ptr(), self.episode_starts.data_ptr(),
+                      last_values.data_ptr(), dones.data_ptr(), self.advantages.data_ptr(), self.returns.data_ptr(),
+                      self.n_steps, self.num_envs, float(gamma), float(gae_lambda),
+                      torch.cuda.current_stream(self.rewards.device).cuda_stream)
+        if rc != 0:
+            raise _lib.RocketLibraryError(f"rl_gae failed ({rc}): {L.rl_rollout_last_error().decode()}")
+
+
+@torch.no_grad()
+def collect_rollout(env, policy: ActorCriticMLP, buffer: DeviceRolloutBuffer, last_obs: torch.Tensor,
+                    last_episode_starts: torch.Tensor, gamma: float = 0.99, gae_lambda: float = 0.95,
+                    bootstrap_timeouts: bool = True, generator: Optional[torch.Generator] = None):
+    """One ``collect_rollouts`` pass of ``buffer.n_steps`` steps.  ``env`` is a
+    ``RocketLandingVecEnv`` or a ``DeviceVecNormalize`` around one (auto-reset on).  Returns
+    ``(last_obs, last_episode_starts)`` for the next pass."""
+    low = torch.tensor([0.0, -1.0], device=last_obs.device)
+    high = torch.tensor([1.0, 1.0], device=last_obs.device)
+    obs = last_obs
+    starts = last_episode_starts
+    for t in range(buffer.n_steps):
+        actions, values, log_probs = policy(obs, generator)
+        buffer.observations[t].copy_(obs)
+        buffer.actions[t].copy_(actions)
+        buffer.values[t].copy_(values)
+        buffer.log_probs[t].copy_(log_probs)
+        buffer.episode_starts[t].copy_(starts)
+        clipped = torch.clamp(actions, low, high).contiguous()       # SB3 clips Box actions before env.step
+        obs, rewards, terminated, truncated, info = env.step(clipped)
+        buffer.rewards[t].copy_(rewards)
+        if bootstrap_timeouts:
+            timeout = truncated & ~terminated                         # infos[i]["TimeLimit.truncated"]
+            if bool(timeout.any()):
+                tv = policy.predict_values(info["terminal_observation"][timeout])
+                buffer.rewards[t][timeout] += gamma * tv
+        starts = terminated | truncated
+    last_values = policy.predict_values(obs)
+    buffer.compute_returns_and_advantage(last_values, starts, gamma, gae_lambda)
+    return obs, starts

@@ -1,0 +1,78 @@
+"""Rollout path (SURVEY.md section 8f row 2 / BASELINE.json configs[4]): policy shape, GAE kernel
+against the restated SB3 recurrence, and an end-to-end device-resident collection."""
+import numpy as np
+import pytest
+
+from oracle.ppo_rollout_oracle import compute_returns_and_advantage
+
+
+def test_policy_has_the_parameter_count_of_the_shipped_checkpoints():
+    from rocket_landing_rl_b200 import ActorCriticMLP
+    net = ActorCriticMLP()
+    assert sum(p.numel() for p in net.parameters()) == 136_965        # assets/model/v3
+    import torch
+    a, v, lp = net(torch.zeros(5, 8))
+    assert a.shape == (5, 2) and v.shape == (5,) and lp.shape == (5,)
+
+
+def test_gae_oracle_closed_form():
+    # single env, no terminations, lambda = 1: advantage = discounted return + bootstrap - value
+    r = np.array([[1.0], [2.0], [3.0]])
+    v = np.array([[0.5], [0.25], [0.125]])
+    adv, ret = compute_returns_and_advantage(r, v, np.zeros((3, 1), bool), np.array([4.0]), np.array([False]), 0.9, 1.0)
+    want0 = 1 + 0.9 * 2 + 0.81 * 3 + 0.729 * 4 - 0.5
+    assert adv[0, 0] == pytest.approx(want0) and ret[0, 0] == pytest.approx(want0 + 0.5)
+    # an episode boundary cuts the bootstrap
+    adv, _ = compute_returns_and_advantage(r, v, np.array([[0], [0], [1]], bool), np.array([4.0]), np.array([False]), 0.9, 1.0)
+    assert adv[1, 0] == pytest.approx(2.0 - 0.25)
+
+
+@pytest.mark.gpu
+def test_gae_kernel_matches_the_oracle():
+    import torch
+    from rocket_landing_rl_b200 import DeviceRolloutBuffer
+    T, n = 37, 5003
+    g = torch.Generator(device="cuda").manual_seed(0)
+    buf = DeviceRolloutBuffer(T, n, "cuda")
+    buf.rewards.copy_(torch.randn((T, n), device="cuda", generator=g) * 10)
+    buf.values.copy_(torch.randn((T, n), device="cuda", generator=g))
+    buf.episode_starts.copy_(torch.rand((T, n), device="cuda", generator=g) < 0.02)
+    last_v = torch.randn(n, device="cuda", generator=g)
+    dones = torch.rand(n, device="cuda", generator=g) < 0.05
+    buf.compute_returns_and_advantage(last_v, dones, 0.99, 0.95)
+    adv, ret = compute_returns_and_advantage(buf.rewards.cpu().numpy(), buf.values.cpu().numpy(),
+                                             buf.episode_starts.cpu().numpy(), last_v.cpu().numpy(),
+                                             dones.cpu().numpy(), 0.99, 0.95)
+    np.testing.assert_allclose(buf.advantages.cpu().numpy(), adv, rtol=2e-5, atol=2e-4)
+    np.testing.assert_allclose(buf.returns.cpu().numpy(), ret, rtol=2e-5, atol=2e-4)
+
+
+@pytest.mark.gpu
+def test_device_resident_rollout_collection():
+    """configs[4] in miniature: envs -> VecNormalize -> policy -> buffer -> GAE, all on the GPU."""
+    import torch
+    from rocket_landing_rl_b200 import (ActorCriticMLP, DeviceRolloutBuffer, DeviceVecNormalize,
+                                        RocketLandingVecEnv, collect_rollout)
+    torch.manual_seed(0)
+    n, T = 8192, 160
+    env = DeviceVecNormalize(RocketLandingVecEnv(n, seed=0), gamma=0.99)
+    policy = ActorCriticMLP().cuda()
+    buf = DeviceRolloutBuffer(T, n, "cuda")
+    obs = env.reset()
+    starts = torch.ones(n, dtype=torch.bool, device="cuda")
+    obs, starts = collect_rollout(env, policy, buf, obs, starts, gamma=0.99, gae_lambda=0.95)
+    assert bool(torch.isfinite(buf.advantages).all()) and bool(torch.isfinite(buf.returns).all())
+    assert bool(buf.episode_starts[0].all()) and 0 < int(buf.episode_starts[1:].sum()) < n * 3
+    assert float(buf.observations.abs().max()) <= 10.0 + 1e-5           # clip_obs
+    assert float(buf.rewards.abs().max()) <= 10.0 + 1e-4               # clip_reward (no time-limit bootstraps here)
+    # the stored actions are the UNCLIPPED samples, as in SB3
+    assert float(buf.actions[..., 0].min()) < 0.0 and float(buf.actions[..., 0].max()) > 1.0
+    adv, ret = compute_returns_and_advantage(buf.rewards.cpu().numpy(), buf.values.cpu().numpy(),
+                                             buf.episode_starts.cpu().numpy(),
+                                             policy.predict_values(obs).detach().cpu().numpy(), starts.cpu().numpy(),
+                                             0.99, 0.95)
+    np.testing.assert_allclose(buf.advantages.cpu().numpy(), adv, rtol=1e-4, atol=1e-3)
+    stats = env.venv.stats()
+    assert stats.env_steps == n * T and stats.episodes > 0.8 * n
+    env.close()
+    env.venv.close()
