@@ -204,6 +204,20 @@ int rl_step_host(RlEnv *env, const float *actions, float *obs, float *reward,
                  int auto_reset);
 int rl_reset_host(RlEnv *env, float *obs);
 
+/* Simulation mode -- the reference's second caller of the step, the UI loop: one tick of
+ * SimulationController.step (backend/simulation/controller.py:223-269) over RocketControls.step
+ * (backend/rocket/controls.py:27-113) for every rocket, emitting the BinaryProtocol record of
+ * backend/protocol.py (16 float32 = 64 bytes per rocket: x y vx vy ax ay angle angularVelocity
+ * angularAcceleration mass fuelMass reward throttle coldGas landing_code is_active).  The action is
+ * clipped before physics AND reward, there is no time limit and no auto-reset, a rocket freezes
+ * at touchdown and is reported inactive (reward NaN) from the next tick on; rl_reset re-arms it.
+ *   rl_sim_step      : DEVICE buffers; telemetry float32 [N][16]; reward [N] / done [N] nullable.
+ *   rl_sim_step_host : HOST buffers; `message` receives the complete wire message,
+ *                      1 header byte (1 = telemetry) + 64 N bytes. */
+int rl_sim_step(RlEnv *env, const float *actions, float *telemetry, float *reward, uint8_t *done,
+                void *stream);
+int rl_sim_step_host(RlEnv *env, const float *actions, uint8_t *message);
+
 /* Number of kernels this handle has launched so far (step / reset / state / stats). */
 int64_t rl_launch_count(const RlEnv *env);
 

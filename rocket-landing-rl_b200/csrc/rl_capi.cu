@@ -7,6 +7,7 @@
 #include <new>
 
 #include "rl_kernels.cuh"
+#include "rl_sim.cuh"
 
 namespace {
 
@@ -355,6 +356,22 @@ int rl_stats(RlEnv* e, double* out16, int reset_after, void* stream) {
     return RL_OK;
 }
 
+// ---- simulation mode (controller.py / controls.py / protocol.py) ------------------------------
+int rl_sim_step(RlEnv* e, const float* actions, float* telemetry, float* reward, uint8_t* done, void* stream) {
+    if (!e || !actions || !telemetry) return fail(RL_E_INVALID, "rl_sim_step: actions and telemetry are required");
+    if (misaligned(actions, 8) || misaligned(telemetry, 16)) return fail(RL_E_INVALID, "rl_sim_step: actions need 8-byte, telemetry 16-byte alignment");
+    DeviceGuard guard(e->device);
+    if (e->folded)
+        rl::sim_step_kernel<rl::DefaultParams><<<grid_for(e, e->n), rl::kCtaThreads, 0, (cudaStream_t)stream>>>(
+            e->dev, e->planes, reinterpret_cast<const float2*>(actions), reinterpret_cast<float4*>(telemetry), reward, done, (uint32_t)e->n);
+    else
+        rl::sim_step_kernel<rl::DevParams><<<grid_for(e, e->n), rl::kCtaThreads, 0, (cudaStream_t)stream>>>(
+            e->dev, e->planes, reinterpret_cast<const float2*>(actions), reinterpret_cast<float4*>(telemetry), reward, done, (uint32_t)e->n);
+    e->launches += 1;
+    RL_CUDA(cudaGetLastError());
+    return RL_OK;
+}
+
 // ---- host-buffer path ------------------------------------------------------------------
 // Device staging for one full batch: actions | obs | reward | terminated | truncated |
 // terminal_obs | episode_return | episode_length | landing, each 256-byte aligned.
@@ -447,6 +464,29 @@ int rl_step_host(RlEnv* e, const float* actions, float* obs, float* reward, uint
     }
     RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
     RL_CUDA(cudaStreamSynchronize(e->h_streams[1]));
+    return RL_OK;
+}
+
+// One tick with HOST buffers: `actions` float32 [N,2]; `message` receives the complete binary
+// telemetry message of protocol.py: 1 header byte (1 = telemetry) + 64 bytes per rocket.
+int rl_sim_step_host(RlEnv* e, const float* actions, uint8_t* message) {
+    if (!e || !actions || !message) return fail(RL_E_INVALID, "rl_sim_step_host: null argument");
+    DeviceGuard guard(e->device);
+    Stage s;
+    int rc = ensure_stage(e, s);
+    if (rc != RL_OK) return rc;
+    const size_t n = (size_t)e->n;
+    cudaStream_t st = e->h_streams[0];
+    // The 64 B / rocket of records occupy the staging span that starts at the obs area (obs 32 n +
+    // reward 4 n + flags 2 n + terminal_obs 32 n >= 64 n bytes, contiguous); the gym-mode host path
+    // and this one never run concurrently on a handle.
+    float* records = s.obs;
+    RL_CUDA(cudaMemcpyAsync(s.actions, actions, 8 * n, cudaMemcpyHostToDevice, st));
+    rc = rl_sim_step(e, s.actions, records, nullptr, nullptr, st);
+    if (rc != RL_OK) return rc;
+    message[0] = 1;                   // BinaryProtocol.MSG_TELEMETRY
+    RL_CUDA(cudaMemcpyAsync(message + 1, records, 64 * n, cudaMemcpyDeviceToHost, st));
+    RL_CUDA(cudaStreamSynchronize(st));
     return RL_OK;
 }
 

@@ -40,6 +40,7 @@ struct Rocket {                // the ten persistent words (RL_W_*)
 struct StepResult {
     float obs[8];
     float reward;
+    float ax, ay, alpha;       // raw accelerations of this step (telemetry: protocol.py:9-14)
     bool terminated, truncated, out_of_bounds, tipped, nonfinite;
     int landing;               // 0 none, 1 safe, 2 good, 3 ok, 4 unsafe (protocol.py:31-41)
 };
@@ -221,7 +222,7 @@ __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw
     const float cg = clipf(cg_raw, -1.0f, 1.0f);
     const float m = r.dry + fuel_now;                          // pre-burn mass, base.py:143-144
 
-    float ax = 0.0f, ay = 0.0f, vx_a = vx_b, vy_a = vy_b, om_a = om_b;
+    float ax = 0.0f, ay = 0.0f, alpha = 0.0f, vx_a = vx_b, vy_a = vy_b, om_a = om_b;
     if (m > P.mass_gate) {                                     // base.py:145-147: else no-op
         const float inv_m = rl_rcp(m);
         // drag (engine.py:78-98): 0.5 rho Cd A v^2 (-v/|v|) = -drag_k |v| v
@@ -236,7 +237,7 @@ __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw
         const float t = (th > P.throttle_gate) ? th * P.thrust_power * inv_m : 0.0f;
         ax = fmaf(t, s, a0x);
         ay = fmaf(t, c, a0y);
-        const float alpha = (m >= P.alpha_min_mass) ? cg * P.alpha_k * inv_m : 0.0f;  // engine.py:125-155
+        alpha = (m >= P.alpha_min_mass) ? cg * P.alpha_k * inv_m : 0.0f;              // engine.py:125-155
 
         // carried deltas; a FRESH rocket gets the Verlet bootstrap (base.py:65-130):
         // x - x_prev = v dt - a0 dt^2 / 2 and, alpha0 being 0, angle - angle_prev = omega dt
@@ -324,6 +325,9 @@ __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw
     o.landing = landing;
     o.truncated = oob || (steps >= P.max_episode_steps);       // lander.py:237-241
     o.reward = total;
+    o.ax = ax;
+    o.ay = ay;
+    o.alpha = alpha;
     o.nonfinite = !(fabsf(total) <= 3.0e38f) || !(fabsf(y_a) <= 3.0e38f);
     r.ep_ret += total;
     clip_obs(P, x_a, y_a, vx_a, vy_a, ax, ay, ang_a, om_a, o.obs);

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kThreads) vn_moments(VnState* __restrict__ st,
             const float v[kObs] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int k = 0; k < kObs; ++k) {
-                const double d = (double)(v[k] - sh[k]);
+                const double d = (double)v[k] - (double)sh[k];
                 acc[k] += d;
                 acc[kObs + k] += d * d;
             }

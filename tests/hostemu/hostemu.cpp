@@ -72,6 +72,43 @@ int emu_step(const RlParams* p, float* soa, int64_t n, const float* actions, flo
     return 0;
 }
 
+// One simulation-mode tick (rl_sim.cuh semantics) on the host: soa in/out, telemetry [n][16].
+int emu_sim_step(const RlParams* p, float* soa, int64_t n, const float* actions, float* telemetry) {
+    rl::DevParams P;
+    char err[256];
+    if (rl::derive_params(*p, P, err, sizeof(err)) != RL_OK) return -1;
+    const uint32_t kLanded = 0x40000000u;
+    for (int64_t i = 0; i < n; ++i) {
+        rl::Rocket r;
+        r.x = soa[RL_W_X * n + i]; r.y = soa[RL_W_Y * n + i]; r.ang = soa[RL_W_ANGLE * n + i];
+        r.sx = soa[RL_W_SX * n + i]; r.sy = soa[RL_W_SY * n + i]; r.sang = soa[RL_W_SANGLE * n + i];
+        r.dry = soa[RL_W_DRY * n + i]; r.fuel = soa[RL_W_FUEL * n + i];
+        std::memcpy(&r.meta, &soa[RL_W_META * n + i], 4); r.ep_ret = soa[RL_W_EPRET * n + i];
+        float* rec = telemetry + 16 * i;
+        if (r.meta & kLanded) {
+            for (int k = 0; k < 16; ++k) rec[k] = 0.0f;
+            rec[11] = std::nanf("");
+            rec[14] = (float)((r.meta >> 27) & 7u);
+            continue;
+        }
+        const float th = std::fmin(std::fmax(actions[2 * i], 0.0f), 1.0f);
+        const float cg = std::fmin(std::fmax(actions[2 * i + 1], -1.0f), 1.0f);
+        rl::StepResult o;
+        rl::rocket_step(P, r, th, cg, o);
+        const bool landed = o.terminated;
+        if (landed) r.meta |= kLanded | ((uint32_t)o.landing << 27);
+        soa[RL_W_X * n + i] = r.x; soa[RL_W_Y * n + i] = r.y; soa[RL_W_ANGLE * n + i] = r.ang;
+        soa[RL_W_SX * n + i] = r.sx; soa[RL_W_SY * n + i] = r.sy; soa[RL_W_SANGLE * n + i] = r.sang;
+        soa[RL_W_FUEL * n + i] = r.fuel; std::memcpy(&soa[RL_W_META * n + i], &r.meta, 4);
+        soa[RL_W_EPRET * n + i] = r.ep_ret;
+        const float rv[16] = {r.x, r.y, r.sx * P.inv_dt, r.sy * P.inv_dt, o.ax, o.ay, r.ang, r.sang * P.inv_dt,
+                              o.alpha, r.dry, r.fuel, o.reward, landed ? 0.0f : actions[2 * i],
+                              landed ? 0.0f : actions[2 * i + 1], (float)o.landing, 1.0f};
+        std::memcpy(rec, rv, sizeof(rv));
+    }
+    return 0;
+}
+
 int emu_matches_default(const RlParams* p) {
     rl::DevParams P;
     char err[256];
