@@ -249,7 +249,7 @@ def main() -> None:
     bytes_per_launch = BYTES_PER_ENV_STEP * count / 1.0       # one launch = `count` rockets x substeps
     achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "rl::step_kernel<true>", "kernel_ms": kernel_ms,
+                "traffic": None, "kernel": "rl::step_kernel<auto_reset, single_step=%s, DefaultParams>" % (args.substeps == 1), "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_env_step": BYTES_PER_ENV_STEP / args.substeps, "peak_source": peak_src}
     traffic_file = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
     if os.path.exists(traffic_file):
