@@ -25,7 +25,10 @@
 
 namespace rl {
 
-constexpr int kCtaThreads = 256;     // rockets per tile == threads per CTA
+#ifndef RL_CTA_THREADS
+#define RL_CTA_THREADS 256
+#endif
+constexpr int kCtaThreads = RL_CTA_THREADS;   // rockets per tile == threads per CTA
 #ifndef RL_STAGES
 #define RL_STAGES 2
 #endif
@@ -186,6 +189,18 @@ __device__ __forceinline__ void store_rocket(const StatePlanes& st, uint32_t i, 
     if (write_dry) st.dry[i] = r.dry;
 }
 
+// Stores of the per-step OUTPUTS (observation, reward, flags).  They are written once and read by
+// somebody else later; RL_STREAMING_STORES marks them evict-first (st.global.cs) so that they do
+// not displace the state planes from L2 -- which only matters for batches whose state fits L2.
+template <class T>
+__device__ __forceinline__ void out_store(T* p, T v) {
+#ifdef RL_STREAMING_STORES
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
+
 // Episode end + reset of the done lanes of one warp (rare: ~1 rocket in 113 per step; inlined
 // into a cold branch -- an out-of-line call would force the rocket's registers onto the stack).
 // Records the finished episode, hands the terminal observation / return / length to the
@@ -337,12 +352,12 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
 
         if (valid) {
             store_rocket(a.st, i, r, false);
-            a.obs[2 * (size_t)i] = make_float4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]);
-            a.obs[2 * (size_t)i + 1] = make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]);
-            a.reward[i] = reward;
-            a.terminated[i] = terminated ? 1 : 0;
-            a.truncated[i] = truncated ? 1 : 0;
-            if (a.landing) a.landing[i] = (int8_t)landing;
+            out_store(&a.obs[2 * (size_t)i], make_float4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]));
+            out_store(&a.obs[2 * (size_t)i + 1], make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]));
+            out_store(&a.reward[i], reward);
+            out_store(&a.terminated[i], (uint8_t)(terminated ? 1 : 0));
+            out_store(&a.truncated[i], (uint8_t)(truncated ? 1 : 0));
+            if (a.landing) out_store(reinterpret_cast<uint8_t*>(&a.landing[i]), (uint8_t)landing);
         }
     }
     cp_async_wait<0>();

@@ -100,6 +100,7 @@ class RocketLandingVecEnv:
         self.episode_length = torch.zeros((n,), dtype=torch.int32, device=self.device)
         self.landing = torch.zeros((n,), dtype=torch.int8, device=self.device)
         self._stats = torch.zeros((STATS_WORDS,), dtype=torch.float64, device=self.device)
+        self._out_ptrs = None            # cached data_ptr()s of the output buffers (see step)
 
     # ------------------------------------------------------------------ gym surface
     def _stream(self) -> int:
@@ -125,11 +126,14 @@ class RocketLandingVecEnv:
             action = action.to(device=self.device, dtype=torch.float32).contiguous()
         if action.shape != (self.num_envs, 2):
             raise ValueError(f"action must have shape ({self.num_envs}, 2), got {tuple(action.shape)}")
-        _lib.check(self._L.rl_step(
-            self._h, action.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
-            self.terminated.data_ptr(), self.truncated.data_ptr(), self.terminal_obs.data_ptr(),
-            self.episode_return.data_ptr(), self.episode_length.data_ptr(), self.landing.data_ptr(),
-            self.substeps, int(self.auto_reset), self._stream()), "rl_step")
+        outs = (self.obs, self.reward, self.terminated, self.truncated, self.terminal_obs,
+                self.episode_return, self.episode_length, self.landing)
+        if self._out_ptrs is None or self._out_ptrs[0] is not self.obs:      # buffers are persistent; a
+            self._out_ptrs = (self.obs, tuple(t.data_ptr() for t in outs))   # caller may swap self.obs
+        rc = self._L.rl_step(self._h, action.data_ptr(), *self._out_ptrs[1], self.substeps,
+                             int(self.auto_reset), self._stream())
+        if rc != 0:
+            _lib.check(rc, "rl_step")
         info = {"terminal_observation": self.terminal_obs, "episode_return": self.episode_return,
                 "episode_length": self.episode_length, "landing": self.landing}
         return self.obs, self.reward, self.terminated, self.truncated, info
