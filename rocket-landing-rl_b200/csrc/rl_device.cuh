@@ -35,6 +35,9 @@ struct Rocket {                // the ten persistent words (RL_W_*)
     float dry, fuel;
     float ep_ret;
     uint32_t meta;
+    // precise-altitude mode only (RL_W_YLO, RL_W_SYLO): low-order words of y and of its delta,
+    // so that y = y + y_lo and sy = sy + sy_lo carry ~48 bits; zero and unused otherwise
+    float y_lo = 0.0f, sy_lo = 0.0f;
 };
 
 struct StepResult {
@@ -204,7 +207,12 @@ __device__ __forceinline__ float landing_reward(const PP& P, float avx, float av
 
 // One env step (lander.py:188-255) of one rocket, no reset.  th_raw / cg_raw are the raw
 // action: physics clips it (base.py:135-136), the reward does not (reward.py:69-70).
-template <class PP>
+//
+// kPreciseY: the altitude recurrence (dy' = dy + ay dt^2, y' = y + dy') and the touchdown test run
+// in fp64 on (hi, lo) float pairs; everything else, the forces included, stays fp32.  Altitude is
+// the one word whose error decides a discrete outcome (the touchdown step): in fp32 it reaches
+// ~1e-3 m by the end of a descent from 2000 m, i.e. a +-1-step disagreement in ~1 of 10^4 episodes.
+template <class PP, bool kPreciseY = false>
 __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw, float cg_raw,
                                             StepResult& o) {
     const bool fresh = (r.meta & RL_META_FRESH) != 0u;
@@ -213,8 +221,13 @@ __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw
 
     // ---- state before the action (Rocket.get_state, base.py:220) --------------------------
     const float y_b = r.y, ang_b = r.ang;
+    const double y_b_d = (double)r.y + (double)r.y_lo;          // (precise mode only)
     const float vscale = fresh ? 1.0f : P.inv_dt;               // slots hold v while FRESH, deltas after
-    const float vx_b = r.sx * vscale, vy_b = r.sy * vscale, om_b = r.sang * vscale;
+    const float vx_b = r.sx * vscale, om_b = r.sang * vscale;
+    float vy_b = r.sy * vscale;
+    if constexpr (kPreciseY) {
+        if (!fresh) vy_b = (float)(((double)r.sy + (double)r.sy_lo) * (1.0 / (double)P.dt_d));
+    }
 
     // ---- Rocket.apply_action (base.py:132-184) -----------------------------------------------
     const float fuel_now = r.fuel;
@@ -223,6 +236,7 @@ __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw
     const float m = r.dry + fuel_now;                          // pre-burn mass, base.py:143-144
 
     float ax = 0.0f, ay = 0.0f, alpha = 0.0f, vx_a = vx_b, vy_a = vy_b, om_a = om_b;
+    double y_a_d = y_b_d;
     if (m > P.mass_gate) {                                     // base.py:145-147: else no-op
         const float inv_m = rl_rcp(m);
         // drag (engine.py:78-98): 0.5 rho Cd A v^2 (-v/|v|) = -drag_k |v| v
@@ -255,14 +269,27 @@ __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw
         const float ndy = fmaf(ay, P.dt2, dy);
         const float ndang = fmaf(dang, P.damp, alpha * P.dt2);
         r.x += ndx;
-        r.y += ndy;
         vx_a = ndx * P.inv_dt;
-        vy_a = ndy * P.inv_dt;
+        if constexpr (kPreciseY) {
+            const double dtd = (double)P.dt_d;
+            const double dy_d = fresh ? ((double)vy_b * dtd - 0.5 * (double)a0y * dtd * dtd)
+                                      : ((double)r.sy + (double)r.sy_lo);
+            const double ndy_d = dy_d + (double)ay * (dtd * dtd);
+            y_a_d = y_b_d + ndy_d;
+            r.y = (float)y_a_d;
+            r.y_lo = (float)(y_a_d - (double)r.y);
+            r.sy = (float)ndy_d;
+            r.sy_lo = (float)(ndy_d - (double)r.sy);
+            vy_a = (float)(ndy_d * (1.0 / dtd));
+        } else {
+            r.y += ndy;
+            vy_a = ndy * P.inv_dt;
+            r.sy = ndy;
+        }
         om_a = ndang * P.inv_dt;                               // before normalisation, engine.py:220-222
         int k;
         r.ang = normalize_angle(ang_b + ndang, k);             // engine.py:226
         r.sx = ndx;
-        r.sy = ndy;
         r.sang = ndang;
         r.fuel = fmaxf(0.0f, fuel_now - fmaxf(0.0f, th * P.burn_per_step));   // engine.py:239-243, base.py:174-175
         r.meta = (((uint32_t)k & 7u) << RL_META_WRAP_SHIFT) | (uint32_t)steps;   // FRESH cleared
@@ -287,7 +314,7 @@ __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw
     const float amp = (need && effect > 0.0f) ? fmaf(effect, effect, 1.0f) : 1.0f;
     const float gain = need ? (ab + wb) * (correct ? P.k_direction : -P.k_direction) : -0.3f;
     total = fmaf(fabsf(cg_raw) * gain * P.k_cold_gas, amp, total);
-    const bool airborne = y_a > P.ground_y;
+    const bool airborne = kPreciseY ? (y_a_d > 0.1) : (y_a > P.ground_y);
     const bool descending = airborne && (vy_a < 0.0f);
     // 2. throttle while descending (reward.py:171-186)
     const float af = fmaxf(0.0f, fmaf(aa, -1.0f / 45.0f, 1.0f));
@@ -312,7 +339,8 @@ __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw
     total += tipped ? P.r_tip : 0.0f;
 
     // ---- ground contact (reward.py:73-102): replaces the shaping reward, skips bounds / tip ----
-    const bool terminated = (y_a <= P.ground_y) && (y_b > P.ground_y);
+    const bool terminated = kPreciseY ? ((y_a_d <= 0.1) && (y_b_d > 0.1))
+                                      : ((y_a <= P.ground_y) && (y_b > P.ground_y));
     int landing = 0;
     if (terminated) {
         total = landing_reward(P, fabsf(vx_a), avy, aa, landing);

@@ -32,6 +32,7 @@ namespace rl {
 // `x > c` == `x > down(c)` and `x < c` == `x < up(c)` for every fp32 x.
 struct DevParams {
     float dt, inv_dt, dt2, half_dt2;
+    double dt_d;               // time step in fp64 (precise-altitude mode)
     float gravity;
     float thrust_power;        // N at throttle 1
     float drag_k;              // 0.5 rho Cd A   (engine.py:88-94); drag force = -drag_k |v| v
@@ -65,6 +66,7 @@ struct DevParams {
 struct DefaultParams {
     static constexpr double kDt = 0.1, kPi = 3.14159265358979323846;
     static constexpr float dt = (float)kDt;
+    static constexpr double dt_d = kDt;
     static constexpr float inv_dt = (float)(1.0 / kDt);
     static constexpr float dt2 = (float)(kDt * kDt);
     static constexpr float half_dt2 = (float)(0.5 * kDt * kDt);
@@ -107,7 +109,7 @@ struct DefaultParams {
 
 inline bool matches_default(const DevParams& d) {
     using D = DefaultParams;
-    bool ok = d.dt == D::dt && d.inv_dt == D::inv_dt && d.dt2 == D::dt2 && d.half_dt2 == D::half_dt2 &&
+    bool ok = d.dt == D::dt && d.dt_d == D::dt_d && d.inv_dt == D::inv_dt && d.dt2 == D::dt2 && d.half_dt2 == D::half_dt2 &&
               d.gravity == D::gravity && d.thrust_power == D::thrust_power && d.drag_k == D::drag_k &&
               d.alpha_k == D::alpha_k && d.alpha_min_mass == D::alpha_min_mass && d.damp == D::damp &&
               d.burn_per_step == D::burn_per_step && d.mass_gate == D::mass_gate &&
@@ -160,6 +162,7 @@ inline int derive_params(const RlParams& p, DevParams& d, char* err, size_t err_
     const double pi = 3.14159265358979323846;
     const double dt = p.time_step;
     d.dt = (float)dt;
+    d.dt_d = dt;
     d.inv_dt = (float)(1.0 / dt);
     d.dt2 = (float)(dt * dt);
     d.half_dt2 = (float)(0.5 * dt * dt);

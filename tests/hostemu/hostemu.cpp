@@ -72,6 +72,33 @@ int emu_step(const RlParams* p, float* soa, int64_t n, const float* actions, flo
     return 0;
 }
 
+// Precise-altitude mode (rocket_step<PP, true>): `lo` is float32 [2][n] = y_lo, sy_lo, in/out.
+int emu_step_precise(const RlParams* p, float* soa, float* lo, int64_t n, const float* actions, float* obs,
+                     float* reward, uint8_t* terminated, uint8_t* truncated, int8_t* landing) {
+    rl::DevParams P;
+    char err[256];
+    if (rl::derive_params(*p, P, err, sizeof(err)) != RL_OK) return -1;
+    for (int64_t i = 0; i < n; ++i) {
+        rl::Rocket r;
+        r.x = soa[RL_W_X * n + i]; r.y = soa[RL_W_Y * n + i]; r.ang = soa[RL_W_ANGLE * n + i];
+        r.sx = soa[RL_W_SX * n + i]; r.sy = soa[RL_W_SY * n + i]; r.sang = soa[RL_W_SANGLE * n + i];
+        r.dry = soa[RL_W_DRY * n + i]; r.fuel = soa[RL_W_FUEL * n + i];
+        std::memcpy(&r.meta, &soa[RL_W_META * n + i], 4); r.ep_ret = soa[RL_W_EPRET * n + i];
+        r.y_lo = lo[i]; r.sy_lo = lo[n + i];
+        rl::StepResult o;
+        rl::rocket_step<rl::DevParams, true>(P, r, actions[2 * i], actions[2 * i + 1], o);
+        soa[RL_W_X * n + i] = r.x; soa[RL_W_Y * n + i] = r.y; soa[RL_W_ANGLE * n + i] = r.ang;
+        soa[RL_W_SX * n + i] = r.sx; soa[RL_W_SY * n + i] = r.sy; soa[RL_W_SANGLE * n + i] = r.sang;
+        soa[RL_W_DRY * n + i] = r.dry; soa[RL_W_FUEL * n + i] = r.fuel;
+        std::memcpy(&soa[RL_W_META * n + i], &r.meta, 4); soa[RL_W_EPRET * n + i] = r.ep_ret;
+        lo[i] = r.y_lo; lo[n + i] = r.sy_lo;
+        std::memcpy(obs + 8 * i, o.obs, 32);
+        reward[i] = o.reward;
+        terminated[i] = o.terminated; truncated[i] = o.truncated; landing[i] = (int8_t)o.landing;
+    }
+    return 0;
+}
+
 // One simulation-mode tick (rl_sim.cuh semantics) on the host: soa in/out, telemetry [n][16].
 int emu_sim_step(const RlParams* p, float* soa, int64_t n, const float* actions, float* telemetry) {
     rl::DevParams P;
