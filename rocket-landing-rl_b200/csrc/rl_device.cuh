@@ -44,6 +44,8 @@ struct StepResult {
     float obs[8];
     float reward;
     float ax, ay, alpha;       // raw accelerations of this step (telemetry: protocol.py:9-14)
+    float vx, vy, om;          // velocities after the step (unclipped)
+    float phi;                 // potential of the state after the step (reward.py:231-264)
     bool terminated, truncated, out_of_bounds, tipped, nonfinite;
     int landing;               // 0 none, 1 safe, 2 good, 3 ok, 4 unsafe (protocol.py:31-41)
 };
@@ -212,9 +214,14 @@ __device__ __forceinline__ float landing_reward(const PP& P, float avx, float av
 // in fp64 on (hi, lo) float pairs; everything else, the forces included, stays fp32.  Altitude is
 // the one word whose error decides a discrete outcome (the touchdown step): in fp32 it reaches
 // ~1e-3 m by the end of a descent from 2000 m, i.e. a +-1-step disagreement in ~1 of 10^4 episodes.
+//
+// rocket_advance does everything except the observation.  With have_phi, o.phi must hold the
+// potential of the CURRENT state (it does after a previous rocket_advance on the same rocket):
+// the fused-substep loop then evaluates the potential once per substep instead of twice, with
+// bit-identical results (same expression, same operands).
 template <class PP, bool kPreciseY = false>
-__device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw, float cg_raw,
-                                            StepResult& o) {
+__device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_raw, float cg_raw,
+                                               StepResult& o, bool have_phi) {
     const bool fresh = (r.meta & RL_META_FRESH) != 0u;
     const int steps = min((int)(r.meta & RL_META_STEP_MASK) + 1, (int)RL_META_STEP_MASK);   // lander.py:229
     const int k_prev = ((int)(r.meta << 5)) >> 29;             // bits [24,27) sign-extended
@@ -331,7 +338,9 @@ __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw
     const float t5 = vy_a * 0.5f * fminf(1.0f, y_a * 1e-3f) * (1.0f + fminf(1.0f, vy_a * 0.2f));
     total -= (airborne && vy_a > 0.0f) ? t5 : 0.0f;
     // 6. potential shaping (reward.py:267-270)
-    total += fmaf(P.gamma, potential(y_a, vx_a, vy_a, ang_a, om_a), -potential(y_b, vx_b, vy_b, ang_b, om_b));
+    const float phi_b = have_phi ? o.phi : potential(y_b, vx_b, vy_b, ang_b, om_b);
+    const float phi_a = potential(y_a, vx_a, vy_a, ang_a, om_a);
+    total += fmaf(P.gamma, phi_a, -phi_b);
     // truncation penalties (reward.py:274-279); tip-over never ends the episode
     bool oob = (fabsf(x_a) > P.max_x) || (y_a > P.max_y);
     bool tipped = aa > P.tip_angle;
@@ -356,9 +365,25 @@ __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw
     o.ax = ax;
     o.ay = ay;
     o.alpha = alpha;
+    o.vx = vx_a;
+    o.vy = vy_a;
+    o.om = om_a;
+    o.phi = phi_a;
     o.nonfinite = !(fabsf(total) <= 3.0e38f) || !(fabsf(y_a) <= 3.0e38f);
     r.ep_ret += total;
-    clip_obs(P, x_a, y_a, vx_a, vy_a, ax, ay, ang_a, om_a, o.obs);
+}
+
+// _get_obs of the state rocket_advance left behind (lander.py:243)
+template <class PP>
+__device__ __forceinline__ void step_obs(const PP& P, const Rocket& r, StepResult& o) {
+    clip_obs(P, r.x, r.y, o.vx, o.vy, o.ax, o.ay, r.ang, o.om, o.obs);
+}
+
+template <class PP, bool kPreciseY = false>
+__device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw, float cg_raw,
+                                            StepResult& o) {
+    rocket_advance<PP, kPreciseY>(P, r, th_raw, cg_raw, o, false);
+    step_obs(P, r, o);
 }
 
 }  // namespace rl

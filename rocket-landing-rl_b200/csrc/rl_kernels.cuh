@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
             reward = 0.0f;
             done = false;
             for (int k = 0; k < a.substeps; ++k) {
-                rocket_step(P, r, act.x, act.y, o);
+                rocket_advance(P, r, act.x, act.y, o, k > 0);     // potential carried across substeps
                 reward += o.reward;
                 ts.env_steps += valid ? 1 : 0;
                 ts.tip_steps += (valid && o.tipped) ? 1 : 0;
@@ -342,6 +342,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
                 done = valid && (o.terminated || o.truncated);
                 if (done) break;                         // stop integrating at the first done
             }
+            step_obs(P, r, o);                           // the observation is only needed once
         }
         ts.reward_sum += valid ? reward : 0.0f;
 
