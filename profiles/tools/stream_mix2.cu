@@ -1,0 +1,181 @@
+// Second attainable-bandwidth probe for the step kernel's access pattern (no physics).  It asks
+// which properties of the PATTERN cost bandwidth, so that the step kernel can be reshaped:
+//   * calibration: read-only, write-only and copy kernels (what an SM kernel can reach at all);
+//   * the nine-stream mix (48 B read, 75 B written per rocket) with
+//       T  observation rows written as whole 32-byte sectors per instruction (lane-pair exchange),
+//       S  state in tile-major order (one contiguous 10 KiB block per 256 rockets) instead of planes,
+//       N  non-persistent grid (one tile per CTA),
+//       H  cache hints: loads evict-first (.cs), outputs evict-first (.cs),
+//       F- without the three byte-flag streams, R- without the reward stream (marginal costs).
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a stream_mix2.cu -o stream_mix2
+#include <cstdio>
+#include <cstdint>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); return 1; } } while (0)
+
+__global__ void __launch_bounds__(256) copy_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = in[i];
+}
+// torch-style: one CTA per 256 x 4 elements, four independent 128-bit loads per thread
+__global__ void __launch_bounds__(256) copy4_kernel(const float4* __restrict__ in, float4* __restrict__ out, size_t n) {
+    const size_t base = blockIdx.x * 1024ull + threadIdx.x;
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (base + u * 256 < n) v[u] = in[base + u * 256];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (base + u * 256 < n) out[base + u * 256] = v[u];
+}
+__global__ void __launch_bounds__(256) read_kernel(const float4* __restrict__ in, float* __restrict__ out, size_t n) {
+    float acc = 0.f;
+    size_t i = blockIdx.x * 256ull + threadIdx.x;
+    const size_t st = (size_t)gridDim.x * 256;
+    for (; i + 3 * st < n; i += 4 * st) {
+        const float4 a = in[i], b = in[i + st], c = in[i + 2 * st], d = in[i + 3 * st];
+        acc += a.x + b.y + c.z + d.w;
+    }
+    for (; i < n; i += st) acc += in[i].x;
+    if (acc == 12345.678f) out[0] = acc;
+}
+__global__ void __launch_bounds__(256) write_kernel(float4* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * 256ull + threadIdx.x; i < n; i += (size_t)gridDim.x * 256)
+        out[i] = make_float4(1.f, 2.f, 3.f, (float)i);
+}
+
+struct Bufs {
+    float4 *A, *B, *obs; float *fuel, *dry, *rew; const float2* act; uint8_t *f0, *f1, *f2;
+    char* tiled;   // tile-major state: per 256 rockets { float4 A[256]; float4 B[256]; float fuel[256]; float dry[256]; }
+};
+
+template <int kHint, class T> __device__ __forceinline__ T ld(const T* p) {
+    if constexpr (kHint == 1) return __ldcs(p);
+    else if constexpr (kHint == 2) return __ldcg(p);
+    else return *p;
+}
+template <int kHint, class T> __device__ __forceinline__ void st(T* p, T v) {
+    if constexpr (kHint == 1) __stcs(p, v);
+    else if constexpr (kHint == 2) __stcg(p, v);
+    else if constexpr (kHint == 3) __stwt(p, v);
+    else *p = v;
+}
+
+template <int kUnroll, bool kObsT, bool kTiled, bool kPersist, int kLdHint, int kStHint, bool kFlags, bool kReward>
+__global__ void __launch_bounds__(256) mix_kernel(Bufs b, uint32_t n) {
+    const uint32_t stride = kPersist ? gridDim.x * 256u * kUnroll : 0xffffffffu;
+    for (uint32_t base = blockIdx.x * 256u * kUnroll + threadIdx.x; base < n; base += stride) {
+        float4 a[kUnroll], bb[kUnroll]; float fu[kUnroll], d[kUnroll]; float2 ac[kUnroll];
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t i = base + u * 256u;
+            if (i < n) {
+                if constexpr (kTiled) {
+                    const char* t = b.tiled + (size_t)(i >> 8) * 10240u;
+                    const uint32_t l = i & 255u;
+                    a[u] = ld<kLdHint>(reinterpret_cast<const float4*>(t) + l);
+                    bb[u] = ld<kLdHint>(reinterpret_cast<const float4*>(t + 4096) + l);
+                    fu[u] = ld<kLdHint>(reinterpret_cast<const float*>(t + 8192) + l);
+                    d[u] = ld<kLdHint>(reinterpret_cast<const float*>(t + 9216) + l);
+                } else {
+                    a[u] = ld<kLdHint>(b.A + i); bb[u] = ld<kLdHint>(b.B + i);
+                    fu[u] = ld<kLdHint>(b.fuel + i); d[u] = ld<kLdHint>(b.dry + i);
+                }
+                ac[u] = ld<kLdHint>(b.act + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const uint32_t i = base + u * 256u;
+            if (i < n) {      // n is a multiple of 256: uniform per warp, shuffles below are safe
+                const float s = a[u].x + bb[u].y + fu[u] * d[u] + ac[u].x * ac[u].y;
+                const float4 nA = make_float4(a[u].y, a[u].x, a[u].w + s, a[u].z);
+                const float4 nB = make_float4(bb[u].y, bb[u].x, bb[u].w, bb[u].z + s);
+                if constexpr (kTiled) {
+                    char* t = b.tiled + (size_t)(i >> 8) * 10240u;
+                    const uint32_t l = i & 255u;
+                    reinterpret_cast<float4*>(t)[l] = nA;
+                    reinterpret_cast<float4*>(t + 4096)[l] = nB;
+                    reinterpret_cast<float*>(t + 8192)[l] = fu[u] + 1.0f;
+                } else {
+                    b.A[i] = nA; b.B[i] = nB; b.fuel[i] = fu[u] + 1.0f;
+                }
+                const float4 lo = make_float4(s, a[u].x, a[u].y, a[u].z), hi = make_float4(bb[u].x, bb[u].y, bb[u].z, s);
+                if constexpr (kObsT) {
+                    const bool odd = (threadIdx.x & 1u) != 0u;
+                    const float4 snd = odd ? lo : hi;
+                    float4 rcv;
+                    rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, 1); rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, 1);
+                    rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, 1); rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, 1);
+                    const uint32_t er = i & ~1u, orow = i | 1u;
+                    st<kStHint>(&b.obs[2 * (size_t)er + (odd ? 1u : 0u)], odd ? rcv : lo);
+                    st<kStHint>(&b.obs[2 * (size_t)orow + (odd ? 1u : 0u)], odd ? hi : rcv);
+                } else {
+                    st<kStHint>(&b.obs[2 * (size_t)i], lo);
+                    st<kStHint>(&b.obs[2 * (size_t)i + 1], hi);
+                }
+                if constexpr (kReward) st<kStHint>(&b.rew[i], s);
+                if constexpr (kFlags) {
+                    st<kStHint>(&b.f0[i], (uint8_t)(s > 0.0f)); st<kStHint>(&b.f1[i], (uint8_t)(s < 1.0f));
+                    st<kStHint>(&b.f2[i], (uint8_t)(s == 2.0f));
+                }
+            }
+        }
+        if (!kPersist) break;
+    }
+}
+
+int main(int argc, char** argv) {
+    const uint32_t n = argc > 1 ? (uint32_t)atoll(argv[1]) : 16777216u;     // multiple of 512
+    Bufs b; float2* act;
+    CK(cudaMalloc(&b.A, 16ull * n)); CK(cudaMalloc(&b.B, 16ull * n)); CK(cudaMalloc(&b.obs, 32ull * n));
+    CK(cudaMalloc(&b.fuel, 4ull * n)); CK(cudaMalloc(&b.dry, 4ull * n)); CK(cudaMalloc(&b.rew, 4ull * n));
+    CK(cudaMalloc(&act, 8ull * n)); CK(cudaMalloc(&b.f0, n)); CK(cudaMalloc(&b.f1, n)); CK(cudaMalloc(&b.f2, n));
+    CK(cudaMalloc(&b.tiled, 40ull * n));
+    b.act = act;
+    CK(cudaMemset(b.A, 0, 16ull * n)); CK(cudaMemset(b.B, 0, 16ull * n)); CK(cudaMemset(b.fuel, 0, 4ull * n));
+    CK(cudaMemset(b.dry, 0, 4ull * n)); CK(cudaMemset(act, 0, 8ull * n)); CK(cudaMemset(b.tiled, 0, 40ull * n));
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int sms; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    auto time_it = [&](auto launch, const char* name, double bytes) {
+        for (int w = 0; w < 5; ++w) launch();
+        float best = 1e30f, tot = 0;
+        for (int r = 0; r < 20; ++r) {
+            cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1); best = ms < best ? ms : best; tot += ms;
+        }
+        printf("%-44s best %.3f ms %5.0f GB/s   mean %.3f ms %5.0f GB/s\n", name, best, bytes / best / 1e6, tot / 20, bytes / (tot / 20) / 1e6);
+        fflush(stdout);
+    };
+    // calibration on a 2 n float4 array pair (obs <- A|B region is too small; use tiled (40 n B) and obs (32 n B))
+    const size_t nc = 2ull * n;   // float4 elements (32 n bytes)
+    const float4* src = reinterpret_cast<const float4*>(b.tiled);
+    time_it([&] { read_kernel<<<sms * 8, 256>>>(src, b.rew, nc); }, "read-only float4, persistent 8/SM", 16.0 * nc);
+    time_it([&] { write_kernel<<<sms * 8, 256>>>(b.obs, nc); }, "write-only float4, persistent 8/SM", 16.0 * nc);
+    time_it([&] { copy_kernel<<<sms * 8, 256>>>(src, b.obs, nc); }, "copy float4, persistent 8/SM", 32.0 * nc);
+    time_it([&] { copy4_kernel<<<(unsigned)((nc + 1023) / 1024), 256>>>(src, b.obs, nc); }, "copy float4 x4, one tile per CTA", 32.0 * nc);
+    time_it([&] { cudaMemcpyAsync(b.obs, src, 16 * nc, cudaMemcpyDeviceToDevice); }, "cudaMemcpyAsync D2D", 32.0 * nc);
+
+    const unsigned tiles = n / 256;
+#define MIX(name, bytes, grid, ...) time_it([&] { mix_kernel<__VA_ARGS__><<<(grid), 256>>>(b, n); }, name, (bytes) * (double)n)
+    //                                       unroll obsT tiled persist ld st flags reward
+    MIX("mix base 4/SM", 123.0, sms * 4,          1, false, false, true, 0, 0, true, true);
+    MIX("mix T 4/SM", 123.0, sms * 4,             1, true, false, true, 0, 0, true, true);
+    MIX("mix T S 4/SM", 123.0, sms * 4,           1, true, true, true, 0, 0, true, true);
+    MIX("mix S 4/SM", 123.0, sms * 4,             1, false, true, true, 0, 0, true, true);
+    MIX("mix T N (one tile per CTA)", 123.0, tiles, 1, true, false, false, 0, 0, true, true);
+    MIX("mix T S N", 123.0, tiles,                1, true, true, false, 0, 0, true, true);
+    MIX("mix T N unroll2", 123.0, tiles / 2,      2, true, false, false, 0, 0, true, true);
+    MIX("mix T ld.cs 4/SM", 123.0, sms * 4,       1, true, false, true, 1, 0, true, true);
+    MIX("mix T ld.cg 4/SM", 123.0, sms * 4,       1, true, false, true, 2, 0, true, true);
+    MIX("mix T st.cs(outputs) 4/SM", 123.0, sms * 4, 1, true, false, true, 0, 1, true, true);
+    MIX("mix T ld.cs st.cs 4/SM", 123.0, sms * 4, 1, true, false, true, 1, 1, true, true);
+    MIX("mix T st.wt(outputs) 4/SM", 123.0, sms * 4, 1, true, false, true, 0, 3, true, true);
+    MIX("mix T no flags 4/SM (120 B)", 120.0, sms * 4, 1, true, false, true, 0, 0, false, true);
+    MIX("mix T no flags no reward 4/SM (116 B)", 116.0, sms * 4, 1, true, false, true, 0, 0, false, false);
+    MIX("mix T 8/SM", 123.0, sms * 8,             1, true, false, true, 0, 0, true, true);
+    MIX("mix T unroll2 4/SM", 123.0, sms * 4,     2, true, false, true, 0, 0, true, true);
+    MIX("mix T unroll2 8/SM", 123.0, sms * 8,     2, true, false, true, 0, 0, true, true);
+    MIX("mix T S unroll2 8/SM", 123.0, sms * 8,   2, true, true, true, 0, 0, true, true);
+    MIX("mix base unroll2 8/SM", 123.0, sms * 8,  2, false, false, true, 0, 0, true, true);
+    return 0;
+}

@@ -10,7 +10,9 @@ from .config import RlParams
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_NAME = "librocket_landing_b200.so"
-LIB_PATH = os.path.join(_PKG_DIR, LIB_NAME)
+# RL_B200_LIBRARY points the loader at another build of the SAME sources (tools/build_variants.py
+# makes them for kernel experiments); it is still this library or nothing -- there is no fallback.
+LIB_PATH = os.environ.get("RL_B200_LIBRARY") or os.path.join(_PKG_DIR, LIB_NAME)
 ABI_VERSION = 1
 
 # every symbol include/rocket_landing_b200.h declares

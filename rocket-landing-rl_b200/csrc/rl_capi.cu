@@ -38,7 +38,7 @@ struct RlEnv {
     rl::StatePlanes planes;
     void* state_buf = nullptr;
     bool owns_state = false;
-    double* stats = nullptr;          // device, RL_STATS_WORDS
+    double* stats = nullptr;          // device, rl::kStatSlots x RL_STATS_WORDS
     int64_t n = 0;
     int64_t gid0 = 0;
     uint64_t seed = 0;
@@ -48,6 +48,7 @@ struct RlEnv {
     int sms = 0;
     bool folded = false;              // constants equal the reference defaults: use the constexpr kernels
     int step_grid[2][2] = {{0, 0}, {0, 0}};   // [auto_reset][single_step]: SMs x resident CTAs (persistent grid)
+    int tiles_per_cta = -1;           // consecutive tiles per CTA of the step kernel; 0 = persistent grid, -1 = by launch size
     int64_t launches = 0;
     // host-buffer path (rl_step_host): device staging, allocated on first use
     void* h_stage = nullptr;
@@ -126,7 +127,18 @@ int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8
     const int64_t ctas = tile_end - tile_begin;                              // one tile of 256 rockets each
     if (ctas <= 0) return RL_OK;
     const int cap = e->step_grid[auto_reset ? 1 : 0][single ? 1 : 0];
-    const int grid = (int)(ctas < cap ? ctas : cap);
+    // Grid shape (profiles/README.md, "grid order"): large launches run `chunk` consecutive tiles per
+    // CTA, CTAs dispatched in address order by the hardware, which keeps the set of DRAM pages being
+    // streamed compact (+20 % bandwidth over a persistent strided grid at 64 Mi rockets); that needs
+    // at least ~6 waves of CTAs to balance, so smaller launches keep the persistent grid.
+    int chunk = e->tiles_per_cta;
+    if (chunk < 0) {
+        chunk = 0;
+        for (int c : {8, 4})
+            if (ctas >= (int64_t)6 * cap * c) { chunk = c; break; }
+    }
+    a.chunk = (uint32_t)chunk;
+    const int grid = a.chunk ? (int)((ctas + a.chunk - 1) / a.chunk) : (int)(ctas < cap ? ctas : cap);
     step_kernel_for(e->folded, auto_reset != 0, single)<<<grid, rl::kCtaThreads, 0, stream>>>(e->dev, a);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
@@ -229,8 +241,8 @@ int rl_create(const RlParams* params, int64_t n_envs, int64_t env_id_offset, uin
         e->owns_state = true;
     }
     e->planes = rl::carve_state(e->state_buf, n_envs);
-    if (cudaMalloc(&e->stats, RL_STATS_WORDS * sizeof(double)) != cudaSuccess ||
-        cudaMemset(e->stats, 0, RL_STATS_WORDS * sizeof(double)) != cudaSuccess ||
+    if (cudaMalloc(&e->stats, rl::kStatSlots * RL_STATS_WORDS * sizeof(double)) != cudaSuccess ||
+        cudaMemset(e->stats, 0, rl::kStatSlots * RL_STATS_WORDS * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&e->epoch, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemset(e->epoch, 0, sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc(&e->ticket, sizeof(unsigned int)) != cudaSuccess ||
@@ -245,6 +257,10 @@ int rl_create(const RlParams* params, int64_t n_envs, int64_t env_id_offset, uin
     const char* force_generic = getenv("RL_B200_GENERIC_KERNEL");
     e->folded = rl::matches_default(e->dev) && !(force_generic && force_generic[0] == '1');
     cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
+    if (const char* t = getenv("RL_B200_TILES_PER_CTA")) {      // experiment knob: force the grid shape
+        const long v = strtol(t, nullptr, 10);
+        if (v >= -1 && v <= 65536) e->tiles_per_cta = (int)v;
+    }
     for (int ar = 0; ar < 2; ++ar)
         for (int single = 0; single < 2; ++single) {
             StepKernel fn = step_kernel_for(e->folded, ar != 0, single != 0);
@@ -350,7 +366,7 @@ int rl_get_state(RlEnv* e, float* state_soa, void* stream) {
 int rl_stats(RlEnv* e, double* out16, int reset_after, void* stream) {
     if (!e || !out16) return fail(RL_E_INVALID, "rl_stats: null argument");
     DeviceGuard guard(e->device);
-    rl::stats_copy_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(e->stats, out16, reset_after);
+    rl::stats_copy_kernel<<<1, RL_STATS_WORDS * 32, 0, (cudaStream_t)stream>>>(e->stats, out16, reset_after);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
     return RL_OK;

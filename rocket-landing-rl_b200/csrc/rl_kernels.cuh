@@ -10,14 +10,19 @@
 // warp-wide access is one contiguous run (512 B in planes A / B, 128 B in fuel / dry, 256 B of
 // actions, 1 KiB of observations).
 //
-// Inputs are STAGED THROUGH SHARED MEMORY BY ASYNCHRONOUS COPIES (cp.async, SASS LDGSTS): at the
-// top of an iteration each thread issues the copies of ITS OWN rocket of the NEXT tile into the
-// other half of a two-stage ring, then waits only for the current tile's group.  The next tile's
-// bytes are therefore always in flight while the current one is computed, without holding
-// registers for them.  Because a thread only ever reads back what it copied itself there is no
+// Inputs are STAGED THROUGH SHARED MEMORY BY ASYNCHRONOUS COPIES (cp.async, SASS LDGSTS): each
+// iteration a thread waits for the copies of ITS OWN rocket of the current tile, reads them back,
+// and immediately issues the copies of the NEXT tile into the other half of a two-stage ring.  The
+// next tile's bytes are therefore always in flight while the current one is computed, without
+// holding registers for them.  Because a thread only ever reads back what it copied itself there is no
 // barrier, mbarrier or proxy fence in the loop, and warps never wait for one another (a warp on
 // the long reset path does not stall its CTA).  profiles/README.md records why this replaced the
 // two TMA (cp.async.bulk) designs tried first.
+//
+// Grid: large launches give every CTA `chunk` CONSECUTIVE tiles (8 x 256 rockets) and let the
+// hardware dispatch CTAs in address order, so the rockets being streamed at any moment form one
+// compact, advancing window of every plane; a persistent grid striding by gridDim.x (kept for
+// launches too small to fill six waves) scatters that window and loses ~20 % of HBM bandwidth.
 #pragma once
 #include <type_traits>
 
@@ -36,6 +41,18 @@ constexpr int kStages = RL_STAGES;   // depth of the shared-memory ring (tiles i
 constexpr int kPad = 256;            // planes are padded to a multiple of this many rockets
 #ifndef RL_MIN_CTAS
 #define RL_MIN_CTAS 4                // resident CTAs per SM the register allocator must allow
+#endif
+// How a tile's inputs reach the registers (build knob; profiles/README.md records the comparison):
+//   0  cp.async ring, next tile's copies issued BEFORE the current tile is read back
+//   1  cp.async ring, current tile read back first, then the next tile's copies issued
+//   2  no shared memory: the next tile is loaded into registers (LDG) while this one is computed
+#ifndef RL_LOAD_MODE
+#define RL_LOAD_MODE 1
+#endif
+// 1: lane pairs exchange observation halves so that every 128-bit store instruction of a warp
+// writes whole 32-byte sectors (16 rockets x 32 B) instead of half of each of 32 sectors
+#ifndef RL_OBS_TRANSPOSE
+#define RL_OBS_TRANSPOSE 1
 #endif
 
 struct StatePlanes {
@@ -77,6 +94,8 @@ struct StepArgs {
     unsigned long long* __restrict__ epoch_bump;    // device: epoch to advance when the launch ends, or null
     unsigned int* __restrict__ ticket;              // device: CTAs finished in this launch
     uint32_t tile_begin, tile_end;                  // tiles of 256 rockets this launch steps ([0, ceil(n/256)) = all)
+    uint32_t chunk;                                 // consecutive tiles per CTA (grid = ceil(tiles / chunk)); 0 = persistent
+                                                    // grid, CTA b walks tiles b, b + gridDim.x, ...
     int substeps;
 };
 
@@ -108,6 +127,19 @@ struct __align__(16) Stage {          // one tile's inputs, 12 KiB; thread t use
 // The launch epoch lives in device memory so that a CUDA-graph replay of the step advances the
 // Philox stream like an ordinary launch does.  Every CTA reads it on entry; the last CTA to
 // finish (ticket) bumps it for the next launch, which is stream-ordered after this one.
+// The step kernel splits this in two: a CTA takes its ticket as soon as all its threads have read
+// the epoch (the atomic's latency hides behind the CTA's work) and the holder of the last ticket
+// advances the epoch when it finishes -- by then every CTA of the launch has read the old value.
+__device__ __forceinline__ unsigned int epoch_take_ticket(unsigned int* ticket) {
+    __threadfence();                                   // this CTA's epoch reads (ordered by the barrier before) first
+    return atomicAdd(ticket, 1u);
+}
+__device__ __forceinline__ void epoch_bump_if_last(unsigned long long* epoch, unsigned int* ticket, unsigned int mine) {
+    if (mine == gridDim.x - 1) {
+        *ticket = 0u;
+        *epoch += 1ull;
+    }
+}
 __device__ __forceinline__ void epoch_bump(unsigned long long* epoch, unsigned int* ticket) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -124,6 +156,11 @@ __device__ __forceinline__ void epoch_bump(unsigned long long* epoch, unsigned i
 // ---- (the grid is persistent, so that is a few thousand global atomics per launch).  Only the
 // ---- per-class episode counts use shared-memory atomics, and those are native integer adds
 // ---- (a double atomicAdd on shared memory is a CAS loop -- far too slow for a per-step event).
+// The global accumulators are kStatSlots copies of the RL_STATS_WORDS vector (CTA b adds into copy
+// b mod kStatSlots; rl_stats sums them), so that a launch of tens of thousands of CTAs does not
+// serialise its reductions on thirteen addresses.
+constexpr int kStatSlots = 64;
+
 struct ThreadStats {
     float reward_sum = 0.0f, return_sum = 0.0f;
     int env_steps = 0, tip_steps = 0, nonfinite = 0, episodes = 0, length_sum = 0;
@@ -170,7 +207,8 @@ __device__ __forceinline__ void stats_flush(BlockStats& s, double* __restrict__ 
         s.sum[RL_S_TIME_LIMIT] = (double)s.cls[6];
     }
     __syncthreads();
-    if (threadIdx.x < RL_STATS_WORDS && s.sum[threadIdx.x] != 0.0) atomicAdd(&g[threadIdx.x], s.sum[threadIdx.x]);
+    if (threadIdx.x < RL_STATS_WORDS && s.sum[threadIdx.x] != 0.0)
+        atomicAdd(&g[(blockIdx.x % kStatSlots) * RL_STATS_WORDS + threadIdx.x], s.sum[threadIdx.x]);
 }
 
 __device__ __forceinline__ void load_rocket(const StatePlanes& st, uint32_t i, Rocket& r) {
@@ -198,6 +236,32 @@ __device__ __forceinline__ void out_store(T* p, T v) {
     __stcs(p, v);
 #else
     *p = v;
+#endif
+}
+
+// Observation rows of the warp's 32 rockets (row i = 32 B at obs + 2 i).  Plain version: two
+// 128-bit stores per lane, each instruction covering one half of every row.  Transposed version:
+// even lane 2j and odd lane 2j+1 swap one half each, so that instruction 1 writes the complete
+// rows of the even lanes and instruction 2 those of the odd lanes -- every sector written whole.
+__device__ __forceinline__ void store_obs(float4* __restrict__ obs, uint32_t i, uint32_t n, const float* o) {
+#if RL_OBS_TRANSPOSE
+    const bool odd = (threadIdx.x & 1u) != 0u;
+    // send: even lanes their high half, odd lanes their low half
+    const float s0 = odd ? o[0] : o[4], s1 = odd ? o[1] : o[5], s2 = odd ? o[2] : o[6], s3 = odd ? o[3] : o[7];
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    const float r2 = __shfl_xor_sync(0xffffffffu, s2, 1), r3 = __shfl_xor_sync(0xffffffffu, s3, 1);
+    const uint32_t even_row = i & ~1u, odd_row = i | 1u;          // the pair's two rockets
+    // instruction 1: row of the even lane -- even lane its own low half, odd lane the even lane's high half
+    const float4 v1 = odd ? make_float4(r0, r1, r2, r3) : make_float4(o[0], o[1], o[2], o[3]);
+    // instruction 2: row of the odd lane -- even lane the odd lane's low half, odd lane its own high half
+    const float4 v2 = odd ? make_float4(o[4], o[5], o[6], o[7]) : make_float4(r0, r1, r2, r3);
+    if (even_row < n) out_store(&obs[2 * (size_t)even_row + (odd ? 1u : 0u)], v1);
+    if (odd_row < n) out_store(&obs[2 * (size_t)odd_row + (odd ? 1u : 0u)], v2);
+#else
+    if (i < n) {
+        out_store(&obs[2 * (size_t)i], make_float4(o[0], o[1], o[2], o[3]));
+        out_store(&obs[2 * (size_t)i + 1], make_float4(o[4], o[5], o[6], o[7]));
+    }
 #endif
 }
 
@@ -265,15 +329,19 @@ template <> struct ParamSel<DefaultParams> {
 template <bool kAutoReset, bool kSingleStep, class PP>
 __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __grid_constant__ DevParams Prt,
                                                                         const __grid_constant__ StepArgs a) {
+#if RL_LOAD_MODE != 2
     __shared__ Stage ring[kStages];
+#endif
     __shared__ BlockStats bs;
 
     const auto& P = ParamSel<PP>::get(Prt);
     const uint32_t tid = threadIdx.x;
-    const uint32_t n_tiles = a.tile_end;                // one past the last tile of this launch
-    const uint32_t tile0 = a.tile_begin + blockIdx.x;   // this CTA's first tile
-    const uint32_t stride = gridDim.x;
+    // persistent grid (chunk == 0): tiles b, b + gridDim.x, ...; otherwise `chunk` consecutive tiles
+    const uint32_t stride = a.chunk ? 1u : gridDim.x;
+    const uint32_t tile0 = a.tile_begin + (a.chunk ? blockIdx.x * a.chunk : blockIdx.x);   // this CTA's first tile
+    const uint32_t n_tiles = a.chunk ? min(a.tile_end, tile0 + a.chunk) : a.tile_end;       // one past its last
 
+#if RL_LOAD_MODE != 2
     // this thread's rocket of `tile` -> stage s (state planes are padded, so only the caller's
     // action array needs a bounds guard: out-of-range rockets get a zero action)
     auto prefetch = [&](uint32_t tile, uint32_t s) {
@@ -285,40 +353,92 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
         const bool in = j < a.n;
         cp_async_8_zfill(&ring[s].act[tid], a.actions + (in ? j : 0u), in ? 8u : 0u);
     };
+#else
+    // this thread's rocket of `tile` -> registers; consumed one iteration later, so the loads stay
+    // in flight while the current tile is computed (L2-only loads: every word is read exactly once)
+    float4 nA, nB;
+    float nfuel, ndry;
+    float2 nact;
+    auto prefetch_regs = [&](uint32_t tile) {
+        const uint32_t j = tile * kCtaThreads + tid;
+        nA = __ldcg(a.st.A + j);
+        nB = __ldcg(a.st.B + j);
+        nfuel = __ldcg(a.st.fuel + j);
+        ndry = __ldcg(a.st.dry + j);
+        nact = (j < a.n) ? __ldcs(a.actions + j) : make_float2(0.0f, 0.0f);
+    };
+#endif
 
     stats_init(bs);
+#if RL_LOAD_MODE != 2
 #pragma unroll
     for (uint32_t d = 0; d + 1 < (uint32_t)kStages; ++d) {   // prologue: the first kStages - 1 tiles
         const uint32_t tile = tile0 + d * stride;
         if (tile < n_tiles) prefetch(tile, d);
         cp_async_commit();
     }
-    __syncthreads();                                    // stats_init visible CTA-wide
+#else
+    if (tile0 < n_tiles) prefetch_regs(tile0);
+#endif
     const uint64_t epoch = *a.epoch;
+    __syncthreads();                                    // stats_init visible CTA-wide; every thread has read the epoch
+    unsigned int my_ticket = 0u;
+    if (a.epoch_bump && tid == 0) my_ticket = epoch_take_ticket(a.ticket);   // uniform over the grid
     ThreadStats ts;
 
+#if RL_LOAD_MODE != 2
     uint32_t s = 0;
+#endif
     for (uint32_t tile = tile0; tile < n_tiles; tile += stride) {
         const uint32_t i = tile * kCtaThreads + tid;
         const bool valid = i < a.n;
 
-        const uint32_t next = tile + (uint32_t)(kStages - 1) * stride;
-        const uint32_t s_next = (s == 0u) ? (uint32_t)(kStages - 1) : s - 1u;   // the stage drained last iteration
-        if (next < n_tiles) prefetch(next, s_next);     // kStages - 1 tiles in flight while this one is computed
-        cp_async_commit();                              // (possibly empty) keeps the group count uniform
-        cp_async_wait<kStages - 1>();                   // everything but the newest kStages - 1 groups has landed
-
         Rocket r;
+        float2 act;
+#if RL_LOAD_MODE == 0
         {
+            const uint32_t next = tile + (uint32_t)(kStages - 1) * stride;
+            const uint32_t s_next = (s == 0u) ? (uint32_t)(kStages - 1) : s - 1u;   // the stage drained last iteration
+            if (next < n_tiles) prefetch(next, s_next);     // kStages - 1 tiles in flight while this one is computed
+            cp_async_commit();                              // (possibly empty) keeps the group count uniform
+            cp_async_wait<kStages - 1>();                   // everything but the newest kStages - 1 groups has landed
             const float4 va = ring[s].A[tid];
             const float4 vb = ring[s].B[tid];
             r.fuel = ring[s].fuel[tid];
             r.dry = ring[s].dry[tid];
             r.x = va.x; r.y = va.y; r.ang = va.z; r.meta = __float_as_uint(va.w);
             r.sx = vb.x; r.sy = vb.y; r.sang = vb.z; r.ep_ret = vb.w;
+            act = ring[s].act[tid];
+            s = (s + 1u == (uint32_t)kStages) ? 0u : s + 1u;
         }
-        const float2 act = ring[s].act[tid];
-        s = (s + 1u == (uint32_t)kStages) ? 0u : s + 1u;
+#elif RL_LOAD_MODE == 1
+        {
+            cp_async_wait<kStages - 2>();                   // this tile's group has landed
+            const float4 va = ring[s].A[tid];
+            const float4 vb = ring[s].B[tid];
+            r.fuel = ring[s].fuel[tid];
+            r.dry = ring[s].dry[tid];
+            r.x = va.x; r.y = va.y; r.ang = va.z; r.meta = __float_as_uint(va.w);
+            r.sx = vb.x; r.sy = vb.y; r.sang = vb.z; r.ep_ret = vb.w;
+            act = ring[s].act[tid];
+            // the shared-memory reads above are complete (their values are in registers) before the
+            // copies below are issued by the same thread, so refilling a stage is hazard-free
+            const uint32_t next = tile + (uint32_t)(kStages - 1) * stride;
+            const uint32_t s_next = (kStages == 2) ? (s ^ 1u) : ((s == 0u) ? (uint32_t)(kStages - 1) : s - 1u);
+            if (next < n_tiles) prefetch(next, s_next);
+            cp_async_commit();
+            s = (s + 1u == (uint32_t)kStages) ? 0u : s + 1u;
+        }
+#else
+        {
+            r.x = nA.x; r.y = nA.y; r.ang = nA.z; r.meta = __float_as_uint(nA.w);
+            r.sx = nB.x; r.sy = nB.y; r.sang = nB.z; r.ep_ret = nB.w;
+            r.fuel = nfuel; r.dry = ndry;
+            act = nact;
+            const uint32_t next = tile + stride;
+            if (next < n_tiles) prefetch_regs(next);
+        }
+#endif
 
         StepResult o;
         float reward;
@@ -351,19 +471,20 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
         const int landing = o.landing;
         if (done_mask) warp_episode_end<kAutoReset>(P, a, bs, ts, done_mask, done, i, epoch, r, o);
 
+        store_obs(a.obs, i, a.n, o.obs);
         if (valid) {
             store_rocket(a.st, i, r, false);
-            out_store(&a.obs[2 * (size_t)i], make_float4(o.obs[0], o.obs[1], o.obs[2], o.obs[3]));
-            out_store(&a.obs[2 * (size_t)i + 1], make_float4(o.obs[4], o.obs[5], o.obs[6], o.obs[7]));
             out_store(&a.reward[i], reward);
             out_store(&a.terminated[i], (uint8_t)(terminated ? 1 : 0));
             out_store(&a.truncated[i], (uint8_t)(truncated ? 1 : 0));
             if (a.landing) out_store(reinterpret_cast<uint8_t*>(&a.landing[i]), (uint8_t)landing);
         }
     }
+#if RL_LOAD_MODE != 2
     cp_async_wait<0>();
+#endif
     stats_flush(bs, a.stats, ts);
-    if (a.epoch_bump) epoch_bump(a.epoch_bump, a.ticket);   // uniform over the grid
+    if (a.epoch_bump && tid == 0) epoch_bump_if_last(a.epoch_bump, a.ticket, my_ticket);
 }
 
 // RocketLandingEnv.reset (lander.py:168-186) for all / masked rockets.
@@ -415,13 +536,20 @@ __global__ void __launch_bounds__(kCtaThreads) get_state_kernel(StatePlanes st, 
     }
 }
 
-// rl_stats: copy (and optionally clear) the accumulators on the stream.
-__global__ void stats_copy_kernel(double* __restrict__ acc, double* __restrict__ out, int reset_after) {
-    const int t = threadIdx.x;
-    if (t < RL_STATS_WORDS) {
-        out[t] = acc[t];
-        if (reset_after) acc[t] = 0.0;
+// rl_stats: sum the kStatSlots copies of the accumulators into out[RL_STATS_WORDS] (and optionally
+// clear them), on the stream.  One CTA of RL_STATS_WORDS x 32 threads: thread (w, l) sums word w of
+// copies l, l + 32, ...; a warp shuffle finishes each word.
+__global__ void __launch_bounds__(RL_STATS_WORDS * 32) stats_copy_kernel(double* __restrict__ acc, double* __restrict__ out,
+                                                                          int reset_after) {
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    double v = 0.0;
+    for (int sl = l; sl < kStatSlots; sl += 32) {
+        v += acc[sl * RL_STATS_WORDS + w];
+        if (reset_after) acc[sl * RL_STATS_WORDS + w] = 0.0;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (l == 0) out[w] = v;
 }
 
 }  // namespace rl
