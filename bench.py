@@ -163,6 +163,9 @@ def main() -> None:
     ap.add_argument("--spinup", type=int, default=2000,
                     help="untimed env steps before the warm-up, so that episodes are desynchronised "
                          "(steady state: ~1/113 of the rockets reset per step, as in a long rollout)")
+    ap.add_argument("--cooldown", type=float, default=0.0,
+                    help="experiment only: idle this many seconds before the timed region (lets the board "
+                         "leave its power cap) and report the per-step times of the first and last steps")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -215,6 +218,8 @@ def main() -> None:
 
     sampler = ClockSampler(local_rank)
     barrier()
+    if args.cooldown > 0:
+        time.sleep(args.cooldown)
     if rank == 0:
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -234,6 +239,7 @@ def main() -> None:
     elapsed_ms = ev0.elapsed_time(ev1)
     kernel_ms = sum(a.elapsed_time(b) for a, b in zip(k0, k1)) / max(args.steps, 1)
     launches = env.launch_count - launches0
+    per_step = [a.elapsed_time(b) for a, b in zip(k0, k1)]
     t_all = torch.tensor([elapsed_ms, kernel_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
@@ -305,6 +311,10 @@ def main() -> None:
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "episodes": final.episodes, "mean_episode_length": final.mean_length,
         }
+        if args.cooldown > 0:
+            m = max(1, min(10, len(per_step) // 2))
+            line["cooldown"] = {"seconds": args.cooldown, "first_steps_ms": sum(per_step[:m]) / m,
+                                "last_steps_ms": sum(per_step[-m:]) / m}
         if world == 1 and not args.no_cpu_baseline:
             from oracle import c_oracle
             c_oracle.build()

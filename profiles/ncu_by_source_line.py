@@ -9,8 +9,12 @@ rockets = int(sys.argv[4]) if len(sys.argv) > 4 else 16777216
 N = rockets / 32
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith('.cubin')][0]
-sass = subprocess.run(['nvdisasm', '-g', '-c', cubin], cwd=tmp, capture_output=True, text=True).stdout.splitlines()
+sass = []
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith('.cubin')):   # the one that holds the kernel
+    out = subprocess.run(['nvdisasm', '-g', '-c', cubin], cwd=tmp, capture_output=True, text=True).stdout
+    if sub in out:
+        sass = out.splitlines()
+        break
 # walk the kernel's section: remember the current "//## File ..., line N" for every instruction
 lines, cur, inside = [], None, False
 for ln in sass:
@@ -39,7 +43,7 @@ for (loc, text), row in zip(lines, data):
 tot = sum(agg.values()); ts = sum(samp.values())
 print(f'total {tot / N:.1f} warp-instructions per warp-step')
 srcs = {}
-for (f, l), c in agg.most_common(45):
+for (f, l), c in agg.most_common(int(os.environ.get('TOP', '45'))):
     if f not in srcs:
         p = os.path.join(os.path.dirname(os.path.abspath(lib)), 'csrc', f)
         srcs[f] = open(p).read().splitlines() if os.path.exists(p) else []

@@ -124,6 +124,64 @@ __global__ void __launch_bounds__(256) mix_kernel(Bufs b, uint32_t n) {
     }
 }
 
+
+// The step kernel's actual skeleton: `chunk` consecutive tiles per CTA, per-thread cp.async
+// two-stage ring (read back, then prefetch the next tile), observation rows transposed through
+// shared memory, and `work` dependent FMAs per rocket standing in for the physics.
+struct __align__(16) RingStage { float4 A[256]; float4 B[256]; float2 act[256]; float fuel[256]; float dry[256]; };
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int kBytes> __device__ __forceinline__ void cpa(void* dst, const void* src) {
+    if constexpr (kBytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(kBytes) : "memory");
+}
+template <int kStages>
+__global__ void __launch_bounds__(256, 4) mix_ring(Bufs b, uint32_t n_tiles_total, uint32_t chunk, int work) {
+    __shared__ RingStage ring[kStages];
+    __shared__ float4 ostage[8][64];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t tile0 = blockIdx.x * chunk, tile_end = min(n_tiles_total, tile0 + chunk);
+    auto prefetch = [&](uint32_t tile, uint32_t s) {
+        const uint32_t j = tile * 256u + tid;
+        cpa<16>(&ring[s].A[tid], b.A + j); cpa<16>(&ring[s].B[tid], b.B + j);
+        cpa<4>(&ring[s].fuel[tid], b.fuel + j); cpa<4>(&ring[s].dry[tid], b.dry + j);
+        cpa<8>(&ring[s].act[tid], b.act + j);
+    };
+#pragma unroll
+    for (int d = 0; d + 1 < kStages; ++d) {
+        if (tile0 + d < tile_end) prefetch(tile0 + d, d);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    uint32_t s = 0;
+    for (uint32_t tile = tile0; tile < tile_end; ++tile) {
+        const uint32_t i = tile * 256u + tid;
+        asm volatile("cp.async.wait_group %0;" ::"n"(kStages - 2) : "memory");
+        const float4 a = ring[s].A[tid], bb = ring[s].B[tid];
+        const float fu = ring[s].fuel[tid], d = ring[s].dry[tid];
+        const float2 ac = ring[s].act[tid];
+        const uint32_t next = tile + kStages - 1;
+        const uint32_t s_next = (kStages == 2) ? (s ^ 1u) : ((s == 0u) ? (uint32_t)(kStages - 1) : s - 1u);
+        if (next < tile_end) prefetch(next, s_next);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        s = (s + 1u == (uint32_t)kStages) ? 0u : s + 1u;
+        float sacc = a.x + bb.y + fu * d + ac.x * ac.y;
+        for (int k = 0; k < work; ++k) sacc = fmaf(sacc, 0.999f, 0.001f);      // dependent chain, `work` issue slots
+        const float4 nA = make_float4(a.y, a.x, a.w + sacc, a.z), nB = make_float4(bb.y, bb.x, bb.w, bb.z + sacc);
+        b.A[i] = nA; b.B[i] = nB; b.fuel[i] = fu + 1.0f;
+        float4* st = ostage[tid >> 5];
+        const uint32_t w = (lane >> 2) & 1u;
+        st[(2u * lane) ^ w] = make_float4(sacc, a.x, a.y, a.z);
+        st[(2u * lane + 1u) ^ w] = make_float4(bb.x, bb.y, bb.z, sacc);
+        __syncwarp();
+        const uint32_t c = lane ^ ((lane >> 3) & 1u);
+        const float4 v1 = st[c], v2 = st[32u + c];
+        __syncwarp();
+        const uint32_t row0 = i - lane;
+        b.obs[2 * (size_t)row0 + lane] = v1; b.obs[2 * (size_t)row0 + 32u + lane] = v2;
+        b.rew[i] = sacc;
+        b.f0[i] = sacc > 0.0f; b.f1[i] = sacc < 1.0f; b.f2[i] = (uint8_t)(sacc == 2.0f);
+    }
+}
+
 int main(int argc, char** argv) {
     const uint32_t n = argc > 1 ? (uint32_t)atoll(argv[1]) : 16777216u;     // multiple of 512
     Bufs b; float2* act;
@@ -156,6 +214,42 @@ int main(int argc, char** argv) {
     time_it([&] { cudaMemcpyAsync(b.obs, src, 16 * nc, cudaMemcpyDeviceToDevice); }, "cudaMemcpyAsync D2D", 32.0 * nc);
 
     const unsigned tiles = n / 256;
+    if (argc > 2 && argv[2][0] == 'r') {
+        // ring mode: the step kernel's skeleton with `work` dependent FMAs per rocket
+        for (int work : {0, 100, 200, 300, 400, 600})
+            for (unsigned chunk : {8u}) {
+                char name[64];
+                snprintf(name, sizeof name, "ring s2 chunk %u work %d", chunk, work);
+                time_it([&] { mix_ring<2><<<(tiles + chunk - 1) / chunk, 256>>>(b, tiles, chunk, work); }, name, 123.0 * n);
+                snprintf(name, sizeof name, "ring s3 chunk %u work %d", chunk, work);
+                time_it([&] { mix_ring<3><<<(tiles + chunk - 1) / chunk, 256>>>(b, tiles, chunk, work); }, name, 123.0 * n);
+            }
+        for (unsigned chunk : {1u, 2u, 4u, 16u, 32u}) {
+            char name[64];
+            snprintf(name, sizeof name, "ring s2 chunk %u work 0", chunk);
+            time_it([&] { mix_ring<2><<<(tiles + chunk - 1) / chunk, 256>>>(b, tiles, chunk, 0); }, name, 123.0 * n);
+        }
+        return 0;
+    }
+    if (argc > 2) {
+        // sustained mode: the same kernel back to back for ~4 s, GB/s per batch of launches -- does the
+        // attainable bandwidth hold once the board sits at its power cap (as it does inside bench.py)?
+        auto sustain = [&](auto launch, const char* name, double bytes, int per_batch) {
+            for (int b = 0; b < 16; ++b) {
+                cudaEventRecord(e0);
+                for (int k = 0; k < per_batch; ++k) launch();
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                printf("%-40s batch %2d: %6.0f GB/s (%.3f ms per launch)\n", name, b, bytes * per_batch / ms / 1e6, ms / per_batch);
+                fflush(stdout);
+            }
+        };
+        const int pb = (int)(250.0 / (123.0 * n / 6.0e9) + 1);      // ~0.25 s per batch
+        sustain([&] { copy4_kernel<<<(unsigned)((nc + 1023) / 1024), 256>>>(src, b.obs, nc); }, "copy float4 x4, one tile per CTA", 32.0 * nc, pb * 2);
+        sustain([&] { mix_kernel<1, true, false, false, 0, 0, true, true><<<tiles, 256>>>(b, n); }, "mix T N (one tile per CTA)", 123.0 * n, pb);
+        sustain([&] { mix_kernel<1, true, false, true, 0, 0, true, true><<<sms * 4, 256>>>(b, n); }, "mix T 4/SM (persistent)", 123.0 * n, pb);
+        return 0;
+    }
 #define MIX(name, bytes, grid, ...) time_it([&] { mix_kernel<__VA_ARGS__><<<(grid), 256>>>(b, n); }, name, (bytes) * (double)n)
     //                                       unroll obsT tiled persist ld st flags reward
     MIX("mix base 4/SM", 123.0, sms * 4,          1, false, false, true, 0, 0, true, true);

@@ -69,16 +69,20 @@ int grid_for(const RlEnv* e, int64_t n) {
 
 using StepKernel = void (*)(const rl::DevParams, const rl::StepArgs);
 
-// [folded constants][auto_reset][single_step]
-StepKernel step_kernel_for(bool folded, bool auto_reset, bool single) {
+// [folded constants][auto_reset][single_step][chunked grid]
+StepKernel step_kernel_for(bool folded, bool auto_reset, bool single, bool chunked) {
     using rl::DefaultParams;
     using rl::DevParams;
-    static const StepKernel table[2][2][2] = {
-        {{rl::step_kernel<false, false, DevParams>, rl::step_kernel<false, true, DevParams>},
-         {rl::step_kernel<true, false, DevParams>, rl::step_kernel<true, true, DevParams>}},
-        {{rl::step_kernel<false, false, DefaultParams>, rl::step_kernel<false, true, DefaultParams>},
-         {rl::step_kernel<true, false, DefaultParams>, rl::step_kernel<true, true, DefaultParams>}}};
-    return table[folded ? 1 : 0][auto_reset ? 1 : 0][single ? 1 : 0];
+    static const StepKernel table[2][2][2][2] = {
+        {{{rl::step_kernel<false, false, false, DevParams>, rl::step_kernel<false, false, true, DevParams>},
+          {rl::step_kernel<false, true, false, DevParams>, rl::step_kernel<false, true, true, DevParams>}},
+         {{rl::step_kernel<true, false, false, DevParams>, rl::step_kernel<true, false, true, DevParams>},
+          {rl::step_kernel<true, true, false, DevParams>, rl::step_kernel<true, true, true, DevParams>}}},
+        {{{rl::step_kernel<false, false, false, DefaultParams>, rl::step_kernel<false, false, true, DefaultParams>},
+          {rl::step_kernel<false, true, false, DefaultParams>, rl::step_kernel<false, true, true, DefaultParams>}},
+         {{rl::step_kernel<true, false, false, DefaultParams>, rl::step_kernel<true, false, true, DefaultParams>},
+          {rl::step_kernel<true, true, false, DefaultParams>, rl::step_kernel<true, true, true, DefaultParams>}}}};
+    return table[folded ? 1 : 0][auto_reset ? 1 : 0][single ? 1 : 0][chunked ? 1 : 0];
 }
 
 struct DeviceGuard {
@@ -139,7 +143,7 @@ int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8
     }
     a.chunk = (uint32_t)chunk;
     const int grid = a.chunk ? (int)((ctas + a.chunk - 1) / a.chunk) : (int)(ctas < cap ? ctas : cap);
-    step_kernel_for(e->folded, auto_reset != 0, single)<<<grid, rl::kCtaThreads, 0, stream>>>(e->dev, a);
+    step_kernel_for(e->folded, auto_reset != 0, single, chunk != 0)<<<grid, rl::kCtaThreads, 0, stream>>>(e->dev, a);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
     return RL_OK;
@@ -263,12 +267,14 @@ int rl_create(const RlParams* params, int64_t n_envs, int64_t env_id_offset, uin
     }
     for (int ar = 0; ar < 2; ++ar)
         for (int single = 0; single < 2; ++single) {
-            StepKernel fn = step_kernel_for(e->folded, ar != 0, single != 0);
             int per_sm = 0;
-            // each CTA stages its warps' tiles in ~25 KiB of static shared memory: ask for the largest
+            // each CTA stages its warps' tiles in ~33 KiB of static shared memory: ask for the largest
             // carve-out so that registers, not shared memory, bound the resident CTAs
-            cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, rl::kCtaThreads, 0);
+            for (int chunked = 1; chunked >= 0; --chunked) {     // (both grid shapes have the same footprint)
+                StepKernel fn = step_kernel_for(e->folded, ar != 0, single != 0, chunked != 0);
+                cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, rl::kCtaThreads, 0);
+            }
             if (e->sms <= 0 || per_sm <= 0) {
                 rl_destroy(e);
                 return fail(RL_E_CUDA, "rl_create: occupancy query failed (no sm_100a image for this device?): %s",

@@ -64,13 +64,18 @@ __device__ __forceinline__ float rl_sqrt(float x) {
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float rl_div_fast(float a, float b) { return __fdividef(a, b); }
+// 1/x for x >= 1 (no denormal / overflow handling needed): bare MUFU.RCP, 1 ulp
+__device__ __forceinline__ float rl_rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ uint32_t rl_f2u(float f) { return __float_as_uint(f); }
 __device__ __forceinline__ float rl_u2f(uint32_t u) { return __uint_as_float(u); }
 #else
 inline float rl_rcp(float x) { return 1.0f / x; }
 inline float rl_sqrt(float x) { return std::sqrt(x); }
-inline float rl_div_fast(float a, float b) { return a / b; }
+inline float rl_rcp_fast(float x) { return 1.0f / x; }
 inline uint32_t rl_f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline float rl_u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 #endif
@@ -328,7 +333,7 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_
     const float t2 = th_raw * (-vy_a) * af * (1.0f + fminf(1.0f, avy * 0.1f)) * P.k_throttle_descent;
     total += descending ? t2 : 0.0f;
     // 3. free fall (reward.py:190-201)
-    const float prox = 1.0f + rl_div_fast(8.0f, fmaxf(y_a, 1.0f));
+    const float prox = fmaf(8.0f, rl_rcp_fast(fmaxf(y_a, 1.0f)), 1.0f);
     const float t3 = P.k_free_fall * (-vy_a) * prox * (1.0f + fminf(1.0f, avy * (1.0f / 15.0f)));
     total -= (descending && th_raw < P.throttle_lo_lt) ? t3 : 0.0f;
     // 4. throttle while tilted (reward.py:205-219)

@@ -239,25 +239,30 @@ __device__ __forceinline__ void out_store(T* p, T v) {
 #endif
 }
 
-// Observation rows of the warp's 32 rockets (row i = 32 B at obs + 2 i).  Plain version: two
-// 128-bit stores per lane, each instruction covering one half of every row.  Transposed version:
-// even lane 2j and odd lane 2j+1 swap one half each, so that instruction 1 writes the complete
-// rows of the even lanes and instruction 2 those of the odd lanes -- every sector written whole.
-__device__ __forceinline__ void store_obs(float4* __restrict__ obs, uint32_t i, uint32_t n, const float* o) {
+// Observation rows of the warp's 32 rockets (row i = 32 B at obs + 2 i).  Every lane holds one
+// row in registers; written directly that is two 128-bit stores per lane, each instruction
+// covering HALF of every one of 32 sectors.  Instead the warp transposes through 1 KiB of shared
+// memory (2 STS.128 + 2 LDS.128, 16-byte chunks XOR-swizzled so neither side has bank conflicts)
+// and stores two contiguous 512-byte runs: every instruction writes four whole 128-byte lines
+// (+3.5 % bandwidth on the whole kernel, profiles/README.md).
+struct __align__(16) ObsStage { float4 chunk[64]; };      // one warp's 32 rows of 2 x 16 B
+
+__device__ __forceinline__ void store_obs(ObsStage& st, float4* __restrict__ obs, uint32_t i, uint32_t n, const float* o) {
 #if RL_OBS_TRANSPOSE
-    const bool odd = (threadIdx.x & 1u) != 0u;
-    // send: even lanes their high half, odd lanes their low half
-    const float s0 = odd ? o[0] : o[4], s1 = odd ? o[1] : o[5], s2 = odd ? o[2] : o[6], s3 = odd ? o[3] : o[7];
-    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
-    const float r2 = __shfl_xor_sync(0xffffffffu, s2, 1), r3 = __shfl_xor_sync(0xffffffffu, s3, 1);
-    const uint32_t even_row = i & ~1u, odd_row = i | 1u;          // the pair's two rockets
-    // instruction 1: row of the even lane -- even lane its own low half, odd lane the even lane's high half
-    const float4 v1 = odd ? make_float4(r0, r1, r2, r3) : make_float4(o[0], o[1], o[2], o[3]);
-    // instruction 2: row of the odd lane -- even lane the odd lane's low half, odd lane its own high half
-    const float4 v2 = odd ? make_float4(o[4], o[5], o[6], o[7]) : make_float4(r0, r1, r2, r3);
-    if (even_row < n) out_store(&obs[2 * (size_t)even_row + (odd ? 1u : 0u)], v1);
-    if (odd_row < n) out_store(&obs[2 * (size_t)odd_row + (odd ? 1u : 0u)], v2);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t w = (lane >> 2) & 1u;                  // chunk c lives at c ^ ((c >> 3) & 1); c = 2 lane (+1)
+    st.chunk[(2u * lane) ^ w] = make_float4(o[0], o[1], o[2], o[3]);
+    st.chunk[(2u * lane + 1u) ^ w] = make_float4(o[4], o[5], o[6], o[7]);
+    __syncwarp();
+    const uint32_t c = lane ^ ((lane >> 3) & 1u);
+    const float4 v1 = st.chunk[c], v2 = st.chunk[32u + c];
+    __syncwarp();                                         // the stage is rewritten next iteration
+    const uint32_t row0 = i - lane;                       // the warp's first rocket
+    const uint32_t r1 = row0 + (lane >> 1), r2 = r1 + 16u;
+    if (r1 < n) out_store(&obs[2 * (size_t)row0 + lane], v1);
+    if (r2 < n) out_store(&obs[2 * (size_t)row0 + 32u + lane], v2);
 #else
+    (void)st;
     if (i < n) {
         out_store(&obs[2 * (size_t)i], make_float4(o[0], o[1], o[2], o[3]));
         out_store(&obs[2 * (size_t)i + 1], make_float4(o[4], o[5], o[6], o[7]));
@@ -324,22 +329,23 @@ template <> struct ParamSel<DefaultParams> {
 // The environment step (lander.py:188-255 for every rocket) + VecEnv auto-reset.
 //   kAutoReset   reset done rockets in the same launch (scripts/train.py:82-88 contract)
 //   kSingleStep  substeps == 1 (the reference's step): no substep loop
+//   kChunked     CTA b steps the a.chunk consecutive tiles from b * a.chunk (large launches);
+//                otherwise persistent grid, CTA b walks tiles b, b + gridDim.x, ...
 //   PP           DevParams (runtime constants) or DefaultParams (reference config.yaml folded in)
-// Persistent grid: CTA b walks tiles b, b + gridDim.x, ... of 256 rockets.
-template <bool kAutoReset, bool kSingleStep, class PP>
+template <bool kAutoReset, bool kSingleStep, bool kChunked, class PP>
 __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __grid_constant__ DevParams Prt,
                                                                         const __grid_constant__ StepArgs a) {
 #if RL_LOAD_MODE != 2
     __shared__ Stage ring[kStages];
 #endif
     __shared__ BlockStats bs;
+    __shared__ ObsStage obs_stage[kCtaThreads / 32];
 
     const auto& P = ParamSel<PP>::get(Prt);
     const uint32_t tid = threadIdx.x;
-    // persistent grid (chunk == 0): tiles b, b + gridDim.x, ...; otherwise `chunk` consecutive tiles
-    const uint32_t stride = a.chunk ? 1u : gridDim.x;
-    const uint32_t tile0 = a.tile_begin + (a.chunk ? blockIdx.x * a.chunk : blockIdx.x);   // this CTA's first tile
-    const uint32_t n_tiles = a.chunk ? min(a.tile_end, tile0 + a.chunk) : a.tile_end;       // one past its last
+    const uint32_t stride = kChunked ? 1u : gridDim.x;
+    const uint32_t tile0 = a.tile_begin + (kChunked ? blockIdx.x * a.chunk : blockIdx.x);   // this CTA's first tile
+    const uint32_t n_tiles = kChunked ? min(a.tile_end, tile0 + a.chunk) : a.tile_end;       // one past its last
 
 #if RL_LOAD_MODE != 2
     // this thread's rocket of `tile` -> stage s (state planes are padded, so only the caller's
@@ -446,9 +452,11 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
         if constexpr (kSingleStep) {
             rocket_step(P, r, act.x, act.y, o);
             reward = o.reward;
+            // (padding rockets beyond n hold the all-zero state rl_create wrote and nothing ever
+            // overwrites: massless, never tipped, never non-finite -- only the counts need `valid`)
             ts.env_steps += valid ? 1 : 0;
-            ts.tip_steps += (valid && o.tipped) ? 1 : 0;
-            ts.nonfinite += (valid && o.nonfinite) ? 1 : 0;
+            ts.tip_steps += o.tipped ? 1 : 0;
+            ts.nonfinite += o.nonfinite ? 1 : 0;
             done = valid && (o.terminated || o.truncated);
         } else {
             reward = 0.0f;
@@ -457,8 +465,8 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
                 rocket_advance(P, r, act.x, act.y, o, k > 0);     // potential carried across substeps
                 reward += o.reward;
                 ts.env_steps += valid ? 1 : 0;
-                ts.tip_steps += (valid && o.tipped) ? 1 : 0;
-                ts.nonfinite += (valid && o.nonfinite) ? 1 : 0;
+                ts.tip_steps += o.tipped ? 1 : 0;
+                ts.nonfinite += o.nonfinite ? 1 : 0;
                 done = valid && (o.terminated || o.truncated);
                 if (done) break;                         // stop integrating at the first done
             }
@@ -471,7 +479,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
         const int landing = o.landing;
         if (done_mask) warp_episode_end<kAutoReset>(P, a, bs, ts, done_mask, done, i, epoch, r, o);
 
-        store_obs(a.obs, i, a.n, o.obs);
+        store_obs(obs_stage[tid >> 5], a.obs, i, a.n, o.obs);
         if (valid) {
             store_rocket(a.st, i, r, false);
             out_store(&a.reward[i], reward);
