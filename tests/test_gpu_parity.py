@@ -448,6 +448,41 @@ def test_generic_kernel_parity_with_the_reference(torch, golden_dir):
     rep.assert_ok(max_guard_events=8)
 
 
+@pytest.mark.parametrize("tiles_per_cta", [1, 3, 8])
+def test_grid_shapes_are_bitwise_identical(torch, monkeypatch, tiles_per_cta):
+    """The step kernel runs either a persistent strided grid (small launches) or `chunk`
+    consecutive tiles per CTA in address order (large launches).  Both
+    instantiations must produce the same bits: 70 001 rockets (ragged last tile), 260 steps with
+    auto-reset, so that every rocket finishes at least one episode."""
+    from rocket_landing_rl_b200 import RocketLandingVecEnv
+    n = 70001
+    g = torch.Generator(device="cuda").manual_seed(17)
+    acts = [torch.rand((n, 2), device="cuda", generator=g) for _ in range(4)]
+    for a in acts:
+        a[:, 1].mul_(2).sub_(1)
+
+    def run(env):
+        env.reset()
+        ret = torch.zeros(n, device="cuda", dtype=torch.float64)
+        flags = torch.zeros(n, device="cuda", dtype=torch.int64)
+        for t in range(260):
+            obs, rew, term, trunc, info = env.step(acts[t % 4])
+            ret += rew.double()
+            flags += term.long() + 2 * trunc.long() + 4 * info["landing"].long()
+        torch.cuda.synchronize()
+        return env.get_state().clone(), obs.clone(), ret, flags, info["terminal_observation"].clone(), env.stats()
+
+    monkeypatch.setenv("RL_B200_TILES_PER_CTA", "0")          # persistent strided grid
+    ref = run(RocketLandingVecEnv(n, device="cuda", seed=5))
+    monkeypatch.setenv("RL_B200_TILES_PER_CTA", str(tiles_per_cta))
+    got = run(RocketLandingVecEnv(n, device="cuda", seed=5))
+    for a, b in zip(ref[:5], got[:5]):
+        assert torch.equal(a, b)
+    assert ref[5].episodes == got[5].episodes > n
+    assert ref[5].env_steps == got[5].env_steps == 260 * n
+    assert ref[5].return_sum == pytest.approx(got[5].return_sum, rel=1e-6)    # fp32 partial sums grouped differently
+
+
 def test_ragged_batch_sizes(torch):
     """Sizes around the warp-tile / CTA / padding boundaries, including a single rocket."""
     from rocket_landing_rl_b200 import RocketLandingVecEnv
