@@ -70,12 +70,16 @@ __device__ __forceinline__ float rl_rcp_fast(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+// clamp to [0, 1] as an instruction modifier (FMUL.SAT / FFMA.SAT): min(1, x) for free when x >= 0
+// is known, max(0, x) for free when x <= 1 is known
+__device__ __forceinline__ float rl_sat(float x) { return __saturatef(x); }
 __device__ __forceinline__ uint32_t rl_f2u(float f) { return __float_as_uint(f); }
 __device__ __forceinline__ float rl_u2f(uint32_t u) { return __uint_as_float(u); }
 #else
 inline float rl_rcp(float x) { return 1.0f / x; }
 inline float rl_sqrt(float x) { return std::sqrt(x); }
 inline float rl_rcp_fast(float x) { return 1.0f / x; }
+inline float rl_sat(float x) { return x != x ? 0.0f : std::fmin(std::fmax(x, 0.0f), 1.0f); }
 inline uint32_t rl_f2u(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline float rl_u2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 #endif
@@ -193,7 +197,7 @@ __device__ __forceinline__ void fresh_obs(const PP& P, const Rocket& r, float ax
 // Potential of reward.py:231-264.
 __device__ __forceinline__ float potential(float y, float vx, float vy, float ang, float om) {
     const float yp = fmaxf(0.0f, y);
-    const float w = 2.0f - fminf(1.0f, yp * (1.0f / 2000.0f));
+    const float w = 2.0f - rl_sat(y * (1.0f / 2000.0f));          // 2 - min(1, max(0, y) / 2000)
     const float near_ground = fmaf(0.015f, fabsf(vy), fmaf(0.01f, fabsf(ang), 0.05f * fabsf(om)));
     return -fmaf(w, near_ground, fmaf(0.005f, yp, 0.005f * fabsf(vx)));
 }
@@ -329,18 +333,19 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_
     const bool airborne = kPreciseY ? (y_a_d > 0.1) : (y_a > P.ground_y);
     const bool descending = airborne && (vy_a < 0.0f);
     // 2. throttle while descending (reward.py:171-186)
-    const float af = fmaxf(0.0f, fmaf(aa, -1.0f / 45.0f, 1.0f));
-    const float t2 = th_raw * (-vy_a) * af * (1.0f + fminf(1.0f, avy * 0.1f)) * P.k_throttle_descent;
+    const float af = rl_sat(fmaf(aa, -1.0f / 45.0f, 1.0f));              // max(0, 1 - |angle| / 45), aa >= 0
+    const float t2 = th_raw * (-vy_a) * af * (1.0f + rl_sat(avy * 0.1f)) * P.k_throttle_descent;
     total += descending ? t2 : 0.0f;
     // 3. free fall (reward.py:190-201)
     const float prox = fmaf(8.0f, rl_rcp_fast(fmaxf(y_a, 1.0f)), 1.0f);
-    const float t3 = P.k_free_fall * (-vy_a) * prox * (1.0f + fminf(1.0f, avy * (1.0f / 15.0f)));
+    const float t3 = P.k_free_fall * (-vy_a) * prox * (1.0f + rl_sat(avy * (1.0f / 15.0f)));
     total -= (descending && th_raw < P.throttle_lo_lt) ? t3 : 0.0f;
     // 4. throttle while tilted (reward.py:205-219)
     const float tilt = (aa > 10.0f) ? aa * (1.0f / 90.0f) : ((aa > 5.0f) ? (aa - 5.0f) * 0.1f : 0.0f);
     total -= (airborne && th_raw > P.throttle_lo_gt) ? th_raw * tilt * P.k_angle_throttle : 0.0f;
     // 5. climbing (reward.py:222-227)
-    const float t5 = vy_a * 0.5f * fminf(1.0f, y_a * 1e-3f) * (1.0f + fminf(1.0f, vy_a * 0.2f));
+    // (both factors only count when y_a > 0.1 and vy_a > 0, where min(1, x) == sat(x))
+    const float t5 = vy_a * 0.5f * rl_sat(y_a * 1e-3f) * (1.0f + rl_sat(vy_a * 0.2f));
     total -= (airborne && vy_a > 0.0f) ? t5 : 0.0f;
     // 6. potential shaping (reward.py:267-270)
     const float phi_b = have_phi ? o.phi : potential(y_b, vx_b, vy_b, ang_b, om_b);

@@ -40,21 +40,8 @@ constexpr int kCtaThreads = RL_CTA_THREADS;   // rockets per tile == threads per
 constexpr int kStages = RL_STAGES;   // depth of the shared-memory ring (tiles in flight = kStages - 1)
 constexpr int kPad = 256;            // planes are padded to a multiple of this many rockets
 #ifndef RL_MIN_CTAS
-#define RL_MIN_CTAS 4                // resident CTAs per SM the register allocator must allow
+#define RL_MIN_CTAS 3                // lets ptxas use 64 registers, with which 4 CTAs are still resident
 #endif
-// How a tile's inputs reach the registers (build knob; profiles/README.md records the comparison):
-//   0  cp.async ring, next tile's copies issued BEFORE the current tile is read back
-//   1  cp.async ring, current tile read back first, then the next tile's copies issued
-//   2  no shared memory: the next tile is loaded into registers (LDG) while this one is computed
-#ifndef RL_LOAD_MODE
-#define RL_LOAD_MODE 1
-#endif
-// 1: lane pairs exchange observation halves so that every 128-bit store instruction of a warp
-// writes whole 32-byte sectors (16 rockets x 32 B) instead of half of each of 32 sectors
-#ifndef RL_OBS_TRANSPOSE
-#define RL_OBS_TRANSPOSE 1
-#endif
-
 struct StatePlanes {
     float4* A;
     float4* B;
@@ -248,7 +235,6 @@ __device__ __forceinline__ void out_store(T* p, T v) {
 struct __align__(16) ObsStage { float4 chunk[64]; };      // one warp's 32 rows of 2 x 16 B
 
 __device__ __forceinline__ void store_obs(ObsStage& st, float4* __restrict__ obs, uint32_t i, uint32_t n, const float* o) {
-#if RL_OBS_TRANSPOSE
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t w = (lane >> 2) & 1u;                  // chunk c lives at c ^ ((c >> 3) & 1); c = 2 lane (+1)
     st.chunk[(2u * lane) ^ w] = make_float4(o[0], o[1], o[2], o[3]);
@@ -261,13 +247,6 @@ __device__ __forceinline__ void store_obs(ObsStage& st, float4* __restrict__ obs
     const uint32_t r1 = row0 + (lane >> 1), r2 = r1 + 16u;
     if (r1 < n) out_store(&obs[2 * (size_t)row0 + lane], v1);
     if (r2 < n) out_store(&obs[2 * (size_t)row0 + 32u + lane], v2);
-#else
-    (void)st;
-    if (i < n) {
-        out_store(&obs[2 * (size_t)i], make_float4(o[0], o[1], o[2], o[3]));
-        out_store(&obs[2 * (size_t)i + 1], make_float4(o[4], o[5], o[6], o[7]));
-    }
-#endif
 }
 
 // Episode end + reset of the done lanes of one warp (rare: ~1 rocket in 113 per step; inlined
@@ -335,9 +314,7 @@ template <> struct ParamSel<DefaultParams> {
 template <bool kAutoReset, bool kSingleStep, bool kChunked, class PP>
 __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __grid_constant__ DevParams Prt,
                                                                         const __grid_constant__ StepArgs a) {
-#if RL_LOAD_MODE != 2
     __shared__ Stage ring[kStages];
-#endif
     __shared__ BlockStats bs;
     __shared__ ObsStage obs_stage[kCtaThreads / 32];
 
@@ -347,7 +324,6 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
     const uint32_t tile0 = a.tile_begin + (kChunked ? blockIdx.x * a.chunk : blockIdx.x);   // this CTA's first tile
     const uint32_t n_tiles = kChunked ? min(a.tile_end, tile0 + a.chunk) : a.tile_end;       // one past its last
 
-#if RL_LOAD_MODE != 2
     // this thread's rocket of `tile` -> stage s (state planes are padded, so only the caller's
     // action array needs a bounds guard: out-of-range rockets get a zero action)
     auto prefetch = [&](uint32_t tile, uint32_t s) {
@@ -359,65 +335,27 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
         const bool in = j < a.n;
         cp_async_8_zfill(&ring[s].act[tid], a.actions + (in ? j : 0u), in ? 8u : 0u);
     };
-#else
-    // this thread's rocket of `tile` -> registers; consumed one iteration later, so the loads stay
-    // in flight while the current tile is computed (L2-only loads: every word is read exactly once)
-    float4 nA, nB;
-    float nfuel, ndry;
-    float2 nact;
-    auto prefetch_regs = [&](uint32_t tile) {
-        const uint32_t j = tile * kCtaThreads + tid;
-        nA = __ldcg(a.st.A + j);
-        nB = __ldcg(a.st.B + j);
-        nfuel = __ldcg(a.st.fuel + j);
-        ndry = __ldcg(a.st.dry + j);
-        nact = (j < a.n) ? __ldcs(a.actions + j) : make_float2(0.0f, 0.0f);
-    };
-#endif
 
     stats_init(bs);
-#if RL_LOAD_MODE != 2
 #pragma unroll
     for (uint32_t d = 0; d + 1 < (uint32_t)kStages; ++d) {   // prologue: the first kStages - 1 tiles
         const uint32_t tile = tile0 + d * stride;
         if (tile < n_tiles) prefetch(tile, d);
         cp_async_commit();
     }
-#else
-    if (tile0 < n_tiles) prefetch_regs(tile0);
-#endif
     const uint64_t epoch = *a.epoch;
     __syncthreads();                                    // stats_init visible CTA-wide; every thread has read the epoch
     unsigned int my_ticket = 0u;
     if (a.epoch_bump && tid == 0) my_ticket = epoch_take_ticket(a.ticket);   // uniform over the grid
     ThreadStats ts;
 
-#if RL_LOAD_MODE != 2
     uint32_t s = 0;
-#endif
     for (uint32_t tile = tile0; tile < n_tiles; tile += stride) {
         const uint32_t i = tile * kCtaThreads + tid;
         const bool valid = i < a.n;
 
         Rocket r;
         float2 act;
-#if RL_LOAD_MODE == 0
-        {
-            const uint32_t next = tile + (uint32_t)(kStages - 1) * stride;
-            const uint32_t s_next = (s == 0u) ? (uint32_t)(kStages - 1) : s - 1u;   // the stage drained last iteration
-            if (next < n_tiles) prefetch(next, s_next);     // kStages - 1 tiles in flight while this one is computed
-            cp_async_commit();                              // (possibly empty) keeps the group count uniform
-            cp_async_wait<kStages - 1>();                   // everything but the newest kStages - 1 groups has landed
-            const float4 va = ring[s].A[tid];
-            const float4 vb = ring[s].B[tid];
-            r.fuel = ring[s].fuel[tid];
-            r.dry = ring[s].dry[tid];
-            r.x = va.x; r.y = va.y; r.ang = va.z; r.meta = __float_as_uint(va.w);
-            r.sx = vb.x; r.sy = vb.y; r.sang = vb.z; r.ep_ret = vb.w;
-            act = ring[s].act[tid];
-            s = (s + 1u == (uint32_t)kStages) ? 0u : s + 1u;
-        }
-#elif RL_LOAD_MODE == 1
         {
             cp_async_wait<kStages - 2>();                   // this tile's group has landed
             const float4 va = ring[s].A[tid];
@@ -428,23 +366,14 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
             r.sx = vb.x; r.sy = vb.y; r.sang = vb.z; r.ep_ret = vb.w;
             act = ring[s].act[tid];
             // the shared-memory reads above are complete (their values are in registers) before the
-            // copies below are issued by the same thread, so refilling a stage is hazard-free
+            // copies below are issued by the same thread, so refilling a stage is hazard-free; issuing
+            // them AFTER the read-back keeps the LDS from queueing behind five LDGSTS in the MIO pipe
             const uint32_t next = tile + (uint32_t)(kStages - 1) * stride;
             const uint32_t s_next = (kStages == 2) ? (s ^ 1u) : ((s == 0u) ? (uint32_t)(kStages - 1) : s - 1u);
-            if (next < n_tiles) prefetch(next, s_next);
-            cp_async_commit();
+            if (next < n_tiles) prefetch(next, s_next);     // kStages - 1 tiles in flight while this one is computed
+            cp_async_commit();                              // (possibly empty) keeps the group count uniform
             s = (s + 1u == (uint32_t)kStages) ? 0u : s + 1u;
         }
-#else
-        {
-            r.x = nA.x; r.y = nA.y; r.ang = nA.z; r.meta = __float_as_uint(nA.w);
-            r.sx = nB.x; r.sy = nB.y; r.sang = nB.z; r.ep_ret = nB.w;
-            r.fuel = nfuel; r.dry = ndry;
-            act = nact;
-            const uint32_t next = tile + stride;
-            if (next < n_tiles) prefetch_regs(next);
-        }
-#endif
 
         StepResult o;
         float reward;
@@ -488,9 +417,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
             if (a.landing) out_store(reinterpret_cast<uint8_t*>(&a.landing[i]), (uint8_t)landing);
         }
     }
-#if RL_LOAD_MODE != 2
     cp_async_wait<0>();
-#endif
     stats_flush(bs, a.stats, ts);
     if (a.epoch_bump && tid == 0) epoch_bump_if_last(a.epoch_bump, a.ticket, my_ticket);
 }

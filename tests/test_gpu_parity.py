@@ -331,7 +331,7 @@ def test_step_is_cuda_graph_capturable_and_replay_advances_the_reset_stream(torc
 # ---------------------------------------------------------------------------------------------
 # BASELINE.json full size: size-independent properties (configs[2]: 16 Mi rockets)
 # ---------------------------------------------------------------------------------------------
-def test_full_size_properties_16m_rockets(torch):
+def test_full_size_properties_16m_rockets(torch, monkeypatch):
     from rocket_landing_rl_b200 import RocketLandingVecEnv
     n = 16 * 1024 * 1024
     env = RocketLandingVecEnv(n, seed=0)
@@ -373,6 +373,17 @@ def test_full_size_properties_16m_rockets(torch):
     assert int(checksum) == int(checksum2)
     env.close()
     env2.close()
+    # ... and the same bits from the other grid shape (this size runs 8 consecutive tiles per CTA
+    # by default; force the persistent strided grid)
+    monkeypatch.setenv("RL_B200_TILES_PER_CTA", "0")
+    env3 = RocketLandingVecEnv(n, seed=0)
+    env3.reset()
+    checksum3 = torch.zeros((), device="cuda", dtype=torch.int64)
+    for t in range(T):
+        obs, rew, _, _, _ = env3.step(a)
+        checksum3 += obs.view(torch.int32).sum(dtype=torch.int64) + rew.view(torch.int32).sum(dtype=torch.int64)
+    assert int(checksum) == int(checksum3)
+    env3.close()
 
 
 # ---------------------------------------------------------------------------------------------
