@@ -4,7 +4,9 @@
 // compute_returns_and_advantage is the recurrence below, run on the host over [T, n_envs] numpy
 // arrays.  Here one thread owns one rocket and walks its T steps backwards; for a fixed step the
 // accesses of a warp are contiguous ([T][N] layout), so the kernel streams 9 B in / 8 B out per
-// (step, rocket) at HBM speed.
+// (step, rocket).  Only the arithmetic of the recurrence is serial: the loads of kAhead steps are
+// issued together, ahead of the chain that consumes them, and CTAs own consecutive rockets and are
+// dispatched in address order (profiles/README.md "grid order").
 #include <cstdarg>
 #include <cstdio>
 
@@ -31,24 +33,43 @@ int ro_fail(int code, const char* fmt, ...) {
 //       last_gae_lam = delta + gamma * gae_lambda * next_non_terminal * last_gae_lam
 //       advantages[step] = last_gae_lam
 //   returns = advantages + values
+constexpr int kAhead = 4;
+
 __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                                                   const uint8_t* __restrict__ episode_starts,
                                                   const float* __restrict__ last_values,
                                                   const uint8_t* __restrict__ last_dones, float* __restrict__ advantages,
                                                   float* __restrict__ returns, int T, int64_t n, float gamma, float lam) {
-    for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
-        float next_value = last_values[i];
-        float next_non_terminal = last_dones[i] ? 0.0f : 1.0f;
-        float gae = 0.0f;
-        for (int t = T - 1; t >= 0; --t) {
-            const int64_t k = (int64_t)t * n + i;
-            const float v = values[k];
-            const float delta = fmaf(gamma * next_value, next_non_terminal, rewards[k]) - v;
-            gae = fmaf(gamma * lam * next_non_terminal, gae, delta);
-            advantages[k] = gae;
-            returns[k] = gae + v;
-            next_value = v;
-            next_non_terminal = episode_starts[k] ? 0.0f : 1.0f;
+    const int64_t i = blockIdx.x * 256ll + threadIdx.x;
+    if (i >= n) return;
+    float next_value = last_values[i];
+    float next_non_terminal = last_dones[i] ? 0.0f : 1.0f;
+    float gae = 0.0f;
+    for (int t0 = T - 1; t0 >= 0; t0 -= kAhead) {
+        float v[kAhead], r[kAhead];
+        uint8_t es[kAhead];
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {                 // steps t0, t0 - 1, ...: every load first
+            const int t = t0 - u;
+            if (t >= 0) {
+                const int64_t k = (int64_t)t * n + i;
+                v[u] = values[k];
+                r[u] = rewards[k];
+                es[u] = episode_starts[k];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+            const int t = t0 - u;
+            if (t >= 0) {
+                const int64_t k = (int64_t)t * n + i;
+                const float delta = fmaf(gamma * next_value, next_non_terminal, r[u]) - v[u];
+                gae = fmaf(gamma * lam * next_non_terminal, gae, delta);
+                advantages[k] = gae;
+                returns[k] = gae + v[u];
+                next_value = v[u];
+                next_non_terminal = es[u] ? 0.0f : 1.0f;
+            }
         }
     }
 }
@@ -68,11 +89,8 @@ int rl_gae(const float* rewards, const float* values, const uint8_t* episode_sta
     if (!rewards || !values || !episode_starts || !last_values || !last_dones || !advantages || !returns)
         return ro_fail(RL_E_INVALID, "rl_gae: null argument");
     if (T < 1 || n_envs < 1) return ro_fail(RL_E_INVALID, "rl_gae: T and n_envs must be positive");
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t ctas = (n_envs + 255) / 256;
-    const int grid = (int)(ctas < (int64_t)sms * 8 ? ctas : (int64_t)sms * 8);
+    if (n_envs > 2147483392LL) return ro_fail(RL_E_INVALID, "rl_gae: at most 2147483392 rockets per call");
+    const int grid = (int)((n_envs + 255) / 256);             // one CTA per 256 consecutive rockets
     gae_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(rewards, values, episode_starts, last_values, last_dones,
                                                        advantages, returns, T, n_envs, (float)gamma, (float)gae_lambda);
     cudaError_t e = cudaGetLastError();
