@@ -134,10 +134,17 @@ template <int kBytes> __device__ __forceinline__ void cpa(void* dst, const void*
     if constexpr (kBytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
     else asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(kBytes) : "memory");
 }
+// div_pct: percentage of warp-tiles that execute div_work extra dependent FMAs (the warps that meet a
+// finished episode: Philox reset path); epilogue: the step kernel's per-CTA statistics flush (35
+// shuffles, shared-memory atomics, two barriers, 13 global atomics)
 template <int kStages>
-__global__ void __launch_bounds__(256, 4) mix_ring(Bufs b, uint32_t n_tiles_total, uint32_t chunk, int work) {
+__global__ void __launch_bounds__(256, 4) mix_ring(Bufs b, uint32_t n_tiles_total, uint32_t chunk, int work,
+                                                   int div_pct = 0, int div_work = 0, int epilogue = 0, double* gstats = nullptr) {
     __shared__ RingStage ring[kStages];
     __shared__ float4 ostage[8][64];
+    __shared__ double sstat[16];
+    if (epilogue) { if (threadIdx.x < 16) sstat[threadIdx.x] = 0.0; __syncthreads(); }
+    float tsum = 0.f; int tcnt = 0;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     const uint32_t tile0 = blockIdx.x * chunk, tile_end = min(n_tiles_total, tile0 + chunk);
     auto prefetch = [&](uint32_t tile, uint32_t s) {
@@ -165,6 +172,12 @@ __global__ void __launch_bounds__(256, 4) mix_ring(Bufs b, uint32_t n_tiles_tota
         s = (s + 1u == (uint32_t)kStages) ? 0u : s + 1u;
         float sacc = a.x + bb.y + fu * d + ac.x * ac.y;
         for (int k = 0; k < work; ++k) sacc = fmaf(sacc, 0.999f, 0.001f);      // dependent chain, `work` issue slots
+        if (div_pct) {                                                         // warp-uniform, pseudo-random per warp-tile
+            const uint32_t h = ((tile * 8u + (tid >> 5)) * 2654435761u) >> 16;
+            if ((int)(h % 100u) < div_pct)
+                for (int k = 0; k < div_work; ++k) sacc = fmaf(sacc, 1.001f, -0.001f);
+        }
+        tsum += sacc; tcnt += 1;
         const float4 nA = make_float4(a.y, a.x, a.w + sacc, a.z), nB = make_float4(bb.y, bb.x, bb.w, bb.z + sacc);
         b.A[i] = nA; b.B[i] = nB; b.fuel[i] = fu + 1.0f;
         float4* st = ostage[tid >> 5];
@@ -179,6 +192,24 @@ __global__ void __launch_bounds__(256, 4) mix_ring(Bufs b, uint32_t n_tiles_tota
         b.obs[2 * (size_t)row0 + lane] = v1; b.obs[2 * (size_t)row0 + 32u + lane] = v2;
         b.rew[i] = sacc;
         b.f0[i] = sacc > 0.0f; b.f1[i] = sacc < 1.0f; b.f2[i] = (uint8_t)(sacc == 2.0f);
+    }
+    if (epilogue) {
+        double d0 = (double)tsum, d1 = (double)tsum * 0.5; int c0 = tcnt, c1 = tcnt, c2 = tcnt, c3 = tcnt, c4 = tcnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            c0 += __shfl_xor_sync(0xffffffffu, c0, o); c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+            c2 += __shfl_xor_sync(0xffffffffu, c2, o); c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+            c4 += __shfl_xor_sync(0xffffffffu, c4, o);
+        }
+        if (lane == 0) {
+            atomicAdd(&sstat[0], d0); atomicAdd(&sstat[1], d1); atomicAdd(&sstat[2], (double)c0); atomicAdd(&sstat[3], (double)c1);
+            atomicAdd(&sstat[4], (double)c2); atomicAdd(&sstat[5], (double)c3); atomicAdd(&sstat[6], (double)c4);
+        }
+        __syncthreads();
+        if (tid == 0) for (int k = 7; k < 13; ++k) sstat[k] = 1.0;
+        __syncthreads();
+        if (tid < 13 && sstat[tid] != 0.0) atomicAdd(&gstats[(blockIdx.x % 64) * 16 + tid], sstat[tid]);
     }
 }
 
@@ -229,6 +260,15 @@ int main(int argc, char** argv) {
             snprintf(name, sizeof name, "ring s2 chunk %u work 0", chunk);
             time_it([&] { mix_ring<2><<<(tiles + chunk - 1) / chunk, 256>>>(b, tiles, chunk, 0); }, name, 123.0 * n);
         }
+        // what separates the skeleton from the step kernel: the divergent reset path and the CTA epilogue
+        double* gstats; CK(cudaMalloc(&gstats, 64 * 16 * sizeof(double))); CK(cudaMemset(gstats, 0, 64 * 16 * sizeof(double)));
+        const unsigned g8 = (tiles + 7) / 8;
+        time_it([&] { mix_ring<2><<<g8, 256>>>(b, tiles, 8, 330); }, "ring chunk 8 work 330", 123.0 * n);
+        time_it([&] { mix_ring<2><<<g8, 256>>>(b, tiles, 8, 330, 0, 0, 1, gstats); }, "ring chunk 8 work 330 + epilogue", 123.0 * n);
+        time_it([&] { mix_ring<2><<<g8, 256>>>(b, tiles, 8, 330, 25, 400); }, "ring chunk 8 work 330 + 25% x 400", 123.0 * n);
+        time_it([&] { mix_ring<2><<<g8, 256>>>(b, tiles, 8, 330, 25, 400, 1, gstats); }, "ring chunk 8 work 330 + 25% x 400 + epilogue", 123.0 * n);
+        time_it([&] { mix_ring<2><<<g8, 256>>>(b, tiles, 8, 430, 0, 0, 1, gstats); }, "ring chunk 8 work 430 (same total, uniform) + epilogue", 123.0 * n);
+        time_it([&] { mix_ring<2><<<g8, 256>>>(b, tiles, 8, 330, 25, 800, 1, gstats); }, "ring chunk 8 work 330 + 25% x 800 + epilogue", 123.0 * n);
         return 0;
     }
     if (argc > 2) {
