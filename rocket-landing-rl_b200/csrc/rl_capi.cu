@@ -54,6 +54,8 @@ struct RlEnv {
     void* h_stage = nullptr;
     size_t h_stage_bytes = 0;
     unsigned long long* h_epoch_snapshot = nullptr;    // inside h_stage
+    void* h_pinned = nullptr;         // small batches: pinned, device-mapped host staging (same layout as h_stage)
+    int64_t small_host = 16384;       // rl_step_host: at most this many rockets take the zero-copy path
     cudaStream_t h_streams[2] = {nullptr, nullptr};
     cudaEvent_t h_events[2] = {nullptr, nullptr};
 };
@@ -261,6 +263,10 @@ int rl_create(const RlParams* params, int64_t n_envs, int64_t env_id_offset, uin
     const char* force_generic = getenv("RL_B200_GENERIC_KERNEL");
     e->folded = rl::matches_default(e->dev) && !(force_generic && force_generic[0] == '1');
     cudaDeviceGetAttribute(&e->sms, cudaDevAttrMultiProcessorCount, device);
+    if (const char* t = getenv("RL_B200_SMALL_HOST")) {           // experiment knob: zero-copy host path up to this size
+        const long long v = strtoll(t, nullptr, 10);
+        if (v >= 0) e->small_host = v;
+    }
     if (const char* t = getenv("RL_B200_TILES_PER_CTA")) {      // experiment knob: force the grid shape
         const long v = strtol(t, nullptr, 10);
         if (v >= -1 && v <= 65536) e->tiles_per_cta = (int)v;
@@ -294,6 +300,7 @@ int rl_destroy(RlEnv* e) {
     if (e->epoch) cudaFree(e->epoch);
     if (e->ticket) cudaFree(e->ticket);
     if (e->h_stage) cudaFree(e->h_stage);
+    if (e->h_pinned) cudaFreeHost(e->h_pinned);
     for (int k = 0; k < 2; ++k) {
         if (e->h_streams[k]) cudaStreamDestroy(e->h_streams[k]);
         if (e->h_events[k]) cudaEventDestroy(e->h_events[k]);
@@ -410,22 +417,16 @@ struct Stage {
     int8_t* landing;
 };
 size_t align256(size_t v) { return (v + 255) / 256 * 256; }
-int ensure_stage(RlEnv* e, Stage& s) {
+size_t stage_sizes(const RlEnv* e, size_t sz[9]) {
     const size_t n = (size_t)e->n;
-    const size_t sz[9] = {align256(8 * n), align256(32 * n), align256(4 * n), align256(n), align256(n),
-                          align256(32 * n), align256(4 * n), align256(4 * n), align256(n)};
+    const size_t v[9] = {align256(8 * n), align256(32 * n), align256(4 * n), align256(n), align256(n),
+                         align256(32 * n), align256(4 * n), align256(4 * n), align256(n)};
     size_t total = 256;                                   // + the epoch snapshot
-    for (size_t v : sz) total += v;
-    if (!e->h_stage) {
-        if (cudaMalloc(&e->h_stage, total) != cudaSuccess) return fail(RL_E_NOMEM, "host path: cudaMalloc(%zu) failed", total);
-        e->h_stage_bytes = total;
-        for (int k = 0; k < 2; ++k) {
-            RL_CUDA(cudaStreamCreateWithFlags(&e->h_streams[k], cudaStreamNonBlocking));
-            RL_CUDA(cudaEventCreateWithFlags(&e->h_events[k], cudaEventDisableTiming));
-        }
-    }
-    char* p = static_cast<char*>(e->h_stage);
-    e->h_epoch_snapshot = reinterpret_cast<unsigned long long*>(p); p += 256;
+    for (int k = 0; k < 9; ++k) { sz[k] = v[k]; total += v[k]; }
+    return total;
+}
+void carve_stage(char* p, const size_t sz[9], Stage& s) {
+    p += 256;
     s.actions = (float*)p; p += sz[0];
     s.obs = (float*)p; p += sz[1];
     s.reward = (float*)p; p += sz[2];
@@ -435,6 +436,44 @@ int ensure_stage(RlEnv* e, Stage& s) {
     s.episode_return = (float*)p; p += sz[6];
     s.episode_length = (int32_t*)p; p += sz[7];
     s.landing = (int8_t*)p;
+}
+int ensure_streams(RlEnv* e) {
+    if (e->h_streams[0]) return RL_OK;
+    for (int k = 0; k < 2; ++k) {
+        RL_CUDA(cudaStreamCreateWithFlags(&e->h_streams[k], cudaStreamNonBlocking));
+        RL_CUDA(cudaEventCreateWithFlags(&e->h_events[k], cudaEventDisableTiming));
+    }
+    return RL_OK;
+}
+int ensure_stage(RlEnv* e, Stage& s) {
+    size_t sz[9];
+    const size_t total = stage_sizes(e, sz);
+    if (!e->h_stage) {
+        if (cudaMalloc(&e->h_stage, total) != cudaSuccess) return fail(RL_E_NOMEM, "host path: cudaMalloc(%zu) failed", total);
+        e->h_stage_bytes = total;
+    }
+    int rc = ensure_streams(e);
+    if (rc != RL_OK) return rc;
+    e->h_epoch_snapshot = reinterpret_cast<unsigned long long*>(e->h_stage);
+    carve_stage(static_cast<char*>(e->h_stage), sz, s);
+    return RL_OK;
+}
+// Small batches: pinned host memory the device reads and writes directly (zero-copy over PCIe).
+// `host` are the CPU's pointers, `dev` the device's aliases of the same bytes.
+int ensure_pinned(RlEnv* e, Stage& host, Stage& dev) {
+    size_t sz[9];
+    const size_t total = stage_sizes(e, sz);
+    if (!e->h_pinned) {
+        if (cudaHostAlloc(&e->h_pinned, total, cudaHostAllocMapped) != cudaSuccess)
+            return fail(RL_E_NOMEM, "host path: cudaHostAlloc(%zu) failed", total);
+        memset(e->h_pinned, 0, total);
+    }
+    int rc = ensure_streams(e);
+    if (rc != RL_OK) return rc;
+    void* d = nullptr;
+    RL_CUDA(cudaHostGetDevicePointer(&d, e->h_pinned, 0));
+    carve_stage(static_cast<char*>(e->h_pinned), sz, host);
+    carve_stage(static_cast<char*>(d), sz, dev);
     return RL_OK;
 }
 }  // namespace
@@ -447,10 +486,34 @@ int rl_step_host(RlEnv* e, const float* actions, float* obs, float* reward, uint
         return fail(RL_E_INVALID, "rl_step_host: actions, obs, reward, terminated and truncated are required");
     if (substeps < 1 || substeps > 4096) return fail(RL_E_INVALID, "rl_step_host: substeps must be in [1, 4096]");
     DeviceGuard guard(e->device);
+    const int64_t n = e->n;
+    if (n <= e->small_host) {
+        // Small batch (the reference trains with rl.n_envs = 8, config.yaml:95): latency, not bandwidth.
+        // The kernel reads the actions from and writes its outputs to pinned host memory directly, so
+        // the call is one launch and one stream synchronisation instead of six copies around it.
+        Stage h, d;
+        int rc = ensure_pinned(e, h, d);
+        if (rc != RL_OK) return rc;
+        const size_t m = (size_t)n;
+        memcpy(h.actions, actions, 8 * m);
+        rc = launch_step(e, d.actions, d.obs, d.reward, d.terminated, d.truncated, terminal_obs ? d.terminal_obs : nullptr,
+                         episode_return ? d.episode_return : nullptr, episode_length ? d.episode_length : nullptr,
+                         landing ? d.landing : nullptr, substeps, auto_reset, e->h_streams[0]);
+        if (rc != RL_OK) return rc;
+        RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
+        memcpy(obs, h.obs, 32 * m);
+        memcpy(reward, h.reward, 4 * m);
+        memcpy(terminated, h.terminated, m);
+        memcpy(truncated, h.truncated, m);
+        if (terminal_obs) memcpy(terminal_obs, h.terminal_obs, 32 * m);      // (only rows of done rockets are meaningful)
+        if (episode_return) memcpy(episode_return, h.episode_return, 4 * m);
+        if (episode_length) memcpy(episode_length, h.episode_length, 4 * m);
+        if (landing) memcpy(landing, h.landing, m);
+        return RL_OK;
+    }
     Stage s;
     int rc = ensure_stage(e, s);
     if (rc != RL_OK) return rc;
-    const int64_t n = e->n;
     const int64_t tiles = (n + rl::kCtaThreads - 1) / rl::kCtaThreads;
     // chunks of >= 1 Mi rockets (PCIe-efficient, and a full persistent grid), at most 16 of them
     int64_t chunks = tiles / 4096;

@@ -228,10 +228,14 @@ def test_sharding_does_not_change_trajectories(torch):
         e.close()
 
 
-def test_host_buffer_vecenv_api_matches_device_api(torch):
-    """The reference-facing plugin call (numpy in, numpy out, SB3 VecEnv surface)."""
+@pytest.mark.parametrize("small_host", ["16384", "0"])
+def test_host_buffer_vecenv_api_matches_device_api(torch, monkeypatch, small_host):
+    """The reference-facing plugin call (numpy in, numpy out, SB3 VecEnv surface), through both
+    host paths of rl_step_host: zero-copy pinned staging (small batches, the default at this size)
+    and the chunked copy pipeline (RL_B200_SMALL_HOST=0 forces it)."""
     from rocket_landing_rl_b200 import RocketLandingSB3VecEnv, RocketLandingVecEnv
     n = 1024
+    monkeypatch.setenv("RL_B200_SMALL_HOST", small_host)
     host = RocketLandingSB3VecEnv(n, seed=11)
     dev = RocketLandingVecEnv(n, seed=11)
     assert host.observation_space.shape == (8,) and host.action_space.shape == (2,)
