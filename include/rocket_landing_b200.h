@@ -259,6 +259,24 @@ int rl_gae(const float *rewards, const float *values, const uint8_t *episode_sta
            const float *last_values, const uint8_t *last_dones, float *advantages, float *returns, int T,
            int64_t n_envs, double gamma, double gae_lambda, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused inference of one of the reference's actor-critic MLPs (scripts/train.py:117: net_arch =
+ * dict(pi=[256, 256], vf=[256, 256]), tanh; assets/model/v3): out = W3 tanh(W2 tanh(W1 obs + b1) +
+ * b2) + b3 for n rockets in one launch, activations kept in registers (tensor cores, bf16 weights,
+ * fp32 accumulation).  `blob` is the packed net in DEVICE memory (16-byte aligned), RL_MLP_BLOB_BYTES:
+ *   bf16 [256][16]  W1[j][0..7] twice (the kernel feeds the observation as bf16 high | low parts)
+ *   f32  [256]      b1
+ *   bf16 [256][256] W2 (row = output unit, as nn.Linear.weight)
+ *   f32  [256]      b2
+ *   f32  [2][256]   W3 (second row ignored when out_dim = 1)
+ *   f32  [4]        b3 (first out_dim used)
+ * obs float32 [n][8], out float32 [n][out_dim], out_dim 1 or 2.  DEVICE pointers, enqueue only. */
+#define RL_MLP_HIDDEN 256
+#define RL_MLP_BLOB_BYTES 143376
+const char *rl_policy_last_error(void);
+int64_t rl_mlp_blob_bytes(void);
+int rl_mlp_forward(const void *blob, const float *obs, float *out, int64_t n, int out_dim, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,9 +15,9 @@ from .env import RocketLandingVecEnv                                   # noqa: F
 from .vec_env import RocketLandingSB3VecEnv                            # noqa: F401
 from .normalize import DeviceVecNormalize                              # noqa: F401
 from .simulation import RocketSimulation                               # noqa: F401
-from .rollout import ActorCriticMLP, DeviceRolloutBuffer, collect_rollout   # noqa: F401
+from .rollout import ActorCriticMLP, DeviceRolloutBuffer, FusedActorCritic, collect_rollout, pack_mlp   # noqa: F401
 
 __all__ = ["Config", "load_params", "default_config_path", "Box", "STATE_WORDS",
            "fresh_state_soa", "state_soa_from_reference", "reference_view", "EpisodeStats",
            "shard_range", "allreduce_stats", "RocketLandingVecEnv", "RocketLandingSB3VecEnv", "DeviceVecNormalize",
-           "ActorCriticMLP", "DeviceRolloutBuffer", "collect_rollout", "RocketSimulation"]
+           "ActorCriticMLP", "DeviceRolloutBuffer", "FusedActorCritic", "pack_mlp", "collect_rollout", "RocketSimulation"]

@@ -11,6 +11,10 @@ GPU: nothing crosses PCIe during collection.
   state-independent log-std, a linear value head -- 136 965 parameters, as
   ``assets/model/v3/best_model.zip``.  It is plain PyTorch (cuBLAS
   GEMMs): the MLP is a neighbour of the hot path, not the path.
+* ``FusedActorCritic`` evaluates the same two nets with the hand-written tensor-core kernel
+  ``rl_mlp_forward`` (``csrc/rl_policy.cu``): one launch per net, the 256-wide activations never
+  leave the registers, bf16 weights with fp32 accumulation.  Same ``forward`` / ``predict_values``
+  surface, so ``collect_rollout`` takes either.
 * ``collect_rollout`` mirrors ``OnPolicyAlgorithm.collect_rollouts``: sample, clip the action to
   the Box (SB3 clips before ``env.step``), step, bootstrap time-limit truncations with the value
   of the terminal observation, store, and finally compute GAE with the ``rl_gae`` CUDA kernel.
@@ -56,6 +60,87 @@ class ActorCriticMLP(nn.Module):
         return self.value_net(self.value_net_body(obs)).squeeze(-1)
 
 
+MLP_BLOB_BYTES = 143376          # include/rocket_landing_b200.h: RL_MLP_BLOB_BYTES
+
+
+def pack_mlp(body: nn.Sequential, head: nn.Linear, device) -> torch.Tensor:
+    """One tanh MLP 8 -> 256 -> 256 -> head (1 or 2 outputs) in the layout ``rl_mlp_forward`` reads
+    (``include/rocket_landing_b200.h``): bf16 W1 stacked twice, f32 b1, bf16 W2, f32 b2, f32 W3 [2][256],
+    f32 b3 [4]."""
+    l1, l2 = body[0], body[2]
+    if (l1.weight.shape, l2.weight.shape, head.weight.shape[1]) != ((256, 8), (256, 256), 256) or head.weight.shape[0] not in (1, 2):
+        raise ValueError("rl_mlp_forward evaluates 8 -> 256 -> 256 -> {1, 2} nets only")
+    blob = torch.zeros(MLP_BLOB_BYTES, dtype=torch.uint8, device=device)
+    off = 0
+
+    def put(t: torch.Tensor) -> None:
+        nonlocal off
+        t = t.detach().to(device).contiguous()
+        nbytes = t.numel() * t.element_size()
+        blob[off:off + nbytes].view(t.dtype).copy_(t.reshape(-1))
+        off += nbytes
+
+    put(torch.cat([l1.weight, l1.weight], dim=1).to(torch.bfloat16))           # [256][16]
+    put(l1.bias.float())
+    put(l2.weight.to(torch.bfloat16))                                          # [256][256]
+    put(l2.bias.float())
+    w3 = torch.zeros((2, 256), dtype=torch.float32, device=head.weight.device)
+    w3[:head.weight.shape[0]] = head.weight.detach().float()
+    put(w3)
+    b3 = torch.zeros(4, dtype=torch.float32, device=head.bias.device)
+    b3[:head.bias.shape[0]] = head.bias.detach().float()
+    put(b3)
+    assert off == MLP_BLOB_BYTES
+    return blob
+
+
+class FusedActorCritic:
+    """``ActorCriticMLP`` evaluated by the fused tensor-core kernel (inference only: rollout
+    collection does not need gradients).  Call ``refresh()`` after the wrapped module's parameters
+    change (an optimiser step) to re-pack the weights."""
+
+    def __init__(self, net: ActorCriticMLP, device="cuda"):
+        self._L = _lib.load()
+        self.net = net
+        self.device = torch.device(device)
+        assert int(self._L.rl_mlp_blob_bytes()) == MLP_BLOB_BYTES
+        self.refresh()
+
+    def refresh(self) -> None:
+        self._pi = pack_mlp(self.net.policy_net, self.net.action_net, self.device)
+        self._vf = pack_mlp(self.net.value_net_body, self.net.value_net, self.device)
+        self._log_std = self.net.log_std.detach().to(self.device, torch.float32).clone()
+
+    def _run(self, blob: torch.Tensor, obs: torch.Tensor, out_dim: int) -> torch.Tensor:
+        if obs.dtype != torch.float32 or not obs.is_contiguous():
+            obs = obs.to(torch.float32).contiguous()
+        n = obs.shape[0]
+        out = torch.empty((n, out_dim), dtype=torch.float32, device=obs.device)
+        if n == 0:
+            return out
+        rc = self._L.rl_mlp_forward(blob.data_ptr(), obs.data_ptr(), out.data_ptr(), n, out_dim,
+                                    torch.cuda.current_stream(obs.device).cuda_stream)
+        if rc != 0:
+            raise _lib.RocketLibraryError(f"rl_mlp_forward failed ({rc}): {self._L.rl_policy_last_error().decode()}")
+        return out
+
+    def action_mean(self, obs: torch.Tensor) -> torch.Tensor:
+        return self._run(self._pi, obs, 2)
+
+    def predict_values(self, obs: torch.Tensor) -> torch.Tensor:
+        return self._run(self._vf, obs, 1).squeeze(-1)
+
+    def forward(self, obs: torch.Tensor, generator: Optional[torch.Generator] = None):
+        mean = self.action_mean(obs)
+        values = self.predict_values(obs)
+        noise = torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
+        actions = torch.addcmul(mean, self._log_std.exp(), noise)
+        log_prob = (-0.5 * noise.pow(2) - self._log_std - 0.5 * math.log(2.0 * math.pi)).sum(-1)
+        return actions, values, log_prob
+
+    __call__ = forward
+
+
 class DeviceRolloutBuffer:
     """Pre-allocated ``[T, N, ...]`` device tensors (SB3 ``RolloutBuffer`` fields)."""
 
@@ -85,7 +170,7 @@ class DeviceRolloutBuffer:
 
 
 @torch.no_grad()
-def collect_rollout(env, policy: ActorCriticMLP, buffer: DeviceRolloutBuffer, last_obs: torch.Tensor,
+def collect_rollout(env, policy, buffer: DeviceRolloutBuffer, last_obs: torch.Tensor,
                     last_episode_starts: torch.Tensor, gamma: float = 0.99, gae_lambda: float = 0.95,
                     bootstrap_timeouts: bool = True, generator: Optional[torch.Generator] = None):
     """One ``collect_rollouts`` pass of ``buffer.n_steps`` steps.  ``env`` is a

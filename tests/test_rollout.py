@@ -76,3 +76,36 @@ def test_device_resident_rollout_collection():
     assert stats.env_steps == n * T and stats.episodes > 0.8 * n
     env.close()
     env.venv.close()
+
+
+@pytest.mark.gpu
+def test_fused_mlp_kernel_matches_the_pytorch_module():
+    """rl_mlp_forward (tensor cores, bf16 weights, fp32 accumulation, activations in registers)
+    against the fp32 PyTorch module it packs.  Tolerance: bf16 weights carry 2^-9 relative error
+    each and the hidden activations are rounded to bf16 once; over 256-term dot products of O(1)
+    activations with O(1/16) weights that is ~1e-3 absolute on outputs of O(0.3); 1e-2 is asserted."""
+    import torch
+    from rocket_landing_rl_b200 import ActorCriticMLP, FusedActorCritic
+    torch.manual_seed(3)
+    net = ActorCriticMLP().cuda()
+    with torch.no_grad():                       # biases off zero so that every term of the kernel is exercised
+        for p in net.parameters():
+            if p.ndim == 1:
+                p.uniform_(-0.3, 0.3)
+    fused = FusedActorCritic(net)
+    for n in (1, 15, 16, 17, 127, 128, 129, 5000, 262144 + 77):
+        obs = (torch.randn((n, 8), device="cuda") * 3.0).clamp_(-10, 10)      # normalised observations, clip_obs = 10
+        with torch.no_grad():
+            want_mean = net.action_net(net.policy_net(obs))
+            want_val = net.predict_values(obs)
+        got_mean = fused.action_mean(obs)
+        got_val = fused.predict_values(obs)
+        assert got_mean.shape == (n, 2) and got_val.shape == (n,)
+        assert float((got_mean - want_mean).abs().max()) < 1e-2, n
+        assert float((got_val - want_val).abs().max()) < 1e-2, n
+    # every row is computed from its own observation only: permuting rows permutes outputs exactly
+    obs = torch.randn((1000, 8), device="cuda")
+    perm = torch.randperm(1000, device="cuda")
+    assert torch.equal(fused.action_mean(obs)[perm], fused.action_mean(obs[perm].contiguous()))
+    a, v, lp = fused(obs)
+    assert a.shape == (1000, 2) and v.shape == (1000,) and lp.shape == (1000,)

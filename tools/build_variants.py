@@ -18,7 +18,7 @@ def build(spec: str) -> str:
     out = os.path.join(OUT, f"lib_{name}.so")
     cmd = ["/usr/local/cuda/bin/nvcc", "-O3", "-std=c++17", "-lineinfo", "-gencode",
            "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-Xptxas", "-v", *flags.split(),
-           "-shared", "-o", out, "rl_capi.cu", "rl_vecnorm.cu", "rl_rollout.cu"]
+           "-shared", "-o", out, "rl_capi.cu", "rl_vecnorm.cu", "rl_rollout.cu", "rl_policy.cu"]
     p = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if p.returncode != 0:
         return f"{name}: FAILED\n{p.stderr[-3000:]}"

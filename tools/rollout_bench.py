@@ -12,7 +12,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rocket_landing_rl_b200 import (ActorCriticMLP, DeviceRolloutBuffer, DeviceVecNormalize,   # noqa: E402
-                                    RocketLandingVecEnv, collect_rollout)
+                                    FusedActorCritic, RocketLandingVecEnv, collect_rollout)
 
 
 def timed(fn, reps):
@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--n-steps", type=int, default=32)
     ap.add_argument("--passes", type=int, default=3)
     ap.add_argument("--dtype", default="tf32", choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--fused", action="store_true", help="evaluate the policy with rl_mlp_forward (csrc/rl_policy.cu)")
     args = ap.parse_args()
     torch.backends.cuda.matmul.allow_tf32 = args.dtype != "fp32"
     torch.backends.cudnn.allow_tf32 = args.dtype != "fp32"
@@ -39,6 +40,8 @@ def main():
     raw = RocketLandingVecEnv(n, seed=0)
     env = DeviceVecNormalize(raw, gamma=0.99)
     policy = ActorCriticMLP().cuda()
+    if args.fused:
+        policy = FusedActorCritic(policy)
     buf = DeviceRolloutBuffer(T, n, "cuda")
     obs = env.reset()
     starts = torch.ones(n, dtype=torch.bool, device="cuda")
@@ -59,7 +62,8 @@ def main():
         ms_policy = timed(lambda: policy(state["obs"]), 20)
     ms_gae = timed(lambda: buf.compute_returns_and_advantage(torch.zeros(n, device="cuda"), state["starts"], 0.99, 0.95), 20)
     print(json.dumps({
-        "workload": f"{n} rockets, n_steps {T}, policy 8-256-256 x2 ({sum(p.numel() for p in policy.parameters())} params, {args.dtype} GEMMs)",
+        "workload": f"{n} rockets, n_steps {T}, policy 8-256-256 x2 (136965 params, "
+                    + ("fused tensor-core kernel, bf16 weights)" if args.fused else f"{args.dtype} GEMMs)"),
         "rollout_env_steps_per_s": n * T / (ms_pass * 1e-3), "ms_per_collection_pass": ms_pass,
         "ms_env_step": ms_env, "ms_env_step_plus_vecnormalize": ms_envnorm, "ms_policy_forward": ms_policy,
         "ms_gae_T_steps": ms_gae, "env_only_steps_per_s": n / (ms_env * 1e-3),
