@@ -19,10 +19,16 @@
 //
 // Weights are bf16 (what torch.autocast(bfloat16) would use), accumulation and biases fp32; the
 // test states the tolerance against the fp32 PyTorch module.  mma.sync, not tcgen05: the shape
-// (K = 256, activations produced and consumed in registers) suits the warp-level instruction, and
-// per 16 rows the kernel is bounded as much by reading W2 from shared memory (128 KiB per row
-// block) as by the tensor pipe; a tcgen05 / TMEM version with M = 128 row blocks is the next step
-// if this neighbour of the hot path ever becomes the bottleneck again.
+// (K = 256, activations produced and consumed in registers) suits the warp-level instruction.
+// Measured (profiles/mlp_forward_r1_summary.txt, 1 Mi rockets): 0.37 ms per net = 395 TFLOP/s on
+// the tensor pipe, which is 70 % active (the warp-level HMMA path peaks near 565 TFLOP/s on this
+// part, a quarter of tcgen05), shared-memory wavefronts at 84 % of peak.  A variant in which each
+// warp keeps two row blocks and shares every W2 fragment between them (half the shared-memory
+// traffic, 255 registers) measured the same 0.38-0.40 ms, so it is the tensor pipe plus the tanh /
+// pack work between the layers that bounds it; a tcgen05 / TMEM version (M = 128 row blocks,
+// activations staged in swizzled shared memory) would be MUFU-bound on the 2 x 256 tanh per rocket
+// at roughly half the time -- the next step if this neighbour of the hot path becomes the
+// bottleneck again.
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
