@@ -48,15 +48,19 @@ def test_gae_kernel_matches_the_oracle():
 
 
 @pytest.mark.gpu
-def test_device_resident_rollout_collection():
-    """configs[4] in miniature: envs -> VecNormalize -> policy -> buffer -> GAE, all on the GPU."""
+@pytest.mark.parametrize("fused", [False, True])
+def test_device_resident_rollout_collection(fused):
+    """configs[4] in miniature: envs -> VecNormalize -> policy -> buffer -> GAE, all on the GPU,
+    with the policy evaluated by PyTorch or by the fused tensor-core kernel."""
     import torch
     from rocket_landing_rl_b200 import (ActorCriticMLP, DeviceRolloutBuffer, DeviceVecNormalize,
-                                        RocketLandingVecEnv, collect_rollout)
+                                        FusedActorCritic, RocketLandingVecEnv, collect_rollout)
     torch.manual_seed(0)
     n, T = 8192, 160
     env = DeviceVecNormalize(RocketLandingVecEnv(n, seed=0), gamma=0.99)
     policy = ActorCriticMLP().cuda()
+    if fused:
+        policy = FusedActorCritic(policy)
     buf = DeviceRolloutBuffer(T, n, "cuda")
     obs = env.reset()
     starts = torch.ones(n, dtype=torch.bool, device="cuda")
