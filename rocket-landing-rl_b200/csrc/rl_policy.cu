@@ -24,8 +24,9 @@
 // the tensor pipe, which is 70 % active (the warp-level HMMA path peaks near 565 TFLOP/s on this
 // part, a quarter of tcgen05), shared-memory wavefronts at 84 % of peak.  A variant in which each
 // warp keeps two row blocks and shares every W2 fragment between them (half the shared-memory
-// traffic, 255 registers) measured the same 0.38-0.40 ms, so it is the tensor pipe plus the tanh /
-// pack work between the layers that bounds it; a tcgen05 / TMEM version (M = 128 row blocks,
+// traffic, 255 registers) measured the same 0.38-0.40 ms, and so did 12 and 16 warps per CTA with
+// layer 2 accumulated in quarters / eighths (168 / 128 registers: 0.36 ms), so it is the warp-level
+// tensor path itself that bounds it; a tcgen05 / TMEM version (M = 128 row blocks,
 // activations staged in swizzled shared memory) would be MUFU-bound on the 2 x 256 tanh per rocket
 // at roughly half the time -- the next step if this neighbour of the hot path becomes the
 // bottleneck again.
