@@ -33,6 +33,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -229,6 +230,247 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const unsigned
     }
 }
 
+
+// =================================================================================================
+// tcgen05 / TMEM version: one CTA steps 128-rocket row blocks; both layers are single-thread-issued
+// tcgen05.mma (M = 128, N = 256, K = 16 per instruction, bf16 x bf16 -> fp32 in tensor memory).
+//
+//   shared memory (operands in the canonical K-major no-swizzle layout: 8 x 16-byte "core matrices",
+//   element (row r, k) at (k / 8) LBO + (r / 8) 128 + (r % 8) 16 + (k % 8) 2 bytes):
+//     W2s  256 x 256 bf16, LBO 4096   (loaded once per CTA)        W1s  256 x 16, LBO 4096
+//     A2s  128 x 256 bf16, LBO 2048   (layer-1 activations)        A1s  128 x 16, LBO 2048 (obs hi | lo)
+//   tensor memory (512 columns): D1 = columns 0..255 (layer 1), D2 = columns 256..511 (layer 2)
+//
+//   per row block:  obs -> A1s | MMA 1 -> D1 | all 8 warps: D1 -> +b1, tanh, bf16 -> A2s |
+//                   16 x MMA 2 -> D2 | all 8 warps: D2 -> +b2, tanh, head dot -> out
+//   Warp w reads TMEM lanes 32 (w % 4) .. + 31 (its rows) and the column half w / 4, so the 2 x 256
+//   tanh per rocket (the MUFU pipe is what bounds this kernel once the GEMM is on tcgen05) are spread
+//   over 256 threads.  Generic-proxy writes of A1s / A2s are published to the tensor core with
+//   fence.proxy.async + a CTA barrier; MMA completion comes back through tcgen05.commit -> mbarrier.
+// =================================================================================================
+namespace tc5 {
+
+constexpr int kM = 128;                       // rows per block = TMEM lanes
+constexpr int kLboW = 4096, kLboA = 2048, kSbo = 128;
+constexpr int kSmW2 = 0;                                  // 131072
+constexpr int kSmW1 = kSmW2 + kHidden * kHidden * 2;      // 8192
+constexpr int kSmA2 = kSmW1 + kHidden * 16 * 2;           // 65536
+constexpr int kSmA1 = kSmA2 + kM * kHidden * 2;           // 4096
+constexpr int kSmB1 = kSmA1 + kM * 16 * 2;
+constexpr int kSmB2 = kSmB1 + kHidden * 4;
+constexpr int kSmW3 = kSmB2 + kHidden * 4;
+constexpr int kSmB3 = kSmW3 + 2 * kHidden * 4;
+constexpr int kSmRed = kSmB3 + 16;                        // [2 halves][128 rows][2] f32
+constexpr int kSmBar = kSmRed + 2 * kM * 2 * 4;           // 2 mbarriers + TMEM base address
+constexpr int kSmemBytes = kSmBar + 32;
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A / B bf16, both K-major, N = 256, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kHidden >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), no swizzle, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
+           (1ull << 46);
+}
+
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}\n" :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+
+template <int kOut>
+__global__ void __launch_bounds__(256, 1) mlp_forward_tc5_kernel(const unsigned char* __restrict__ blob,
+                                                                  const float* __restrict__ obs, float* __restrict__ out,
+                                                                  int64_t n) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar1 = sbase + kSmBar, bar2 = sbase + kSmBar + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 16);
+
+    // ---- one-time setup: weights in the canonical layout, barriers, tensor memory ------------------
+    for (int c = tid; c < kHidden * 32; c += 256) {               // W2: chunk (row n, 8 k's kc); consecutive threads -> consecutive rows
+        const int n_row = c & 255, kc = c >> 8;
+        *reinterpret_cast<uint4*>(smem + kSmW2 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
+            *reinterpret_cast<const uint4*>(blob + kOffW2 + n_row * (kHidden * 2) + kc * 16);
+    }
+    for (int c = tid; c < kHidden * 2; c += 256) {                // W1 stacked twice: 2 chunks per row
+        const int n_row = c & 255, kc = c >> 8;
+        *reinterpret_cast<uint4*>(smem + kSmW1 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
+            *reinterpret_cast<const uint4*>(blob + kOffW1 + n_row * 32 + kc * 16);
+    }
+    for (int c = tid; c < kHidden * 4 / 16; c += 256)
+        *reinterpret_cast<uint4*>(smem + kSmB1 + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffB1 + c * 16);
+    for (int c = tid; c < (kSmRed - kSmB2) / 16; c += 256)        // b2 | W3 | b3
+        *reinterpret_cast<uint4*>(smem + kSmB2 + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffB2 + c * 16);
+    if (tid == 0) {
+        mbar_init(bar1, 1);
+        mbar_init(bar2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {                                              // one warp allocates all 512 columns (1 CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_proxy();                                          // the weights were written through the generic proxy
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    const float* b1s = reinterpret_cast<const float*>(smem + kSmB1);
+    const float* b2s = reinterpret_cast<const float*>(smem + kSmB2);
+    const float* w3s = reinterpret_cast<const float*>(smem + kSmW3);
+    const float* b3s = reinterpret_cast<const float*>(smem + kSmB3);
+    float* red = reinterpret_cast<float*>(smem + kSmRed);
+
+    const int row = 32 * (warp & 3) + lane;                       // this thread's row of the block = its TMEM lane
+    const int half = warp >> 2;                                   // ... and its half of the 256 columns
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+    uint32_t parity = 0;
+
+    const int64_t n_blocks = (n + kM - 1) / kM;
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const int64_t row0 = blk * kM;
+        // ---- observations -> A1s: k 0..7 = bf16 high parts, k 8..15 = low parts ----------------------
+        if (tid < kM) {
+            float x[8];
+            const int64_t r = row0 + tid;
+            if (r < n) {
+                const float4 a = *reinterpret_cast<const float4*>(obs + r * kObs);
+                const float4 b = *reinterpret_cast<const float4*>(obs + r * kObs + 4);
+                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = 0.f;
+            }
+            float hi[8], lo[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) split_bf16(x[k], hi[k], lo[k]);
+            unsigned char* dst = smem + kSmA1 + (tid >> 3) * kSbo + (tid & 7) * 16;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+            *reinterpret_cast<uint4*>(dst + kLboA) = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+        }
+        fence_async_proxy();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {                                           // layer 1: D1 = A1 (128 x 16) W1^T (16 x 256)
+            fence_after_sync();
+            mma_f16_ss(tmem, smem_desc(sbase + kSmA1, kLboA, kSbo), smem_desc(sbase + kSmW1, kLboW, kSbo), kIdesc, 0u);
+            mma_commit(bar1);
+        }
+        mbar_wait(bar1, parity);
+        fence_after_sync();
+        // ---- epilogue 1: D1 -> tanh(. + b1) -> bf16 -> A2s (this thread: its row, 128 of the 256 units) --
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            float v[32];
+            const int col0 = 128 * half + 32 * c;
+            tmem_ld32(t_lane + (uint32_t)col0, v);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {                      // 8 units = one 16-byte chunk of the K-major operand
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 bias = *reinterpret_cast<const float2*>(b1s + col0 + 8 * k4 + 2 * j);
+                    w[j] = pack_bf16(tanh_fast(v[8 * k4 + 2 * j] + bias.x), tanh_fast(v[8 * k4 + 2 * j + 1] + bias.y));
+                }
+                const int kc = (col0 >> 3) + k4;
+                *reinterpret_cast<uint4*>(smem + kSmA2 + kc * kLboA + (row >> 3) * kSbo + (row & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+        fence_async_proxy();
+        fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {                                           // layer 2: D2 = A2 (128 x 256) W2^T, 16 steps of K = 16
+            fence_after_sync();
+#pragma unroll
+            for (int ks = 0; ks < kHidden / 16; ++ks)
+                mma_f16_ss(tmem + 256u, smem_desc(sbase + kSmA2 + ks * 2 * kLboA, kLboA, kSbo),
+                           smem_desc(sbase + kSmW2 + ks * 2 * kLboW, kLboW, kSbo), kIdesc, ks > 0 ? 1u : 0u);
+            mma_commit(bar2);
+        }
+        mbar_wait(bar2, parity);
+        fence_after_sync();
+        parity ^= 1u;
+        // ---- epilogue 2: D2 -> tanh(. + b2) -> head dot over this thread's 128 units ---------------------
+        float s[kOut];
+#pragma unroll
+        for (int o = 0; o < kOut; ++o) s[o] = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            float v[32];
+            const int col0 = 128 * half + 32 * c;
+            tmem_ld32(t_lane + 256u + (uint32_t)col0, v);
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+                const float4 bias = *reinterpret_cast<const float4*>(b2s + col0 + k);
+                const float h0 = tanh_fast(v[k] + bias.x), h1 = tanh_fast(v[k + 1] + bias.y);
+                const float h2 = tanh_fast(v[k + 2] + bias.z), h3 = tanh_fast(v[k + 3] + bias.w);
+#pragma unroll
+                for (int o = 0; o < kOut; ++o) {
+                    const float4 w = *reinterpret_cast<const float4*>(w3s + o * kHidden + col0 + k);
+                    s[o] = fmaf(h0, w.x, fmaf(h1, w.y, fmaf(h2, w.z, fmaf(h3, w.w, s[o]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kOut; ++o) red[(half * kM + row) * 2 + o] = s[o];
+        fence_before_sync();                                      // this thread's TMEM reads are done before the next block's MMAs
+        __syncthreads();
+        if (tid < kM) {
+            const int64_t r = row0 + tid;
+            if (r < n) {
+#pragma unroll
+                for (int o = 0; o < kOut; ++o) out[r * kOut + o] = red[tid * 2 + o] + red[(kM + tid) * 2 + o] + b3s[o];
+            }
+        }
+        // (red is rewritten only after two more CTA barriers; A1s only after MMA 1 of this block completed)
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+}
+
+}  // namespace tc5
+
 }  // namespace
 
 extern "C" {
@@ -248,9 +490,26 @@ int rl_mlp_forward(const void* blob, const float* obs, float* out, int64_t n, in
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e;
+    static const bool use_tc5 = [] { const char* t = getenv("RL_B200_MLP_TCGEN05"); return t && t[0] == '1'; }();
+    if (use_tc5) {
+        const int64_t blocks5 = (n + tc5::kM - 1) / tc5::kM;
+        const int grid5 = (int)(blocks5 < sms ? blocks5 : sms);
+        if (out_dim == 2) {
+            e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
+            if (e == cudaSuccess)
+                tc5::mlp_forward_tc5_kernel<2><<<grid5, 256, tc5::kSmemBytes, (cudaStream_t)stream>>>((const unsigned char*)blob, obs, out, n);
+        } else {
+            e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
+            if (e == cudaSuccess)
+                tc5::mlp_forward_tc5_kernel<1><<<grid5, 256, tc5::kSmemBytes, (cudaStream_t)stream>>>((const unsigned char*)blob, obs, out, n);
+        }
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) return po_fail(RL_E_CUDA, "rl_mlp_forward (tcgen05) launch failed: %s", cudaGetErrorString(e));
+        return RL_OK;
+    }
     const int64_t blocks = (n + kRowsPerCta - 1) / kRowsPerCta;
     const int grid = (int)(blocks < sms ? blocks : sms);
-    cudaError_t e;
     if (out_dim == 2) {
         e = cudaFuncSetAttribute(mlp_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e == cudaSuccess)
