@@ -260,8 +260,8 @@ constexpr int kSmB1 = kSmA1 + kM * 16 * 2;
 constexpr int kSmB2 = kSmB1 + kHidden * 4;
 constexpr int kSmW3 = kSmB2 + kHidden * 4;
 constexpr int kSmB3 = kSmW3 + 2 * kHidden * 4;
-constexpr int kSmRed = kSmB3 + 16;                        // [2 halves][128 rows][2] f32
-constexpr int kSmBar = kSmRed + 2 * kM * 2 * 4;           // 2 mbarriers + TMEM base address
+constexpr int kSmRed = kSmB3 + 16;                        // [column slices][128 rows][2] f32
+constexpr int kSmBar = kSmRed + 4 * kM * 2 * 4;           // 2 mbarriers + TMEM base address
 constexpr int kSmemBytes = kSmBar + 32;
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -299,9 +299,9 @@ __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// 32 consecutive fp32 columns of this thread's TMEM lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 32 consecutive fp32 columns of this thread's TMEM lane: issue, and (later) wait.  The wait names
+// the registers as in/out operands so that no use of them can be scheduled above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -311,13 +311,33 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr) : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = __uint_as_float(r[k]);
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :: "memory");
+}
+// tanh of two bf16 values in one MUFU operation
+__device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
+    uint32_t y;
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
 }
 
+#ifndef RL_MLP_TC5_SPLIT
+#define RL_MLP_TC5_SPLIT 4                  // warps per TMEM lane quarter = column slices per row
+#endif
+constexpr int kSplit = RL_MLP_TC5_SPLIT;
+constexpr int kTc5Threads = 128 * kSplit;
+constexpr int kColsPerThread = kHidden / kSplit;
+constexpr int kChunks = kColsPerThread / 32;
+static_assert(kSmBar - kSmRed >= kSplit * kM * 2 * 4, "head partial sums");
+
 template <int kOut>
-__global__ void __launch_bounds__(256, 1) mlp_forward_tc5_kernel(const unsigned char* __restrict__ blob,
+__global__ void __launch_bounds__(kTc5Threads, 1) mlp_forward_tc5_kernel(const unsigned char* __restrict__ blob,
                                                                   const float* __restrict__ obs, float* __restrict__ out,
                                                                   int64_t n) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -327,19 +347,19 @@ __global__ void __launch_bounds__(256, 1) mlp_forward_tc5_kernel(const unsigned 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 16);
 
     // ---- one-time setup: weights in the canonical layout, barriers, tensor memory ------------------
-    for (int c = tid; c < kHidden * 32; c += 256) {               // W2: chunk (row n, 8 k's kc); consecutive threads -> consecutive rows
+    for (int c = tid; c < kHidden * 32; c += kTc5Threads) {               // W2: chunk (row n, 8 k's kc); consecutive threads -> consecutive rows
         const int n_row = c & 255, kc = c >> 8;
         *reinterpret_cast<uint4*>(smem + kSmW2 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
             *reinterpret_cast<const uint4*>(blob + kOffW2 + n_row * (kHidden * 2) + kc * 16);
     }
-    for (int c = tid; c < kHidden * 2; c += 256) {                // W1 stacked twice: 2 chunks per row
+    for (int c = tid; c < kHidden * 2; c += kTc5Threads) {                // W1 stacked twice: 2 chunks per row
         const int n_row = c & 255, kc = c >> 8;
         *reinterpret_cast<uint4*>(smem + kSmW1 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
             *reinterpret_cast<const uint4*>(blob + kOffW1 + n_row * 32 + kc * 16);
     }
-    for (int c = tid; c < kHidden * 4 / 16; c += 256)
+    for (int c = tid; c < kHidden * 4 / 16; c += kTc5Threads)
         *reinterpret_cast<uint4*>(smem + kSmB1 + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffB1 + c * 16);
-    for (int c = tid; c < (kSmRed - kSmB2) / 16; c += 256)        // b2 | W3 | b3
+    for (int c = tid; c < (kSmRed - kSmB2) / 16; c += kTc5Threads)        // b2 | W3 | b3
         *reinterpret_cast<uint4*>(smem + kSmB2 + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffB2 + c * 16);
     if (tid == 0) {
         mbar_init(bar1, 1);
@@ -363,25 +383,26 @@ __global__ void __launch_bounds__(256, 1) mlp_forward_tc5_kernel(const unsigned 
     float* red = reinterpret_cast<float*>(smem + kSmRed);
 
     const int row = 32 * (warp & 3) + lane;                       // this thread's row of the block = its TMEM lane
-    const int half = warp >> 2;                                   // ... and its half of the 256 columns
+    const int half = warp >> 2;                                   // ... and its slice of the 256 columns
     const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
     uint32_t parity = 0;
 
     const int64_t n_blocks = (n + kM - 1) / kM;
-    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const int64_t row0 = blk * kM;
-        // ---- observations -> A1s: k 0..7 = bf16 high parts, k 8..15 = low parts ----------------------
+    // Layer 1 of the NEXT row block is issued as soon as epilogue 1 of this one has drained D1, so its
+    // latency -- and that of the global load of its observations, held in registers one block ahead --
+    // never sits on the critical path.
+    float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
+    auto load_obs = [&](int64_t blk) {                            // threads 0..127: one observation row each
+        oa = ob = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int64_t r = blk * kM + tid;
+        if (tid < kM && blk < n_blocks && r < n) {
+            oa = *reinterpret_cast<const float4*>(obs + r * kObs);
+            ob = *reinterpret_cast<const float4*>(obs + r * kObs + 4);
+        }
+    };
+    auto stage_obs = [&]() {                                      // -> A1s: k 0..7 = bf16 high parts, k 8..15 = low parts
         if (tid < kM) {
-            float x[8];
-            const int64_t r = row0 + tid;
-            if (r < n) {
-                const float4 a = *reinterpret_cast<const float4*>(obs + r * kObs);
-                const float4 b = *reinterpret_cast<const float4*>(obs + r * kObs + 4);
-                x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) x[k] = 0.f;
-            }
+            const float x[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
             float hi[8], lo[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) split_bf16(x[k], hi[k], lo[k]);
@@ -389,44 +410,74 @@ __global__ void __launch_bounds__(256, 1) mlp_forward_tc5_kernel(const unsigned 
             *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
             *reinterpret_cast<uint4*>(dst + kLboA) = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
         }
+    };
+    auto issue_layer1 = [&]() {                                   // thread 0: D1 = A1 (128 x 16) W1^T (16 x 256)
+        mma_f16_ss(tmem, smem_desc(sbase + kSmA1, kLboA, kSbo), smem_desc(sbase + kSmW1, kLboW, kSbo), kIdesc, 0u);
+        mma_commit(bar1);
+    };
+    if ((int64_t)blockIdx.x < n_blocks) {                         // prologue: layer 1 of the first block
+        load_obs(blockIdx.x);
+        stage_obs();
+        load_obs((int64_t)blockIdx.x + gridDim.x);
         fence_async_proxy();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {                                           // layer 1: D1 = A1 (128 x 16) W1^T (16 x 256)
+        if (tid == 0) {
             fence_after_sync();
-            mma_f16_ss(tmem, smem_desc(sbase + kSmA1, kLboA, kSbo), smem_desc(sbase + kSmW1, kLboW, kSbo), kIdesc, 0u);
-            mma_commit(bar1);
+            issue_layer1();
         }
-        mbar_wait(bar1, parity);
+    }
+    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        const int64_t row0 = blk * kM;
+        const bool has_next = blk + gridDim.x < n_blocks;
+        mbar_wait(bar1, parity);                                  // layer 1 of this block is in D1; A1s is free again
         fence_after_sync();
-        // ---- epilogue 1: D1 -> tanh(. + b1) -> bf16 -> A2s (this thread: its row, 128 of the 256 units) --
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            float v[32];
-            const int col0 = 128 * half + 32 * c;
-            tmem_ld32(t_lane + (uint32_t)col0, v);
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {                      // 8 units = one 16-byte chunk of the K-major operand
-                uint32_t w[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 bias = *reinterpret_cast<const float2*>(b1s + col0 + 8 * k4 + 2 * j);
-                    w[j] = pack_bf16(tanh_fast(v[8 * k4 + 2 * j] + bias.x), tanh_fast(v[8 * k4 + 2 * j + 1] + bias.y));
-                }
-                const int kc = (col0 >> 3) + k4;
-                *reinterpret_cast<uint4*>(smem + kSmA2 + kc * kLboA + (row >> 3) * kSbo + (row & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
+        if (has_next) {
+            stage_obs();                                          // next block's observations (published by the barriers below)
+            load_obs(blk + 2 * (int64_t)gridDim.x);
         }
-        fence_async_proxy();
-        fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {                                           // layer 2: D2 = A2 (128 x 256) W2^T, 16 steps of K = 16
-            fence_after_sync();
+        // ---- epilogue 1: D1 -> tanh(. + b1) -> bf16 -> A2s (this thread: its row, 128 of the 256 units),
+        // ---- 32 units at a time; as soon as the whole CTA has written a slice of K, the layer-2 MMAs that
+        // ---- consume it are issued, so that the tensor core works while the MUFU-bound epilogue goes on
+        {
+            uint32_t ra[32], rb[32];
+            tmem_ld32_issue(t_lane + (uint32_t)(kColsPerThread * half), ra);
 #pragma unroll
-            for (int ks = 0; ks < kHidden / 16; ++ks)
-                mma_f16_ss(tmem + 256u, smem_desc(sbase + kSmA2 + ks * 2 * kLboA, kLboA, kSbo),
-                           smem_desc(sbase + kSmW2 + ks * 2 * kLboW, kLboW, kSbo), kIdesc, ks > 0 ? 1u : 0u);
-            mma_commit(bar2);
+            for (int c = 0; c < kChunks; ++c) {
+                uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+                uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+                tmem_ld_wait(cur);
+                if (c + 1 < kChunks) tmem_ld32_issue(t_lane + (uint32_t)(kColsPerThread * half + 32 * (c + 1)), nxt);
+                const int col0 = kColsPerThread * half + 32 * c;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {                  // 8 units = one 16-byte chunk of the K-major operand
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 bias = *reinterpret_cast<const float2*>(b1s + col0 + 8 * k4 + 2 * j);
+                        w[j] = tanh_bf16x2(pack_bf16(__uint_as_float(cur[8 * k4 + 2 * j]) + bias.x,
+                                                     __uint_as_float(cur[8 * k4 + 2 * j + 1]) + bias.y));
+                    }
+                    const int kc = (col0 >> 3) + k4;
+                    *reinterpret_cast<uint4*>(smem + kSmA2 + kc * kLboA + (row >> 3) * kSbo + (row & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                fence_async_proxy();
+                fence_before_sync();
+                __syncthreads();
+                if (tid == 0) {                                   // every column slice has written its K range [32 c, 32 c + 32)
+                    fence_after_sync();
+#pragma unroll
+                    for (int j = 0; j < 2 * kSplit; ++j) {
+                        const int ks = (kColsPerThread / 16) * (j >> 1) + 2 * c + (j & 1);
+                        mma_f16_ss(tmem + 256u, smem_desc(sbase + kSmA2 + ks * 2 * kLboA, kLboA, kSbo),
+                                   smem_desc(sbase + kSmW2 + ks * 2 * kLboW, kLboW, kSbo), kIdesc, (c | j) ? 1u : 0u);
+                    }
+                    if (c == kChunks - 1) {
+                        mma_commit(bar2);
+                        if (has_next) issue_layer1();             // every thread's reads of D1 are complete (barrier above)
+                    }
+                }
+            }
         }
         mbar_wait(bar2, parity);
         fence_after_sync();
@@ -435,20 +486,26 @@ __global__ void __launch_bounds__(256, 1) mlp_forward_tc5_kernel(const unsigned 
         float s[kOut];
 #pragma unroll
         for (int o = 0; o < kOut; ++o) s[o] = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            float v[32];
-            const int col0 = 128 * half + 32 * c;
-            tmem_ld32(t_lane + 256u + (uint32_t)col0, v);
+        {
+            uint32_t ra[32], rb[32];
+            tmem_ld32_issue(t_lane + 256u + (uint32_t)(kColsPerThread * half), ra);
 #pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-                const float4 bias = *reinterpret_cast<const float4*>(b2s + col0 + k);
-                const float h0 = tanh_fast(v[k] + bias.x), h1 = tanh_fast(v[k + 1] + bias.y);
-                const float h2 = tanh_fast(v[k + 2] + bias.z), h3 = tanh_fast(v[k + 3] + bias.w);
+            for (int c = 0; c < kChunks; ++c) {
+                uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+                uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+                tmem_ld_wait(cur);
+                if (c + 1 < kChunks) tmem_ld32_issue(t_lane + 256u + (uint32_t)(kColsPerThread * half + 32 * (c + 1)), nxt);
+                const int col0 = kColsPerThread * half + 32 * c;
 #pragma unroll
-                for (int o = 0; o < kOut; ++o) {
-                    const float4 w = *reinterpret_cast<const float4*>(w3s + o * kHidden + col0 + k);
-                    s[o] = fmaf(h0, w.x, fmaf(h1, w.y, fmaf(h2, w.z, fmaf(h3, w.w, s[o]))));
+                for (int k = 0; k < 32; k += 4) {
+                    const float4 bias = *reinterpret_cast<const float4*>(b2s + col0 + k);
+                    const float h0 = tanh_fast(__uint_as_float(cur[k]) + bias.x), h1 = tanh_fast(__uint_as_float(cur[k + 1]) + bias.y);
+                    const float h2 = tanh_fast(__uint_as_float(cur[k + 2]) + bias.z), h3 = tanh_fast(__uint_as_float(cur[k + 3]) + bias.w);
+#pragma unroll
+                    for (int o = 0; o < kOut; ++o) {
+                        const float4 w = *reinterpret_cast<const float4*>(w3s + o * kHidden + col0 + k);
+                        s[o] = fmaf(h0, w.x, fmaf(h1, w.y, fmaf(h2, w.z, fmaf(h3, w.w, s[o]))));
+                    }
                 }
             }
         }
@@ -460,7 +517,12 @@ __global__ void __launch_bounds__(256, 1) mlp_forward_tc5_kernel(const unsigned 
             const int64_t r = row0 + tid;
             if (r < n) {
 #pragma unroll
-                for (int o = 0; o < kOut; ++o) out[r * kOut + o] = red[tid * 2 + o] + red[(kM + tid) * 2 + o] + b3s[o];
+                for (int o = 0; o < kOut; ++o) {
+                    float v = b3s[o];
+#pragma unroll
+                    for (int sl = 0; sl < kSplit; ++sl) v += red[(sl * kM + tid) * 2 + o];
+                    out[r * kOut + o] = v;
+                }
             }
         }
         // (red is rewritten only after two more CTA barriers; A1s only after MMA 1 of this block completed)
@@ -498,11 +560,11 @@ int rl_mlp_forward(const void* blob, const float* obs, float* out, int64_t n, in
         if (out_dim == 2) {
             e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
             if (e == cudaSuccess)
-                tc5::mlp_forward_tc5_kernel<2><<<grid5, 256, tc5::kSmemBytes, (cudaStream_t)stream>>>((const unsigned char*)blob, obs, out, n);
+                tc5::mlp_forward_tc5_kernel<2><<<grid5, tc5::kTc5Threads, tc5::kSmemBytes, (cudaStream_t)stream>>>((const unsigned char*)blob, obs, out, n);
         } else {
             e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
             if (e == cudaSuccess)
-                tc5::mlp_forward_tc5_kernel<1><<<grid5, 256, tc5::kSmemBytes, (cudaStream_t)stream>>>((const unsigned char*)blob, obs, out, n);
+                tc5::mlp_forward_tc5_kernel<1><<<grid5, tc5::kTc5Threads, tc5::kSmemBytes, (cudaStream_t)stream>>>((const unsigned char*)blob, obs, out, n);
         }
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) return po_fail(RL_E_CUDA, "rl_mlp_forward (tcgen05) launch failed: %s", cudaGetErrorString(e));
