@@ -270,12 +270,24 @@ int rl_gae(const float *rewards, const float *values, const uint8_t *episode_sta
  *   f32  [256]      b2
  *   f32  [2][256]   W3 (second row ignored when out_dim = 1)
  *   f32  [4]        b3 (first out_dim used)
- * obs float32 [n][8], out float32 [n][out_dim], out_dim 1 or 2.  DEVICE pointers, enqueue only. */
+ * obs float32 [n][8] (16-byte aligned), out float32 [n][out_dim], out_dim 1 or 2.  DEVICE pointers,
+ * enqueue only.
+ *
+ * rl_policy_sample: the policy net (out_dim 2) with SB3's DiagGaussian sampling fused into its
+ * epilogue (what OnPolicyAlgorithm.collect_rollouts does around policy.forward): actions[n][2] =
+ * mean + exp(log_std) eps, eps ~ N(0, 1) (unclipped: what the rollout buffer stores); clipped[n][2]
+ * = actions clipped to the Box [low2, high2] (what env.step receives); log_prob[n]; mean[n][2]
+ * optional (nullable).  eps is Philox4x32-10 keyed by `seed` at counter (row, draw) + Box-Muller:
+ * pass a different `draw` on every call.  log_std is a DEVICE pointer to 2 floats; low2 / high2 are
+ * HOST pointers to 2 floats. */
 #define RL_MLP_HIDDEN 256
 #define RL_MLP_BLOB_BYTES 143376
 const char *rl_policy_last_error(void);
 int64_t rl_mlp_blob_bytes(void);
 int rl_mlp_forward(const void *blob, const float *obs, float *out, int64_t n, int out_dim, void *stream);
+int rl_policy_sample(const void *blob, const float *obs, const float *log_std, uint64_t seed, uint64_t draw,
+                     const float *low2, const float *high2, float *actions, float *clipped, float *log_prob,
+                     float *mean, int64_t n, void *stream);
 
 #ifdef __cplusplus
 }

@@ -4,32 +4,38 @@
 // (scripts/train.py:117-134): two separate tanh MLPs 8 -> 256 -> 256 with a linear head (2 action
 // means / 1 value), 136 965 parameters as in assets/model/v3.  Run layer by layer (PyTorch / cuBLAS)
 // the 256-wide activations of a million rockets go to HBM and back after every layer and the
-// collection loop spends 3.3 of its 3.6 ms per step there.  Here one launch evaluates one whole net:
-// a 16-rocket row block stays in the registers of one warp from the observation to the head.
+// collection loop spends 3.3 of its 3.6 ms per step there.  Here one launch evaluates one whole net
+// and nothing but the observation (32 B) and the head output (4-8 B) of a rocket touches HBM.
 //
-//   layer 1  (8 -> 256)    tensor cores, K = 16 = [bf16 high part | bf16 low part] of the fp32
-//                          observation against W1 stacked twice: the input keeps ~16 mantissa bits
-//   tanh                   MUFU tanh.approx on the fp32 accumulators
-//   layer 2  (256 -> 256)  tensor cores (mma.sync m16n8k16, bf16 x bf16 -> fp32).  The accumulator
-//                          fragments of layer 1 ARE the A fragments of layer 2 (same lane / register
-//                          map once packed to bf16x2), so the activations never leave the register
-//                          file; W2 (bf16, 128 KiB) sits in shared memory for the life of the CTA, its
-//                          rows padded to 528 B so that ldmatrix is bank-conflict free
-//   tanh, head             fp32 on the CUDA cores from the accumulator fragments, quad shuffle reduce
+// tcgen05 / TMEM: one CTA steps 128-rocket row blocks; both layers are single-thread-issued
+// tcgen05.mma (M = 128, N = 256, K = 16 per instruction, bf16 x bf16 -> fp32 in tensor memory).
 //
-// Weights are bf16 (what torch.autocast(bfloat16) would use), accumulation and biases fp32; the
-// test states the tolerance against the fp32 PyTorch module.  mma.sync, not tcgen05: the shape
-// (K = 256, activations produced and consumed in registers) suits the warp-level instruction.
-// Measured (profiles/mlp_forward_r1_summary.txt, 1 Mi rockets): 0.37 ms per net = 395 TFLOP/s on
-// the tensor pipe, which is 70 % active (the warp-level HMMA path peaks near 565 TFLOP/s on this
-// part, a quarter of tcgen05), shared-memory wavefronts at 84 % of peak.  A variant in which each
-// warp keeps two row blocks and shares every W2 fragment between them (half the shared-memory
-// traffic, 255 registers) measured the same 0.38-0.40 ms, and so did 12 and 16 warps per CTA with
-// layer 2 accumulated in quarters / eighths (168 / 128 registers: 0.36 ms), so it is the warp-level
-// tensor path itself that bounds it; a tcgen05 / TMEM version (M = 128 row blocks,
-// activations staged in swizzled shared memory) would be MUFU-bound on the 2 x 256 tanh per rocket
-// at roughly half the time -- the next step if this neighbour of the hot path becomes the
-// bottleneck again.
+//   shared memory (operands in the canonical K-major no-swizzle layout: 8 x 16-byte "core matrices",
+//   element (row r, k) at (k / 8) LBO + (r / 8) 128 + (r % 8) 16 + (k % 8) 2 bytes):
+//     W2s  256 x 256 bf16, LBO 4096   (loaded once per CTA)        W1s  256 x 16, LBO 4096
+//     A2s  128 x 256 bf16, LBO 2048   (layer-1 activations)        A1s  128 x 16, LBO 2048 (obs hi | lo)
+//   tensor memory (512 columns): D1 = columns 0..255 (layer 1), D2 = columns 256..511 (layer 2)
+//
+//   layer 1 (8 -> 256)   K = 16 = [bf16 high part | bf16 low part] of the fp32 observation against W1
+//                        stacked twice: the input keeps ~16 mantissa bits
+//   epilogue 1           all 16 warps: D1 -> +b1, tanh, bf16 -> A2s, 32 units at a time; as soon as the
+//                        whole CTA has written a slice of K the layer-2 MMAs that consume it are issued
+//   layer 2 (256 -> 256) 16 x tcgen05.mma into D2; when the last one is issued, layer 1 of the NEXT row
+//                        block follows it (its observations were loaded one block ahead)
+//   epilogue 2           D2 -> +b2, tanh, head dot product -> out (or: sample the action, see below)
+//
+//   Warp w reads TMEM lanes 32 (w % 4) .. + 31 (its rows) and column slice w / 4, so the 2 x 256 tanh
+//   per rocket -- the MUFU pipe is what bounds this kernel once the GEMM is on tcgen05 -- are spread
+//   over 512 threads.  Generic-proxy writes of A1s / A2s are published to the tensor core with
+//   fence.proxy.async + a CTA barrier; MMA completion comes back through tcgen05.commit -> mbarrier.
+//
+// Weights are bf16 (what torch.autocast(bfloat16) would use), accumulation and biases fp32; measured
+// against the fp32 module: rms error 8e-4, max 4e-3 on outputs of mean magnitude 0.24 (autocast:
+// 1.2e-3 / 7e-3; tools/mlp_error_probe.py), and the test states the tolerance.
+// Measured (profiles/README.md): 0.22 ms per net at 1 Mi rockets.  The first version of this kernel
+// used warp-level mma.sync with the activations chained through registers (layer-1 accumulator
+// fragments = layer-2 A fragments): 0.37 ms, 70 % of the legacy tensor path's peak -- a quarter of
+// tcgen05's; it is in the history of this file.
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -39,6 +45,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/rocket_landing_b200.h"
+#include "rl_device.cuh"
 
 namespace {
 
@@ -53,10 +60,6 @@ int po_fail(int code, const char* fmt, ...) {
 
 constexpr int kHidden = RL_MLP_HIDDEN;     // 256
 constexpr int kObs = 8;
-constexpr int kThreads = 256;              // 8 warps x 16 rows = 128 rows per CTA iteration
-constexpr int kRowsPerWarp = 16;
-constexpr int kRowsPerCta = (kThreads / 32) * kRowsPerWarp;
-
 // packed weights in global memory (RL_MLP_BLOB_BYTES, built by the host side: rollout.py pack_mlp)
 constexpr int kOffW1 = 0;                               // bf16 [256][16]: W1[n][0..7] twice
 constexpr int kOffB1 = kOffW1 + kHidden * 16 * 2;       // f32 [256]
@@ -66,30 +69,7 @@ constexpr int kOffW3 = kOffB2 + kHidden * 4;            // f32 [2][256]     (sec
 constexpr int kOffB3 = kOffW3 + 2 * kHidden * 4;        // f32 [2]
 static_assert(kOffB3 + 16 == RL_MLP_BLOB_BYTES, "blob layout");
 
-// shared memory: padded copies
-constexpr int kW2Stride = kHidden * 2 + 16;             // 528 B: 8 consecutive rows hit 8 different 16-byte bank groups
-constexpr int kW1Stride = 48;                           // 16 bf16 + 16 B pad, same reason
-constexpr int kSmW2 = 0;
-constexpr int kSmW1 = kSmW2 + kHidden * kW2Stride;
-constexpr int kSmB1 = kSmW1 + kHidden * kW1Stride;
-constexpr int kSmB2 = kSmB1 + kHidden * 4;
-constexpr int kSmW3 = kSmB2 + kHidden * 4;
-constexpr int kSmB3 = kSmW3 + 2 * kHidden * 4;
-constexpr int kSmemBytes = kSmB3 + 16;
-
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-
-// D (16x8, fp32) += A (16x16, bf16, row) x B (16x8, bf16, col)
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 __device__ __forceinline__ float tanh_fast(float x) {
     float y;
@@ -108,146 +88,21 @@ __device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
     lo = x - hi;
 }
 
-template <int kOut>
-__global__ void __launch_bounds__(kThreads, 1) mlp_forward_kernel(const unsigned char* __restrict__ blob,
-                                                                   const float* __restrict__ obs, float* __restrict__ out,
-                                                                   int64_t n) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// Optional epilogue of the policy net (out_dim 2): draw the action the way SB3's DiagGaussian
+// distribution does -- action = mean + exp(log_std) eps, eps ~ N(0, 1); log-probability summed over
+// the two components; the Box-clipped copy that goes to env.step (SB3 clips before stepping and
+// stores the unclipped sample) -- with counter-based noise: Philox4x32-10 keyed by `seed`, counter
+// (row, draw), Box-Muller.  All null / zero: plain forward.
+struct SampleArgs {
+    const float* log_std;      // device [2]
+    float* actions;            // [n][2] unclipped samples (null: no sampling)
+    float* clipped;            // [n][2]
+    float* log_prob;           // [n]
+    float* mean;               // [n][2], nullable
+    unsigned long long seed, draw;
+    float lo0, lo1, hi0, hi1;
+};
 
-    // ---- weights -> shared memory, once per CTA (persistent grid) --------------------------------
-    for (int c = tid; c < kHidden * 32; c += kThreads) {          // W2: 256 rows x 32 chunks of 16 B
-        const int row = c >> 5, ch = c & 31;
-        *reinterpret_cast<uint4*>(smem + kSmW2 + row * kW2Stride + ch * 16) =
-            *reinterpret_cast<const uint4*>(blob + kOffW2 + row * (kHidden * 2) + ch * 16);
-    }
-    for (int c = tid; c < kHidden * 2; c += kThreads) {           // W1 (stacked twice): 256 rows x 2 chunks
-        const int row = c >> 1, ch = c & 1;
-        *reinterpret_cast<uint4*>(smem + kSmW1 + row * kW1Stride + ch * 16) =
-            *reinterpret_cast<const uint4*>(blob + kOffW1 + row * 32 + ch * 16);
-    }
-    for (int c = tid; c < kHidden * 4 / 16; c += kThreads)        // b1
-        *reinterpret_cast<uint4*>(smem + kSmB1 + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffB1 + c * 16);
-    for (int c = tid; c < (kSmemBytes - kSmB2) / 16; c += kThreads)   // b2 | W3 | b3: contiguous in the blob and here
-        *reinterpret_cast<uint4*>(smem + kSmB2 + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffB2 + c * 16);
-    __syncthreads();
-
-    const float* b1s = reinterpret_cast<const float*>(smem + kSmB1);
-    const float* b2s = reinterpret_cast<const float*>(smem + kSmB2);
-    const float* w3s = reinterpret_cast<const float*>(smem + kSmW3);
-    const float* b3s = reinterpret_cast<const float*>(smem + kSmB3);
-
-    // fragment coordinates of this lane (PTX ISA, mma.m16n8k16): rows g and g + 8, column pair 2 q
-    const int g = lane >> 2, q = lane & 3;
-    // ldmatrix.x4 row address of this lane: matrix lane / 8 = (n-tile pair member, k half), row lane % 8
-    const int lm_mat = lane >> 3, lm_row = lane & 7;
-    const uint32_t w2_lane = smem_u32(smem + kSmW2) + (uint32_t)((8 * (lm_mat >> 1) + lm_row) * kW2Stride + 16 * (lm_mat & 1));
-    const uint32_t w1_lane = smem_u32(smem + kSmW1) + (uint32_t)((8 * (lm_mat >> 1) + lm_row) * kW1Stride + 16 * (lm_mat & 1));
-
-    const int64_t n_blocks = (n + kRowsPerCta - 1) / kRowsPerCta;
-    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const int64_t row0 = blk * kRowsPerCta + warp * kRowsPerWarp;       // this warp's 16 rows
-        if (row0 >= n) continue;
-        const int64_t ra = row0 + g, rb = row0 + g + 8;
-
-        // ---- layer 1: A = [obs_hi | obs_lo] (16 x 16), B = W1 stacked twice ------------------------
-        uint32_t a1[4];
-        {
-            float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
-            if (ra < n) xa = *reinterpret_cast<const float2*>(obs + ra * kObs + 2 * q);
-            if (rb < n) xb = *reinterpret_cast<const float2*>(obs + rb * kObs + 2 * q);
-            float h0, l0, h1, l1, h2, l2, h3, l3;
-            split_bf16(xa.x, h0, l0); split_bf16(xa.y, h1, l1);
-            split_bf16(xb.x, h2, l2); split_bf16(xb.y, h3, l3);
-            a1[0] = pack_bf16(h0, h1);      // row g,     k = 2q, 2q+1        (high parts)
-            a1[1] = pack_bf16(h2, h3);      // row g + 8
-            a1[2] = pack_bf16(l0, l1);      // row g,     k = 8 + 2q, 9 + 2q  (low parts)
-            a1[3] = pack_bf16(l2, l3);      // row g + 8
-        }
-        uint32_t a2[kHidden / 16][4];       // layer-2 A fragments: 16 k-tiles of the 16 x 256 activations
-#pragma unroll
-        for (int np = 0; np < kHidden / 16; ++np) {                 // pairs of n-tiles 2 np, 2 np + 1 = k-tile np of layer 2
-            uint32_t b0, b1, b2, b3;
-            ldmatrix_x4(w1_lane + (uint32_t)(np * 16 * kW1Stride), b0, b1, b2, b3);
-            float d0[4] = {0.f, 0.f, 0.f, 0.f}, d1[4] = {0.f, 0.f, 0.f, 0.f};
-            mma_bf16(d0, a1, b0, b1);
-            mma_bf16(d1, a1, b2, b3);
-            const float2 ba = *reinterpret_cast<const float2*>(b1s + 16 * np + 2 * q);
-            const float2 bb = *reinterpret_cast<const float2*>(b1s + 16 * np + 8 + 2 * q);
-            a2[np][0] = pack_bf16(tanh_fast(d0[0] + ba.x), tanh_fast(d0[1] + ba.y));     // row g,     k = 16 np + 2q ..
-            a2[np][1] = pack_bf16(tanh_fast(d0[2] + ba.x), tanh_fast(d0[3] + ba.y));     // row g + 8
-            a2[np][2] = pack_bf16(tanh_fast(d1[0] + bb.x), tanh_fast(d1[1] + bb.y));     // row g,     k = 16 np + 8 + 2q ..
-            a2[np][3] = pack_bf16(tanh_fast(d1[2] + bb.x), tanh_fast(d1[3] + bb.y));     // row g + 8
-        }
-
-        // ---- layer 2 in two halves of 128 output units, head accumulated on the fly -------------------
-        float sa[kOut], sb[kOut];           // head partial sums of rows g and g + 8
-#pragma unroll
-        for (int o = 0; o < kOut; ++o) sa[o] = sb[o] = 0.f;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float acc[16][4];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-#pragma unroll
-            for (int kt = 0; kt < kHidden / 16; ++kt) {
-#pragma unroll
-                for (int jp = 0; jp < 8; ++jp) {                    // n-tiles 16 half + 2 jp, + 1
-                    uint32_t b0, b1, b2, b3;
-                    ldmatrix_x4(w2_lane + (uint32_t)((128 * half + 16 * jp) * kW2Stride + 32 * kt), b0, b1, b2, b3);
-                    mma_bf16(acc[2 * jp], a2[kt], b0, b1);
-                    mma_bf16(acc[2 * jp + 1], a2[kt], b2, b3);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int col = 128 * half + 8 * j + 2 * q;
-                const float2 bias = *reinterpret_cast<const float2*>(b2s + col);
-                const float va0 = tanh_fast(acc[j][0] + bias.x), va1 = tanh_fast(acc[j][1] + bias.y);
-                const float vb0 = tanh_fast(acc[j][2] + bias.x), vb1 = tanh_fast(acc[j][3] + bias.y);
-#pragma unroll
-                for (int o = 0; o < kOut; ++o) {
-                    const float2 w = *reinterpret_cast<const float2*>(w3s + o * kHidden + col);
-                    sa[o] = fmaf(va0, w.x, fmaf(va1, w.y, sa[o]));
-                    sb[o] = fmaf(vb0, w.x, fmaf(vb1, w.y, sb[o]));
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 0; o < kOut; ++o) {                            // the four lanes of a quad hold one row's partial sums
-            sa[o] += __shfl_xor_sync(0xffffffffu, sa[o], 1);
-            sa[o] += __shfl_xor_sync(0xffffffffu, sa[o], 2);
-            sb[o] += __shfl_xor_sync(0xffffffffu, sb[o], 1);
-            sb[o] += __shfl_xor_sync(0xffffffffu, sb[o], 2);
-        }
-        if (q == 0) {
-#pragma unroll
-            for (int o = 0; o < kOut; ++o) {
-                if (ra < n) out[ra * kOut + o] = sa[o] + b3s[o];
-                if (rb < n) out[rb * kOut + o] = sb[o] + b3s[o];
-            }
-        }
-    }
-}
-
-
-// =================================================================================================
-// tcgen05 / TMEM version: one CTA steps 128-rocket row blocks; both layers are single-thread-issued
-// tcgen05.mma (M = 128, N = 256, K = 16 per instruction, bf16 x bf16 -> fp32 in tensor memory).
-//
-//   shared memory (operands in the canonical K-major no-swizzle layout: 8 x 16-byte "core matrices",
-//   element (row r, k) at (k / 8) LBO + (r / 8) 128 + (r % 8) 16 + (k % 8) 2 bytes):
-//     W2s  256 x 256 bf16, LBO 4096   (loaded once per CTA)        W1s  256 x 16, LBO 4096
-//     A2s  128 x 256 bf16, LBO 2048   (layer-1 activations)        A1s  128 x 16, LBO 2048 (obs hi | lo)
-//   tensor memory (512 columns): D1 = columns 0..255 (layer 1), D2 = columns 256..511 (layer 2)
-//
-//   per row block:  obs -> A1s | MMA 1 -> D1 | all 8 warps: D1 -> +b1, tanh, bf16 -> A2s |
-//                   16 x MMA 2 -> D2 | all 8 warps: D2 -> +b2, tanh, head dot -> out
-//   Warp w reads TMEM lanes 32 (w % 4) .. + 31 (its rows) and the column half w / 4, so the 2 x 256
-//   tanh per rocket (the MUFU pipe is what bounds this kernel once the GEMM is on tcgen05) are spread
-//   over 256 threads.  Generic-proxy writes of A1s / A2s are published to the tensor core with
-//   fence.proxy.async + a CTA barrier; MMA completion comes back through tcgen05.commit -> mbarrier.
-// =================================================================================================
 namespace tc5 {
 
 constexpr int kM = 128;                       // rows per block = TMEM lanes
@@ -339,7 +194,7 @@ static_assert(kSmBar - kSmRed >= kSplit * kM * 2 * 4, "head partial sums");
 template <int kOut>
 __global__ void __launch_bounds__(kTc5Threads, 1) mlp_forward_tc5_kernel(const unsigned char* __restrict__ blob,
                                                                   const float* __restrict__ obs, float* __restrict__ out,
-                                                                  int64_t n) {
+                                                                  int64_t n, const SampleArgs sa) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem);
@@ -516,12 +371,33 @@ __global__ void __launch_bounds__(kTc5Threads, 1) mlp_forward_tc5_kernel(const u
         if (tid < kM) {
             const int64_t r = row0 + tid;
             if (r < n) {
+                float v[kOut];
 #pragma unroll
                 for (int o = 0; o < kOut; ++o) {
-                    float v = b3s[o];
+                    v[o] = b3s[o];
 #pragma unroll
-                    for (int sl = 0; sl < kSplit; ++sl) v += red[(sl * kM + tid) * 2 + o];
-                    out[r * kOut + o] = v;
+                    for (int sl = 0; sl < kSplit; ++sl) v[o] += red[(sl * kM + tid) * 2 + o];
+                }
+                if (kOut == 2 && sa.actions != nullptr) {
+                    const uint4 bits = rl::philox4x32_10(make_uint4((uint32_t)r, (uint32_t)((uint64_t)r >> 32), (uint32_t)sa.draw,
+                                                                    (uint32_t)(sa.draw >> 32)),
+                                                         make_uint2((uint32_t)sa.seed, (uint32_t)(sa.seed >> 32)));
+                    const float u1 = (float)((bits.x >> 8) + 1u) * 5.9604644775390625e-8f;      // (0, 1]
+                    const float u2 = (float)(bits.y >> 8) * 5.9604644775390625e-8f;             // [0, 1)
+                    const float rad = sqrtf(-2.0f * logf(u1));
+                    float sn, cs;
+                    sincospif(2.0f * u2, &sn, &cs);
+                    const float z0 = rad * cs, z1 = rad * sn;
+                    const float ls0 = sa.log_std[0], ls1 = sa.log_std[1];
+                    const float a0 = fmaf(expf(ls0), z0, v[0]), a1 = fmaf(expf(ls1), z1, v[kOut - 1]);
+                    *reinterpret_cast<float2*>(sa.actions + 2 * r) = make_float2(a0, a1);
+                    *reinterpret_cast<float2*>(sa.clipped + 2 * r) =
+                        make_float2(fminf(fmaxf(a0, sa.lo0), sa.hi0), fminf(fmaxf(a1, sa.lo1), sa.hi1));
+                    sa.log_prob[r] = (-0.5f * z0 * z0 - ls0 - 0.91893853320467274f) + (-0.5f * z1 * z1 - ls1 - 0.91893853320467274f);
+                    if (sa.mean) *reinterpret_cast<float2*>(sa.mean + 2 * r) = make_float2(v[0], v[kOut - 1]);
+                } else {
+#pragma unroll
+                    for (int o = 0; o < kOut; ++o) out[r * kOut + o] = v[o];
                 }
             }
         }
@@ -541,49 +417,60 @@ const char* rl_policy_last_error(void) { return g_po_err; }
 
 int64_t rl_mlp_blob_bytes(void) { return RL_MLP_BLOB_BYTES; }
 
-// out[n][out_dim] = head(tanh(W2 tanh(W1 obs + b1) + b2)) for the packed net `blob` (DEVICE memory,
-// RL_MLP_BLOB_BYTES, 16-byte aligned); obs float32 [n][8] (8-byte aligned), out float32.  Enqueue only.
-int rl_mlp_forward(const void* blob, const float* obs, float* out, int64_t n, int out_dim, void* stream) {
-    if (!blob || !obs || !out) return po_fail(RL_E_INVALID, "rl_mlp_forward: null argument");
-    if (n < 1) return po_fail(RL_E_INVALID, "rl_mlp_forward: n must be positive");
-    if (out_dim != 1 && out_dim != 2) return po_fail(RL_E_INVALID, "rl_mlp_forward: out_dim must be 1 or 2 (got %d)", out_dim);
-    if ((reinterpret_cast<uintptr_t>(blob) & 15) || (reinterpret_cast<uintptr_t>(obs) & 7))
-        return po_fail(RL_E_INVALID, "rl_mlp_forward: blob needs 16-byte, obs 8-byte alignment");
+namespace {
+int launch_mlp(const void* blob, const float* obs, float* out, int64_t n, int out_dim, const SampleArgs& sa, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t blocks = (n + tc5::kM - 1) / tc5::kM;
+    const int grid = (int)(blocks < sms ? blocks : sms);          // persistent: the weights are staged once per CTA
     cudaError_t e;
-    static const bool use_tc5 = [] { const char* t = getenv("RL_B200_MLP_TCGEN05"); return t && t[0] == '1'; }();
-    if (use_tc5) {
-        const int64_t blocks5 = (n + tc5::kM - 1) / tc5::kM;
-        const int grid5 = (int)(blocks5 < sms ? blocks5 : sms);
-        if (out_dim == 2) {
-            e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
-            if (e == cudaSuccess)
-                tc5::mlp_forward_tc5_kernel<2><<<grid5, tc5::kTc5Threads, tc5::kSmemBytes, (cudaStream_t)stream>>>((const unsigned char*)blob, obs, out, n);
-        } else {
-            e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
-            if (e == cudaSuccess)
-                tc5::mlp_forward_tc5_kernel<1><<<grid5, tc5::kTc5Threads, tc5::kSmemBytes, (cudaStream_t)stream>>>((const unsigned char*)blob, obs, out, n);
-        }
-        if (e == cudaSuccess) e = cudaGetLastError();
-        if (e != cudaSuccess) return po_fail(RL_E_CUDA, "rl_mlp_forward (tcgen05) launch failed: %s", cudaGetErrorString(e));
-        return RL_OK;
-    }
-    const int64_t blocks = (n + kRowsPerCta - 1) / kRowsPerCta;
-    const int grid = (int)(blocks < sms ? blocks : sms);
     if (out_dim == 2) {
-        e = cudaFuncSetAttribute(mlp_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
         if (e == cudaSuccess)
-            mlp_forward_kernel<2><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>((const unsigned char*)blob, obs, out, n);
+            tc5::mlp_forward_tc5_kernel<2><<<grid, tc5::kTc5Threads, tc5::kSmemBytes, stream>>>((const unsigned char*)blob, obs, out, n, sa);
     } else {
-        e = cudaFuncSetAttribute(mlp_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
         if (e == cudaSuccess)
-            mlp_forward_kernel<1><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>((const unsigned char*)blob, obs, out, n);
+            tc5::mlp_forward_tc5_kernel<1><<<grid, tc5::kTc5Threads, tc5::kSmemBytes, stream>>>((const unsigned char*)blob, obs, out, n, sa);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return po_fail(RL_E_CUDA, "rl_mlp_forward launch failed: %s", cudaGetErrorString(e));
     return RL_OK;
+}
+}  // namespace
+
+// out[n][out_dim] = head(tanh(W2 tanh(W1 obs + b1) + b2)) for the packed net `blob` (DEVICE memory,
+// RL_MLP_BLOB_BYTES, 16-byte aligned); obs float32 [n][8] (16-byte aligned), out float32.  Enqueue only.
+int rl_mlp_forward(const void* blob, const float* obs, float* out, int64_t n, int out_dim, void* stream) {
+    if (!blob || !obs || !out) return po_fail(RL_E_INVALID, "rl_mlp_forward: null argument");
+    if (n < 1) return po_fail(RL_E_INVALID, "rl_mlp_forward: n must be positive");
+    if (out_dim != 1 && out_dim != 2) return po_fail(RL_E_INVALID, "rl_mlp_forward: out_dim must be 1 or 2 (got %d)", out_dim);
+    if ((reinterpret_cast<uintptr_t>(blob) & 15) || (reinterpret_cast<uintptr_t>(obs) & 15))
+        return po_fail(RL_E_INVALID, "rl_mlp_forward: blob and obs need 16-byte alignment");
+    SampleArgs sa = {};
+    return launch_mlp(blob, obs, out, n, out_dim, sa, (cudaStream_t)stream);
+}
+
+// The policy net with SB3's action sampling fused into its epilogue: actions[n][2] = mean +
+// exp(log_std) eps (unclipped, what the rollout buffer stores), clipped[n][2] = the same clipped to
+// [low, high] (what env.step receives), log_prob[n]; mean[n][2] optional.  eps is Philox4x32-10 keyed
+// by `seed` at counter (row, draw): pass a different `draw` every call.  DEVICE pointers, enqueue only.
+int rl_policy_sample(const void* blob, const float* obs, const float* log_std, uint64_t seed, uint64_t draw,
+                     const float* low2, const float* high2, float* actions, float* clipped, float* log_prob,
+                     float* mean, int64_t n, void* stream) {
+    if (!blob || !obs || !log_std || !low2 || !high2 || !actions || !clipped || !log_prob)
+        return po_fail(RL_E_INVALID, "rl_policy_sample: null argument");
+    if (n < 1) return po_fail(RL_E_INVALID, "rl_policy_sample: n must be positive");
+    if ((reinterpret_cast<uintptr_t>(blob) & 15) || (reinterpret_cast<uintptr_t>(obs) & 15) ||
+        (reinterpret_cast<uintptr_t>(actions) & 7) || (reinterpret_cast<uintptr_t>(clipped) & 7) ||
+        (mean && (reinterpret_cast<uintptr_t>(mean) & 7)))
+        return po_fail(RL_E_INVALID, "rl_policy_sample: blob / obs need 16-byte, actions / clipped / mean 8-byte alignment");
+    SampleArgs sa = {};
+    sa.log_std = log_std; sa.actions = actions; sa.clipped = clipped; sa.log_prob = log_prob; sa.mean = mean;
+    sa.seed = seed; sa.draw = draw;
+    sa.lo0 = low2[0]; sa.lo1 = low2[1]; sa.hi0 = high2[0]; sa.hi1 = high2[1];      // HOST pointers: two floats each
+    return launch_mlp(blob, obs, actions, n, 2, sa, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -11,9 +11,10 @@ GPU: nothing crosses PCIe during collection.
   state-independent log-std, a linear value head -- 136 965 parameters, as
   ``assets/model/v3/best_model.zip``.  It is plain PyTorch (cuBLAS
   GEMMs): the MLP is a neighbour of the hot path, not the path.
-* ``FusedActorCritic`` evaluates the same two nets with the hand-written tensor-core kernel
-  ``rl_mlp_forward`` (``csrc/rl_policy.cu``): one launch per net, the 256-wide activations never
-  leave the registers, bf16 weights with fp32 accumulation.  Same ``forward`` / ``predict_values``
+* ``FusedActorCritic`` evaluates the same two nets with the hand-written tcgen05 / TMEM kernel of
+  ``csrc/rl_policy.cu``: one launch per net, the 256-wide activations never leave the SM, bf16
+  weights with fp32 accumulation, and SB3's action sampling (Gaussian noise from Philox, log-prob,
+  Box clipping) fused into the policy net's epilogue.  Same ``forward`` / ``predict_values``
   surface, so ``collect_rollout`` takes either.
 * ``collect_rollout`` mirrors ``OnPolicyAlgorithm.collect_rollouts``: sample, clip the action to
   the Box (SB3 clips before ``env.step``), step, bootstrap time-limit truncations with the value
@@ -99,10 +100,15 @@ class FusedActorCritic:
     collection does not need gradients).  Call ``refresh()`` after the wrapped module's parameters
     change (an optimiser step) to re-pack the weights."""
 
-    def __init__(self, net: ActorCriticMLP, device="cuda"):
+    def __init__(self, net: ActorCriticMLP, device="cuda", seed: int = 0, low=(0.0, -1.0), high=(1.0, 1.0)):
+        import ctypes as C
         self._L = _lib.load()
         self.net = net
         self.device = torch.device(device)
+        self.seed = int(seed) & (2**64 - 1)
+        self.draw = 0                                   # Philox counter word: one per forward() call
+        self._low = (C.c_float * 2)(*low)               # the env's Box (lander.py:65-69)
+        self._high = (C.c_float * 2)(*high)
         assert int(self._L.rl_mlp_blob_bytes()) == MLP_BLOB_BYTES
         self.refresh()
 
@@ -111,11 +117,13 @@ class FusedActorCritic:
         self._vf = pack_mlp(self.net.value_net_body, self.net.value_net, self.device)
         self._log_std = self.net.log_std.detach().to(self.device, torch.float32).clone()
 
-    def _run(self, blob: torch.Tensor, obs: torch.Tensor, out_dim: int) -> torch.Tensor:
+    def _run(self, blob: torch.Tensor, obs: torch.Tensor, out_dim: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if obs.dtype != torch.float32 or not obs.is_contiguous():
             obs = obs.to(torch.float32).contiguous()
         n = obs.shape[0]
-        out = torch.empty((n, out_dim), dtype=torch.float32, device=obs.device)
+        if out is None:
+            out = torch.empty((n, out_dim), dtype=torch.float32, device=obs.device)
+        assert out.is_contiguous() and out.numel() == n * out_dim and out.dtype == torch.float32
         if n == 0:
             return out
         rc = self._L.rl_mlp_forward(blob.data_ptr(), obs.data_ptr(), out.data_ptr(), n, out_dim,
@@ -127,16 +135,39 @@ class FusedActorCritic:
     def action_mean(self, obs: torch.Tensor) -> torch.Tensor:
         return self._run(self._pi, obs, 2)
 
-    def predict_values(self, obs: torch.Tensor) -> torch.Tensor:
-        return self._run(self._vf, obs, 1).squeeze(-1)
+    def predict_values(self, obs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Values ``[n]``; ``out`` (a contiguous float32 ``[n]`` tensor, e.g. a slice of the rollout
+        buffer) is written in place when given."""
+        return self._run(self._vf, obs, 1, out).reshape(-1)
+
+    def act(self, obs: torch.Tensor, actions: Optional[torch.Tensor] = None,
+            log_prob: Optional[torch.Tensor] = None, want_mean: bool = False):
+        """Sample with the fused epilogue (``rl_policy_sample``).  Returns ``(actions, clipped,
+        log_prob, mean or None)``; ``actions`` / ``log_prob`` may be given (slices of the rollout
+        buffer) and are then written in place."""
+        if obs.dtype != torch.float32 or not obs.is_contiguous():
+            obs = obs.to(torch.float32).contiguous()
+        n = obs.shape[0]
+        f32 = dict(dtype=torch.float32, device=obs.device)
+        actions = torch.empty((n, 2), **f32) if actions is None else actions
+        log_prob = torch.empty((n,), **f32) if log_prob is None else log_prob
+        clipped = torch.empty((n, 2), **f32)
+        mean = torch.empty((n, 2), **f32) if want_mean else None
+        assert actions.is_contiguous() and log_prob.is_contiguous()
+        rc = self._L.rl_policy_sample(self._pi.data_ptr(), obs.data_ptr(), self._log_std.data_ptr(), self.seed, self.draw,
+                                      self._low, self._high, actions.data_ptr(), clipped.data_ptr(), log_prob.data_ptr(),
+                                      mean.data_ptr() if mean is not None else None, n,
+                                      torch.cuda.current_stream(obs.device).cuda_stream)
+        if rc != 0:
+            raise _lib.RocketLibraryError(f"rl_policy_sample failed ({rc}): {self._L.rl_policy_last_error().decode()}")
+        self.draw += 1
+        return actions, clipped, log_prob, mean
 
     def forward(self, obs: torch.Tensor, generator: Optional[torch.Generator] = None):
-        mean = self.action_mean(obs)
-        values = self.predict_values(obs)
-        noise = torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
-        actions = torch.addcmul(mean, self._log_std.exp(), noise)
-        log_prob = (-0.5 * noise.pow(2) - self._log_std - 0.5 * math.log(2.0 * math.pi)).sum(-1)
-        return actions, values, log_prob
+        """``(actions, values, log_prob)`` as ``ActorCriticMLP.forward``.  ``generator`` is ignored:
+        the noise comes from the kernel's own Philox stream (``seed``, ``draw``)."""
+        actions, _, log_prob, _ = self.act(obs)
+        return actions, self.predict_values(obs), log_prob
 
     __call__ = forward
 
@@ -180,14 +211,19 @@ def collect_rollout(env, policy, buffer: DeviceRolloutBuffer, last_obs: torch.Te
     high = torch.tensor([1.0, 1.0], device=last_obs.device)
     obs = last_obs
     starts = last_episode_starts
+    fused = hasattr(policy, "act")
     for t in range(buffer.n_steps):
-        actions, values, log_probs = policy(obs, generator)
+        if fused:     # sample, clip and log-prob in the policy kernel's epilogue, straight into the buffer
+            _, clipped, _, _ = policy.act(obs, buffer.actions[t], buffer.log_probs[t])
+            policy.predict_values(obs, out=buffer.values[t])
+        else:
+            actions, values, log_probs = policy(obs, generator)
+            buffer.actions[t].copy_(actions)
+            buffer.values[t].copy_(values)
+            buffer.log_probs[t].copy_(log_probs)
+            clipped = torch.clamp(actions, low, high).contiguous()   # SB3 clips Box actions before env.step
         buffer.observations[t].copy_(obs)
-        buffer.actions[t].copy_(actions)
-        buffer.values[t].copy_(values)
-        buffer.log_probs[t].copy_(log_probs)
         buffer.episode_starts[t].copy_(starts)
-        clipped = torch.clamp(actions, low, high).contiguous()       # SB3 clips Box actions before env.step
         obs, rewards, terminated, truncated, info = env.step(clipped)
         buffer.rewards[t].copy_(rewards)
         if bootstrap_timeouts:

@@ -113,3 +113,43 @@ def test_fused_mlp_kernel_matches_the_pytorch_module():
     assert torch.equal(fused.action_mean(obs)[perm], fused.action_mean(obs[perm].contiguous()))
     a, v, lp = fused(obs)
     assert a.shape == (1000, 2) and v.shape == (1000,) and lp.shape == (1000,)
+
+
+@pytest.mark.gpu
+def test_fused_action_sampling():
+    """rl_policy_sample: the policy net with SB3's DiagGaussian sampling in its epilogue.  The noise
+    is Philox + Box-Muller inside the kernel, so the check is distributional (standardised samples
+    have zero mean, unit variance, no correlation between the two components, Gaussian tails) plus the
+    exact relations between the outputs: log-prob formula, Box clipping, reproducibility."""
+    import math
+    import torch
+    from rocket_landing_rl_b200 import ActorCriticMLP, FusedActorCritic
+    torch.manual_seed(1)
+    net = ActorCriticMLP(log_std_init=-0.7).cuda()
+    with torch.no_grad():
+        net.log_std.copy_(torch.tensor([-0.7, 0.3]))
+    fused = FusedActorCritic(net, seed=123)
+    n = 1 << 20
+    obs = torch.randn((n, 8), device="cuda").clamp_(-10, 10)
+    actions, clipped, logp, mean = fused.act(obs, want_mean=True)
+    assert torch.allclose(mean, fused.action_mean(obs), atol=0, rtol=0)          # same kernel, same numbers
+    std = net.log_std.detach().exp()
+    z = (actions - mean) / std
+    assert abs(float(z.mean())) < 4e-3 and abs(float(z.var()) - 1.0) < 6e-3
+    assert abs(float((z[:, 0] * z[:, 1]).mean())) < 4e-3
+    assert 0.0024 < float((z.abs() > 3.0).float().mean()) < 0.0030             # P(|N| > 3) = 0.0027
+    want_logp = (-0.5 * z.pow(2) - net.log_std.detach() - 0.5 * math.log(2 * math.pi)).sum(-1)
+    assert float((logp - want_logp).abs().max()) < 2e-3
+    low, high = torch.tensor([0.0, -1.0], device="cuda"), torch.tensor([1.0, 1.0], device="cuda")
+    assert torch.equal(clipped, torch.clamp(actions, low, high))
+    # a new draw gives new noise; the same (seed, draw) gives the same bits
+    a2, _, _, _ = fused.act(obs)
+    assert not torch.equal(a2, actions)
+    again = FusedActorCritic(net, seed=123)
+    a3, _, _, _ = again.act(obs)
+    assert torch.equal(a3, actions)
+    # in-place into (slices of) a rollout buffer
+    buf_a = torch.zeros((2, n, 2), device="cuda")
+    buf_l = torch.zeros((2, n), device="cuda")
+    again.act(obs, buf_a[1], buf_l[1])
+    assert torch.equal(buf_a[1], a2) and float(buf_a[0].abs().max()) == 0.0
