@@ -1,5 +1,11 @@
-import sys, torch
-sys.path.insert(0, '/root/repo')
+"""Output error of the fused MLP kernel against the fp32 PyTorch module, next to what tf32 and
+bf16-autocast PyTorch lose on the same inputs (profiles/README.md).  GPU box only."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rocket_landing_rl_b200 import ActorCriticMLP, FusedActorCritic
 torch.manual_seed(3)
 net = ActorCriticMLP().cuda()

@@ -1,5 +1,13 @@
-import sys, torch
-sys.path.insert(0, '/root/repo')
+"""Step-kernel time with and without finished episodes: with auto-reset off and every rocket
+landed, no episode ever ends again and only the always-executed path runs -- the upper bound of what
+moving the reset path out of the step kernel could give (profiles/README.md, "what is left").
+GPU box only."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from rocket_landing_rl_b200 import RocketLandingVecEnv
 for n in (16777216, 67108864):
     for auto in (True, False):
