@@ -59,13 +59,20 @@ class DeviceVecNormalize:
                                              int(self.norm_obs), self._stream()), "rl_vecnorm_reset")
         return self.obs
 
-    def step(self, action: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, Dict[str, Any]]:
+    def step(self, action: torch.Tensor, out_obs: torch.Tensor = None, out_reward: torch.Tensor = None
+             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, Dict[str, Any]]:
+        """``VecNormalize.step``.  ``out_obs`` / ``out_reward`` (contiguous float32 ``[N, 8]`` / ``[N]``,
+        e.g. slices of a rollout buffer) receive the normalised observation / reward instead of this
+        wrapper's own buffers."""
         raw_obs, raw_rew, term, trunc, info = self.venv.step(action)
+        obs = self.obs if out_obs is None else out_obs
+        rew = self.reward if out_reward is None else out_reward
+        assert obs.is_contiguous() and rew.is_contiguous() and obs.dtype == rew.dtype == torch.float32
         self._check(self._L.rl_vecnorm_step(
             self._h, raw_obs.data_ptr(), raw_rew.data_ptr(), term.data_ptr(), trunc.data_ptr(),
-            info["terminal_observation"].data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
+            info["terminal_observation"].data_ptr(), obs.data_ptr(), rew.data_ptr(),
             int(self.training), int(self.norm_obs), int(self.norm_reward), self._stream()), "rl_vecnorm_step")
-        return self.obs, self.reward, term, trunc, info
+        return obs, rew, term, trunc, info
 
     def normalize_obs(self, obs: torch.Tensor) -> torch.Tensor:
         """``VecNormalize.normalize_obs`` for an arbitrary ``[rows, 8]`` batch (inference path)."""

@@ -209,10 +209,15 @@ def collect_rollout(env, policy, buffer: DeviceRolloutBuffer, last_obs: torch.Te
     ``(last_obs, last_episode_starts)`` for the next pass."""
     low = torch.tensor([0.0, -1.0], device=last_obs.device)
     high = torch.tensor([1.0, 1.0], device=last_obs.device)
-    obs = last_obs
-    starts = last_episode_starts
+    T = buffer.n_steps
     fused = hasattr(policy, "act")
-    for t in range(buffer.n_steps):
+    direct = hasattr(env, "venv")          # DeviceVecNormalize can write its outputs straight into the buffer
+    buffer.observations[0].copy_(last_obs)
+    buffer.episode_starts[0].copy_(last_episode_starts)
+    obs = buffer.observations[0]
+    starts = last_episode_starts
+    pending = None                         # (step, time-limit mask) whose bootstrap is still to be decided
+    for t in range(T):
         if fused:     # sample, clip and log-prob in the policy kernel's epilogue, straight into the buffer
             _, clipped, _, _ = policy.act(obs, buffer.actions[t], buffer.log_probs[t])
             policy.predict_values(obs, out=buffer.values[t])
@@ -222,16 +227,59 @@ def collect_rollout(env, policy, buffer: DeviceRolloutBuffer, last_obs: torch.Te
             buffer.values[t].copy_(values)
             buffer.log_probs[t].copy_(log_probs)
             clipped = torch.clamp(actions, low, high).contiguous()   # SB3 clips Box actions before env.step
-        buffer.observations[t].copy_(obs)
-        buffer.episode_starts[t].copy_(starts)
-        obs, rewards, terminated, truncated, info = env.step(clipped)
-        buffer.rewards[t].copy_(rewards)
+        nxt = buffer.observations[t + 1] if t + 1 < T else None      # the next step's observation slot
+        if direct:
+            obs, rewards, terminated, truncated, info = env.step(clipped, out_obs=nxt, out_reward=buffer.rewards[t])
+        else:
+            obs, rewards, terminated, truncated, info = env.step(clipped)
+            buffer.rewards[t].copy_(rewards)
+            if nxt is not None:
+                nxt.copy_(obs)
+                obs = nxt
         if bootstrap_timeouts:
-            timeout = truncated & ~terminated                         # infos[i]["TimeLimit.truncated"]
-            if bool(timeout.any()):
-                tv = policy.predict_values(info["terminal_observation"][timeout])
-                buffer.rewards[t][timeout] += gamma * tv
-        starts = terminated | truncated
+            # SB3 adds gamma V(terminal observation) to the reward of a step that ended by the time limit
+            # (infos[i]["TimeLimit.truncated"]).  Asking the device "did any rocket time out?" every
+            # step would stall the host behind the GPU, so the question is asked asynchronously and
+            # answered one step late: a rocket that timed out at step t was reset at step t and cannot
+            # finish another episode at step t + 1, so its row of the terminal-observation buffer is
+            # still intact then.
+            timeout = torch.logical_and(truncated, torch.logical_not(terminated))
+            flag = _pinned_flags(T, last_obs.device)
+            flag["host"][t].copy_(timeout.any(), non_blocking=True)
+            flag["events"][t].record()
+            if pending is not None:
+                _bootstrap(policy, buffer, info, pending, flag, gamma, terminated | truncated)
+            pending = (t, timeout)
+        if t + 1 < T:
+            starts = torch.logical_or(terminated, truncated, out=buffer.episode_starts[t + 1])
+        else:
+            starts = terminated | truncated
+    if pending is not None:
+        _bootstrap(policy, buffer, info, pending, _pinned_flags(T, last_obs.device), gamma, None)
     last_values = policy.predict_values(obs)
     buffer.compute_returns_and_advantage(last_values, starts, gamma, gae_lambda)
     return obs, starts
+
+
+_FLAGS: dict = {}
+
+
+def _pinned_flags(n_steps: int, device) -> dict:
+    """Per-device pinned host flags + events for the asynchronous "any time-limit truncation?" test."""
+    key = (str(device), n_steps)
+    if key not in _FLAGS:
+        _FLAGS[key] = {"host": torch.zeros(n_steps, dtype=torch.bool).pin_memory(),
+                       "events": [torch.cuda.Event() for _ in range(n_steps)]}
+    return _FLAGS[key]
+
+
+def _bootstrap(policy, buffer: DeviceRolloutBuffer, info, pending, flag, gamma: float, done_now) -> None:
+    """Resolve the time-limit bootstrap of an earlier step (see ``collect_rollout``)."""
+    t, mask = pending
+    flag["events"][t].synchronize()        # recorded a whole env step ago: already complete in steady state
+    if not bool(flag["host"][t]):
+        return
+    if done_now is not None:               # rows overwritten since (cannot happen with episodes longer than one step)
+        mask = torch.logical_and(mask, torch.logical_not(done_now))
+    tv = policy.predict_values(info["terminal_observation"][mask].contiguous())
+    buffer.rewards[t][mask] += gamma * tv

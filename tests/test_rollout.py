@@ -153,3 +153,51 @@ def test_fused_action_sampling():
     buf_l = torch.zeros((2, n), device="cuda")
     again.act(obs, buf_a[1], buf_l[1])
     assert torch.equal(buf_a[1], a2) and float(buf_a[0].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_time_limit_bootstrap_is_resolved_one_step_late_but_exactly():
+    """collect_rollout adds gamma V(terminal observation) to the reward of steps that end by the time
+    limit (SB3's TimeLimit.truncated handling) without a host synchronisation per step: the "any
+    timeout?" flag is read back one step late.  With max_episode_steps = 5 every rocket times out at
+    steps 4, 9, ...: the rewards with and without bootstrapping must differ there, and only there,
+    by gamma V(observation an env WITHOUT auto-reset shows after the same five actions)."""
+    import torch
+    from rocket_landing_rl_b200 import (ActorCriticMLP, DeviceRolloutBuffer, FusedActorCritic,
+                                        RocketLandingVecEnv, collect_rollout, load_params)
+    p = load_params()
+    p.max_episode_steps = 5
+    n, T, gamma = 3000, 12, 0.9
+    torch.manual_seed(0)
+    net = ActorCriticMLP().cuda()
+
+    def run(bootstrap):
+        env = RocketLandingVecEnv(n, seed=4, params=p)
+        pol = FusedActorCritic(net, seed=9)
+        buf = DeviceRolloutBuffer(T, n, "cuda")
+        obs, _ = env.reset()
+        collect_rollout(env, pol, buf, obs, torch.ones(n, dtype=torch.bool, device="cuda"), gamma=gamma,
+                        bootstrap_timeouts=bootstrap)
+        env.close()
+        return buf
+
+    a, b = run(True), run(False)
+    assert torch.equal(a.actions, b.actions) and torch.equal(a.observations, b.observations)
+    diff = a.rewards - b.rewards
+    for t in range(T):
+        if t % 5 == 4:
+            assert bool(a.episode_starts[t + 1].all()) if t + 1 < T else True
+            assert float(diff[t].abs().min()) > 0.0
+        else:
+            assert float(diff[t].abs().max()) == 0.0
+    # the first time limit: terminal observation = what an env without auto-reset returns at step 4
+    env = RocketLandingVecEnv(n, seed=4, params=p, auto_reset=False)
+    env.reset()
+    low, high = torch.tensor([0.0, -1.0], device="cuda"), torch.tensor([1.0, 1.0], device="cuda")
+    for t in range(5):
+        obs, _, term, trunc, _ = env.step(torch.clamp(a.actions[t], low, high).contiguous())
+    assert bool(trunc.all()) and not bool(term.any())
+    want = gamma * FusedActorCritic(net).predict_values(obs)
+    # (diff is a difference of fp32 rewards of magnitude up to ~1e2: 1e-6 relative of those, not of itself)
+    assert torch.allclose(diff[4], want, rtol=1e-4, atol=3e-4)
+    env.close()
