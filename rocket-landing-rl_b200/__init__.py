@@ -12,6 +12,7 @@ from .layout import (STATE_WORDS, fresh_state_soa, state_soa_from_reference,   #
                      reference_view)
 from .stats import EpisodeStats, shard_range, allreduce_stats          # noqa: F401
 from .env import RocketLandingVecEnv                                   # noqa: F401
+from .single_env import RocketLandingEnv                               # noqa: F401
 from .vec_env import RocketLandingSB3VecEnv                            # noqa: F401
 from .normalize import DeviceVecNormalize                              # noqa: F401
 from .simulation import RocketSimulation                               # noqa: F401
@@ -19,5 +20,5 @@ from .rollout import ActorCriticMLP, DeviceRolloutBuffer, FusedActorCritic, coll
 
 __all__ = ["Config", "load_params", "default_config_path", "Box", "STATE_WORDS",
            "fresh_state_soa", "state_soa_from_reference", "reference_view", "EpisodeStats",
-           "shard_range", "allreduce_stats", "RocketLandingVecEnv", "RocketLandingSB3VecEnv", "DeviceVecNormalize",
+           "shard_range", "allreduce_stats", "RocketLandingEnv", "RocketLandingVecEnv", "RocketLandingSB3VecEnv", "DeviceVecNormalize",
            "ActorCriticMLP", "DeviceRolloutBuffer", "FusedActorCritic", "pack_mlp", "collect_rollout", "RocketSimulation"]
