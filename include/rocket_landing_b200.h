@@ -203,6 +203,8 @@ int rl_step_host(RlEnv *env, const float *actions, float *obs, float *reward,
                  float *episode_return, int32_t *episode_length, int8_t *landing, int substeps,
                  int auto_reset);
 int rl_reset_host(RlEnv *env, float *obs);
+/* rl_get_state into HOST memory (float32 [10][N]); synchronous. */
+int rl_get_state_host(RlEnv *env, float *state_soa);
 
 /* Simulation mode -- the reference's second caller of the step, the UI loop: one tick of
  * SimulationController.step (backend/simulation/controller.py:223-269) over RocketControls.step

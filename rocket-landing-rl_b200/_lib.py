@@ -18,7 +18,7 @@ ABI_VERSION = 1
 # every symbol include/rocket_landing_b200.h declares
 EXPORTS = ("rl_abi_version", "rl_last_error", "rl_params_default", "rl_state_bytes", "rl_create",
            "rl_destroy", "rl_num_envs", "rl_uses_folded_constants", "rl_get_epoch", "rl_set_epoch", "rl_reset", "rl_step",
-           "rl_set_state", "rl_get_state", "rl_stats", "rl_step_host", "rl_reset_host",
+           "rl_set_state", "rl_get_state", "rl_stats", "rl_step_host", "rl_reset_host", "rl_get_state_host",
            "rl_launch_count", "rl_vecnorm_last_error", "rl_vecnorm_create", "rl_vecnorm_destroy",
            "rl_vecnorm_reset", "rl_vecnorm_step", "rl_vecnorm_normalize_obs", "rl_vecnorm_get_stats",
            "rl_vecnorm_set_stats", "rl_vecnorm_launch_count", "rl_rollout_last_error", "rl_gae", "rl_sim_step",
@@ -68,6 +68,7 @@ def load():
     L.rl_stats.argtypes = [vp, vp, i32, vp]
     L.rl_step_host.argtypes = [vp] + [vp] * 9 + [i32, i32]
     L.rl_reset_host.argtypes = [vp, vp]
+    L.rl_get_state_host.argtypes = [vp, vp]
     L.rl_launch_count.argtypes = [vp]
     L.rl_launch_count.restype = i64
     f64 = C.c_double

@@ -578,12 +578,50 @@ int rl_sim_step_host(RlEnv* e, const float* actions, uint8_t* message) {
 int rl_reset_host(RlEnv* e, float* obs) {
     if (!e) return fail(RL_E_INVALID, "rl_reset_host: null handle");
     DeviceGuard guard(e->device);
+    if (e->n <= e->small_host) {                       // small batch: the kernel writes the pinned host buffer itself
+        Stage h, d;
+        int rc = ensure_pinned(e, h, d);
+        if (rc != RL_OK) return rc;
+        rc = rl_reset(e, nullptr, obs ? d.obs : nullptr, e->h_streams[0]);
+        if (rc != RL_OK) return rc;
+        RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
+        if (obs) memcpy(obs, h.obs, 32 * (size_t)e->n);
+        return RL_OK;
+    }
     Stage s;
     int rc = ensure_stage(e, s);
     if (rc != RL_OK) return rc;
     rc = rl_reset(e, nullptr, obs ? s.obs : nullptr, e->h_streams[0]);
     if (rc != RL_OK) return rc;
     if (obs) RL_CUDA(cudaMemcpyAsync(obs, s.obs, 32 * (size_t)e->n, cudaMemcpyDeviceToHost, e->h_streams[0]));
+    RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
+    return RL_OK;
+}
+
+// rl_get_state into HOST memory (float32 [10][N], RL_W_*); synchronous.  Small batches go through
+// pinned, device-mapped memory (one launch + one synchronisation).
+int rl_get_state_host(RlEnv* e, float* state_soa) {
+    if (!e || !state_soa) return fail(RL_E_INVALID, "rl_get_state_host: null argument");
+    DeviceGuard guard(e->device);
+    const size_t bytes = 40 * (size_t)e->n;
+    if (e->n <= e->small_host) {
+        Stage h, d;
+        int rc = ensure_pinned(e, h, d);
+        if (rc != RL_OK) return rc;
+        // 40 n bytes fit in the staging span that starts at the observation area (obs 32 n + reward 4 n +
+        // flags 2 n + terminal observations 32 n, contiguous); host-path calls on a handle never overlap
+        rc = rl_get_state(e, d.obs, e->h_streams[0]);
+        if (rc != RL_OK) return rc;
+        RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
+        memcpy(state_soa, h.obs, bytes);
+        return RL_OK;
+    }
+    Stage s;
+    int rc = ensure_stage(e, s);
+    if (rc != RL_OK) return rc;
+    rc = rl_get_state(e, s.obs, e->h_streams[0]);
+    if (rc != RL_OK) return rc;
+    RL_CUDA(cudaMemcpyAsync(state_soa, s.obs, bytes, cudaMemcpyDeviceToHost, e->h_streams[0]));
     RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
     return RL_OK;
 }

@@ -44,12 +44,12 @@ class RocketLandingEnv:
         _lib.check(self._L.rl_create(C.byref(self.params), 1, 0, int(seed) & (2**64 - 1), int(device), None,
                                      C.byref(handle)), "rl_create")
         self._h = handle
-        self._dev = int(device)
         self._act = np.zeros((1, 2), np.float32)
         self._obs = np.zeros((1, 8), np.float32)
         self._rew = np.zeros((1,), np.float32)
         self._term = np.zeros((1,), np.uint8)
         self._trunc = np.zeros((1,), np.uint8)
+        self._soa = np.zeros((10, 1), np.float32)
         self._accel = (0.0, 0.0)            # ax, ay of the last step (or the sampled ones after a reset)
 
     # ---- the reference's surface ------------------------------------------------------------
@@ -74,11 +74,8 @@ class RocketLandingEnv:
         return obs, float(self._rew[0]), bool(self._term[0]), bool(self._trunc[0]), self._get_info()
 
     def _get_info(self) -> Dict[str, Any]:
-        import torch
-        soa = torch.empty((10, 1), dtype=torch.float32, device=f"cuda:{self._dev}")
-        _lib.check(self._L.rl_get_state(self._h, soa.data_ptr(), torch.cuda.current_stream(soa.device).cuda_stream),
-                   "rl_get_state")
-        v = reference_view(soa.cpu().numpy(), self.dt)
+        _lib.check(self._L.rl_get_state_host(self._h, self._soa.ctypes.data), "rl_get_state_host")
+        v = reference_view(self._soa, self.dt)
         vx, vy = float(v["vx"][0]), float(v["vy"][0])
         state = {"x": float(v["x"][0]), "y": float(v["y"][0]), "vx": vx, "vy": vy,
                  "ax": self._accel[0], "ay": self._accel[1], "angle": float(v["angle"][0]),
