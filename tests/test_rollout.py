@@ -201,3 +201,43 @@ def test_time_limit_bootstrap_is_resolved_one_step_late_but_exactly():
     # (diff is a difference of fp32 rewards of magnitude up to ~1e2: 1e-6 relative of those, not of itself)
     assert torch.allclose(diff[4], want, rtol=1e-4, atol=3e-4)
     env.close()
+
+
+def test_pack_mlp_layout_matches_the_header():
+    """Host logic of the fused MLP path (no GPU): the packed blob has the layout
+    include/rocket_landing_b200.h documents for rl_mlp_forward, byte for byte."""
+    import re
+    import torch
+    from rocket_landing_rl_b200 import ActorCriticMLP, pack_mlp
+    from rocket_landing_rl_b200.rollout import MLP_BLOB_BYTES
+    import os
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include",
+                            "rocket_landing_b200.h")).read()
+    assert int(re.search(r"#define RL_MLP_BLOB_BYTES (\d+)", hdr).group(1)) == MLP_BLOB_BYTES
+    torch.manual_seed(0)
+    net = ActorCriticMLP()
+    for body, head in ((net.policy_net, net.action_net), (net.value_net_body, net.value_net)):
+        blob = pack_mlp(body, head, "cpu")
+        assert blob.dtype == torch.uint8 and blob.numel() == MLP_BLOB_BYTES
+        off = 0
+
+        def take(nbytes, dtype):
+            nonlocal off
+            t = blob[off:off + nbytes].view(dtype)
+            off += nbytes
+            return t
+
+        w1 = take(256 * 16 * 2, torch.bfloat16).view(256, 16)
+        assert torch.equal(w1[:, :8], body[0].weight.detach().to(torch.bfloat16)) and torch.equal(w1[:, 8:], w1[:, :8])
+        assert torch.equal(take(256 * 4, torch.float32), body[0].bias.detach())
+        assert torch.equal(take(256 * 256 * 2, torch.bfloat16).view(256, 256), body[2].weight.detach().to(torch.bfloat16))
+        assert torch.equal(take(256 * 4, torch.float32), body[2].bias.detach())
+        w3 = take(2 * 256 * 4, torch.float32).view(2, 256)
+        k = head.weight.shape[0]
+        assert torch.equal(w3[:k], head.weight.detach()) and float(w3[k:].abs().sum()) == 0.0
+        b3 = take(16, torch.float32)
+        assert torch.equal(b3[:k], head.bias.detach()) and float(b3[k:].abs().sum()) == 0.0
+        assert off == MLP_BLOB_BYTES
+    with pytest.raises(ValueError):
+        pack_mlp(torch.nn.Sequential(torch.nn.Linear(8, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh()),
+                 torch.nn.Linear(64, 2), "cpu")
