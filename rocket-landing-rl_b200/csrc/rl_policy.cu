@@ -32,7 +32,11 @@
 // Weights are bf16 (what torch.autocast(bfloat16) would use), accumulation and biases fp32; measured
 // against the fp32 module: rms error 8e-4, max 4e-3 on outputs of mean magnitude 0.24 (autocast:
 // 1.2e-3 / 7e-3; tools/mlp_error_probe.py), and the test states the tolerance.
-// Measured (profiles/README.md): 0.22 ms per net at 1 Mi rockets.  The first version of this kernel
+// Measured (profiles/README.md): 0.22 ms per net at 1 Mi rockets: the MUFU (tanh) pipe is 57 % busy,
+// the tensor pipe 30 %; the two epilogues and the MMAs of ONE row block still run mostly one after
+// the other.  Overlapping epilogue 1 of block i + 1 with layer 2 of block i needs a second A2s
+// buffer (64 KiB more than one SM's shared memory holds beside W2): a cta_group::2 pair with W2
+// split over the two SMs would make room -- the next step for this kernel.  The first version of this kernel
 // used warp-level mma.sync with the activations chained through registers (layer-1 accumulator
 // fragments = layer-2 A fragments): 0.37 ms, 70 % of the legacy tensor path's peak -- a quarter of
 // tcgen05's; it is in the history of this file.
