@@ -241,3 +241,29 @@ def test_pack_mlp_layout_matches_the_header():
     with pytest.raises(ValueError):
         pack_mlp(torch.nn.Sequential(torch.nn.Linear(8, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh()),
                  torch.nn.Linear(64, 2), "cpu")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 127, 129, 1000, 148 * 128 + 5])
+def test_fused_mlp_kernels_stay_inside_their_output_rows(n):
+    """compute-sanitizer is not available on the GPU pool: ragged batches write into views of larger
+    canary-filled tensors, and nothing beyond row n may change (row blocks are 128 rockets wide)."""
+    import torch
+    from rocket_landing_rl_b200 import ActorCriticMLP, FusedActorCritic
+    torch.manual_seed(2)
+    fused = FusedActorCritic(ActorCriticMLP().cuda())
+    obs = torch.randn((n, 8), device="cuda")
+    pad = 300
+
+    def canary(*shape):
+        return torch.full(shape, -7.0, device="cuda")
+
+    vals = canary(n + pad)
+    fused.predict_values(obs, out=vals[:n])
+    acts, logp = canary(n + pad, 2), canary(n + pad)
+    _, clipped, _, mean = fused.act(obs, acts[:n], logp[:n], want_mean=True)
+    torch.cuda.synchronize()
+    for t in (vals, acts, logp):
+        assert bool((t[n:] == -7.0).all()) and bool(torch.isfinite(t[:n]).all())
+    assert clipped.shape == (n, 2) and mean.shape == (n, 2)
+    assert torch.equal(fused.predict_values(obs), vals[:n])
