@@ -14,11 +14,11 @@ from .stats import EpisodeStats, shard_range, allreduce_stats          # noqa: F
 from .env import RocketLandingVecEnv                                   # noqa: F401
 from .single_env import RocketLandingEnv                               # noqa: F401
 from .vec_env import RocketLandingSB3VecEnv                            # noqa: F401
-from .normalize import DeviceVecNormalize                              # noqa: F401
+from .normalize import DeviceVecNormalize, read_sb3_vecnormalize       # noqa: F401
 from .simulation import RocketSimulation                               # noqa: F401
 from .rollout import ActorCriticMLP, DeviceRolloutBuffer, FusedActorCritic, collect_rollout, pack_mlp   # noqa: F401
 
 __all__ = ["Config", "load_params", "default_config_path", "Box", "STATE_WORDS",
            "fresh_state_soa", "state_soa_from_reference", "reference_view", "EpisodeStats",
-           "shard_range", "allreduce_stats", "RocketLandingEnv", "RocketLandingVecEnv", "RocketLandingSB3VecEnv", "DeviceVecNormalize",
+           "shard_range", "allreduce_stats", "RocketLandingEnv", "RocketLandingVecEnv", "RocketLandingSB3VecEnv", "DeviceVecNormalize", "read_sb3_vecnormalize",
            "ActorCriticMLP", "DeviceRolloutBuffer", "FusedActorCritic", "pack_mlp", "collect_rollout", "RocketSimulation"]

@@ -20,6 +20,37 @@ from . import _lib
 from .env import RocketLandingVecEnv
 
 
+def read_sb3_vecnormalize(path: str) -> dict:
+    """Statistics out of the ``vecnormalize.pkl`` that ``VecNormalize.save`` writes
+    (``scripts/train.py:147``, re-loaded at ``backend/rl/agent.py:73-80``) without stable-baselines3
+    or gymnasium installed: the pickle is read with stand-in classes for those two packages (numpy
+    and builtins only otherwise), and only the running moments and the clip / epsilon / gamma
+    settings are kept.  Returns what ``DeviceVecNormalize.load_stats`` takes, plus the settings."""
+    import pickle
+
+    class _Bag:
+        def __init__(self, *a, **k):
+            pass
+
+        def __setstate__(self, state):
+            self.__dict__.update(state if isinstance(state, dict) else {"state": state})
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module.startswith(("stable_baselines3", "gymnasium")):
+                return _Bag
+            if module.startswith("numpy") or module in ("builtins", "collections"):
+                return super().find_class(module, name)
+            raise pickle.UnpicklingError(f"unexpected global {module}.{name} in {path}")
+
+    with open(path, "rb") as fh:
+        vn = _Unpickler(fh).load()
+    return {"obs_mean": np.asarray(vn.obs_rms.mean, np.float64), "obs_var": np.asarray(vn.obs_rms.var, np.float64),
+            "obs_count": float(vn.obs_rms.count), "ret_mean": float(vn.ret_rms.mean), "ret_var": float(vn.ret_rms.var),
+            "ret_count": float(vn.ret_rms.count), "clip_obs": float(vn.clip_obs), "clip_reward": float(vn.clip_reward),
+            "epsilon": float(vn.epsilon), "gamma": float(vn.gamma)}
+
+
 class DeviceVecNormalize:
     def __init__(self, venv: RocketLandingVecEnv, training: bool = True, norm_obs: bool = True,
                  norm_reward: bool = True, clip_obs: float = 10.0, clip_reward: float = 10.0,

@@ -60,6 +60,37 @@ class ActorCriticMLP(nn.Module):
     def predict_values(self, obs: torch.Tensor) -> torch.Tensor:
         return self.value_net(self.value_net_body(obs)).squeeze(-1)
 
+    # ---- the reference's shipped checkpoints (assets/model/v*/best_model.zip) ------------------
+    _SB3_KEYS = {"mlp_extractor.policy_net.0": "policy_net.0", "mlp_extractor.policy_net.2": "policy_net.2",
+                 "mlp_extractor.value_net.0": "value_net_body.0", "mlp_extractor.value_net.2": "value_net_body.2",
+                 "action_net": "action_net", "value_net": "value_net"}
+
+    @classmethod
+    def from_sb3_state_dict(cls, sd) -> "ActorCriticMLP":
+        """Build the module from a stable-baselines3 ``MlpPolicy`` state dict (tensors or arrays):
+        ``mlp_extractor.{policy,value}_net.{0,2}``, ``action_net``, ``value_net``, ``log_std`` -- the
+        contents of ``policy.pth`` inside the zip ``PPO.save`` writes (``scripts/train.py:140-144``)."""
+        net = cls()
+        own = net.state_dict()
+        for src, dst in cls._SB3_KEYS.items():
+            for leaf in ("weight", "bias"):
+                t = torch.as_tensor(sd[f"{src}.{leaf}"], dtype=torch.float32)
+                if t.shape != own[f"{dst}.{leaf}"].shape:
+                    raise ValueError(f"{src}.{leaf}: shape {tuple(t.shape)}, expected {tuple(own[dst + '.' + leaf].shape)}")
+                own[f"{dst}.{leaf}"] = t
+        own["log_std"] = torch.as_tensor(sd["log_std"], dtype=torch.float32)
+        net.load_state_dict(own)
+        return net
+
+    @classmethod
+    def from_sb3_zip(cls, path: str) -> "ActorCriticMLP":
+        """``PPO.load``'s policy without stable-baselines3: read ``policy.pth`` out of the zip."""
+        import io
+        import zipfile
+        with zipfile.ZipFile(path) as z:
+            sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
+        return cls.from_sb3_state_dict(sd)
+
 
 MLP_BLOB_BYTES = 143376          # include/rocket_landing_b200.h: RL_MLP_BLOB_BYTES
 
