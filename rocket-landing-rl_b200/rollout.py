@@ -70,7 +70,9 @@ class ActorCriticMLP(nn.Module):
         """Build the module from a stable-baselines3 ``MlpPolicy`` state dict (tensors or arrays):
         ``mlp_extractor.{policy,value}_net.{0,2}``, ``action_net``, ``value_net``, ``log_std`` -- the
         contents of ``policy.pth`` inside the zip ``PPO.save`` writes (``scripts/train.py:140-144``)."""
-        net = cls()
+        w0, w2 = sd["mlp_extractor.policy_net.0.weight"], sd["mlp_extractor.policy_net.2.weight"]
+        net = cls(obs_dim=int(w0.shape[1]), act_dim=int(sd["action_net.weight"].shape[0]),
+                  hidden=(int(w0.shape[0]), int(w2.shape[0])))        # v2: 128-128, v3: 256-256
         own = net.state_dict()
         for src, dst in cls._SB3_KEYS.items():
             for leaf in ("weight", "bias"):

@@ -13,7 +13,10 @@ stable-baselines3 nor gymnasium is installed here), then drives the UNMODIFIED r
 205`` does: normalise the observation with the loaded statistics, take the deterministic action
 (the policy mean), clip it to the action space (what ``PPO.predict`` does for a ``Box``).
 
-Writes ``ref_policy_v3.npz``: the 13 weight tensors, the statistics, per-episode outcome of 1 500
+The same for ``assets/model/v2`` (an 8 -> 128 -> 128 policy trained for 950 000 steps; ``v1`` takes a
+6-word observation of an earlier env and cannot fly this one).
+
+Writes ``ref_policy_v3.npz`` / ``ref_policy_v2.npz``: the 13 weight tensors, the statistics, per-episode outcome of 1 500
 reference episodes (landing class by ``backend/utils.evaluate_landing``, return, length) and 4 096
 (observation, normalised observation, action mean) triples met on the way, for an open-loop check
 of the fused kernels.
@@ -69,9 +72,9 @@ def load_checkpoint(version: str = "v3"):
     return sd, stats
 
 
-def main() -> None:
+def main(version: str = "v3", episodes: int = 1500) -> None:
     ref = load_reference()
-    sd, st = load_checkpoint("v3")
+    sd, st = load_checkpoint(version)
     w = {k: v.numpy().astype(np.float32) for k, v in sd.items()}
 
     def policy_mean(obs_norm: np.ndarray) -> np.ndarray:          # fp64 numpy: the fixture's reference numbers
@@ -84,7 +87,7 @@ def main() -> None:
     np.random.seed(2024)
     outcomes, returns, lengths, trip_obs, trip_norm, trip_mean = [], [], [], [], [], []
     low, high = np.array([0.0, -1.0]), np.array([1.0, 1.0])
-    for ep in range(1500):
+    for ep in range(episodes):
         obs, _ = env.reset()
         ret, done, t = 0.0, False, 0
         while not done:
@@ -105,11 +108,12 @@ def main() -> None:
     out.update(outcomes=np.asarray(outcomes, np.int8), returns=np.asarray(returns, np.float64),
                lengths=np.asarray(lengths, np.int32), trip_obs=np.asarray(trip_obs, np.float32),
                trip_norm=np.asarray(trip_norm, np.float32), trip_mean=np.asarray(trip_mean, np.float32))
-    np.savez_compressed(os.path.join(_HERE, "ref_policy_v3.npz"), **out)
+    np.savez_compressed(os.path.join(_HERE, f"ref_policy_{version}.npz"), **out)
     oc = np.bincount(np.asarray(outcomes), minlength=5)
-    print(f"1500 reference episodes with the v3 agent: none/safe/good/ok/unsafe = {oc.tolist()}, "
+    print(f"{episodes} reference episodes with the {version} agent: none/safe/good/ok/unsafe = {oc.tolist()}, "
           f"mean return {np.mean(returns):.1f}, mean length {np.mean(lengths):.1f}, triples {len(trip_obs)}")
 
 
 if __name__ == "__main__":
-    main()
+    for v in (sys.argv[1:] or ["v3", "v2"]):       # v1 was trained on an earlier, 6-word observation: not this env
+        main(v)
