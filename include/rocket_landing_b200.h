@@ -34,34 +34,49 @@
 extern "C" {
 #endif
 
-#define RL_ABI_VERSION 1
+#define RL_ABI_VERSION 2
 
 #define RL_OK 0
 #define RL_E_INVALID (-1)   /* bad argument                        */
 #define RL_E_CUDA (-2)      /* a CUDA runtime call / launch failed */
 #define RL_E_NOMEM (-3)     /* allocation failed                   */
 
-/* Words of the public state format used by rl_set_state / rl_get_state: float32 [10][N]
- * (structure of arrays, word-major).  RL_W_META holds raw int32 bits. */
+/* Words of the public state format used by rl_set_state / rl_get_state: 32-bit words [10][N]
+ * (structure of arrays, word-major), passed as float32 buffers.  They are the kernel's own
+ * persistent words, so a get -> set round trip is lossless.  Words that INTEGRATE over an
+ * episode are 32-bit FIXED POINT (raw int32 / uint32 bits inside the float32 buffer): an fp32
+ * rounding error in them would persist for the rest of the episode, and the reference runs
+ * 1000-step episodes in fp64 (DESIGN.md "Long-horizon accuracy").  rocket-landing-rl_b200/layout.py
+ * converts to and from the reference's Rocket.state words. */
 #define RL_STATE_WORDS 10
-#define RL_W_X 0        /* m                                                              */
-#define RL_W_Y 1        /* m                                                              */
-#define RL_W_ANGLE 2    /* deg, normalised to [-180, 180)  (engine.py:230)                */
-#define RL_W_SX 3       /* carried x delta  x(t) - x(t-dt);  vx itself while FRESH        */
-#define RL_W_SY 4       /* carried y delta;                  vy itself while FRESH        */
-#define RL_W_SANGLE 5   /* carried pre-wrap angle delta;     angular velocity while FRESH */
-#define RL_W_DRY 6      /* kg                                                             */
-#define RL_W_FUEL 7     /* kg                                                             */
-#define RL_W_META 8     /* int32 bits: [0,24) episode step count (lander.py:229),
+#define RL_W_X 0        /* f32  m                                                              */
+#define RL_W_Y 1        /* f32  m                                                              */
+#define RL_W_ANGLE 2    /* i32  units of 360 / 2^32 deg: int32 range == [-180, 180), so integer
+                           wrap-around IS normalize_angle_180 (engine.py:230)                  */
+#define RL_W_SX 3       /* i32  carried x delta x(t) - x(t-dt), units of 2^-23 m;
+                           f32 bits of vx itself while FRESH                                   */
+#define RL_W_SY 4       /* i32  carried y delta, units of 2^-23 m; f32 bits of vy while FRESH  */
+#define RL_W_SANGLE 5   /* f32  carried pre-wrap angle delta in deg (high part; 8 more bits in
+                           RL_W_META); angular velocity in deg/s while FRESH                   */
+#define RL_W_DRY 6      /* f32  kg                                                             */
+#define RL_W_FUEL 7     /* i32  units of rl_fuel_unit() kg (2^-12 kg for the reference config) */
+#define RL_W_META 8     /* u32 bits: [0,16) episode step count (lander.py:229),
+                           [16,24) signed low-order extension of RL_W_SANGLE, in units of
+                           ulp(RL_W_SANGLE) / 256,
                            [24,27) signed count k of 360-degree wraps applied by the last
                            normalisation (engine.py:226 stores the normalised angle as the
-                           next step's "previous" angle, base.py:171), bit 31 FRESH = just
-                           reset, Verlet bootstrap (base.py:65) not applied yet           */
-#define RL_W_EPRET 9    /* running episode return                                         */
+                           next step's "previous" angle, base.py:171),
+                           [27,30) landing code and bit 30 "landed" (simulation mode only),
+                           bit 31 FRESH = just reset, Verlet bootstrap (base.py:65) not
+                           applied yet                                                         */
+#define RL_W_EPRET 9    /* f32  running episode return                                         */
 
-#define RL_META_STEP_MASK 0x00FFFFFFu
+#define RL_META_STEP_MASK 0x0000FFFFu
+#define RL_META_DLO_SHIFT 16
 #define RL_META_WRAP_SHIFT 24
 #define RL_META_FRESH 0x80000000u
+#define RL_ANGLE_UNITS_PER_DEG (4294967296.0 / 360.0)
+#define RL_DELTA_UNITS_PER_M 8388608.0
 
 /* Slots of the statistics vector (float64 [16]) returned by rl_stats. */
 #define RL_STATS_WORDS 16
@@ -147,6 +162,12 @@ int rl_create(const RlParams *params, int64_t n_envs, int64_t env_id_offset, uin
 int rl_destroy(RlEnv *env);
 
 int64_t rl_num_envs(const RlEnv *env);
+
+/* kg per unit of the fixed-point fuel word RL_W_FUEL: 2^(k-31), 2^k being the first power of two
+ * above params->reset_high[9] (the largest fuel load a reset can draw; fuel only decreases).
+ * rl_fuel_unit_for computes the same from a parameter set without a handle. */
+double rl_fuel_unit(const RlEnv *env);
+double rl_fuel_unit_for(const RlParams *params);
 
 /* 1 if this handle runs the kernel instantiation with the reference's config.yaml constants
  * folded in at compile time (chosen only when every derived constant is bit-identical to those

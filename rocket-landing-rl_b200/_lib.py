@@ -13,11 +13,11 @@ LIB_NAME = "librocket_landing_b200.so"
 # RL_B200_LIBRARY points the loader at another build of the SAME sources (tools/build_variants.py
 # makes them for kernel experiments); it is still this library or nothing -- there is no fallback.
 LIB_PATH = os.environ.get("RL_B200_LIBRARY") or os.path.join(_PKG_DIR, LIB_NAME)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/rocket_landing_b200.h declares
 EXPORTS = ("rl_abi_version", "rl_last_error", "rl_params_default", "rl_state_bytes", "rl_create",
-           "rl_destroy", "rl_num_envs", "rl_uses_folded_constants", "rl_get_epoch", "rl_set_epoch", "rl_reset", "rl_step",
+           "rl_destroy", "rl_num_envs", "rl_fuel_unit", "rl_fuel_unit_for", "rl_uses_folded_constants", "rl_get_epoch", "rl_set_epoch", "rl_reset", "rl_step",
            "rl_set_state", "rl_get_state", "rl_stats", "rl_step_host", "rl_reset_host", "rl_get_state_host",
            "rl_launch_count", "rl_vecnorm_last_error", "rl_vecnorm_create", "rl_vecnorm_destroy",
            "rl_vecnorm_reset", "rl_vecnorm_step", "rl_vecnorm_normalize_obs", "rl_vecnorm_get_stats",
@@ -57,6 +57,10 @@ def load():
     L.rl_destroy.argtypes = [vp]
     L.rl_num_envs.argtypes = [vp]
     L.rl_num_envs.restype = i64
+    L.rl_fuel_unit.argtypes = [vp]
+    L.rl_fuel_unit.restype = C.c_double
+    L.rl_fuel_unit_for.argtypes = [C.POINTER(RlParams)]
+    L.rl_fuel_unit_for.restype = C.c_double
     L.rl_uses_folded_constants.argtypes = [vp]
     L.rl_get_epoch.argtypes = [vp]
     L.rl_get_epoch.restype = u64

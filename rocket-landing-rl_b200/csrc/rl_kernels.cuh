@@ -1,9 +1,11 @@
 // Kernels of the batched environment step.  State layout in HBM (DESIGN.md "Data layout"):
 //
-//   plane A  float4[Np]  { x, y, angle, meta }          read + written every step
-//   plane B  float4[Np]  { sx, sy, sangle, ep_return }   read + written every step
-//   fuel     float [Np]                                  read + written every step
-//   dry      float [Np]                                  read every step, written on reset only
+//   plane A  16 B x Np  { x f32, y f32, angle i32, meta u32 }          read + written every step
+//   plane B  16 B x Np  { sx i32, sy i32, sangle f32, ep_return f32 }  read + written every step
+//   fuel     i32 [Np]                                                  read + written every step
+//   dry      f32 [Np]                                                  read every step, written on reset only
+// (the integer words are fixed point, rl_device.cuh "PRECISION"; the planes are declared float4 /
+// float and the integer words travel as raw bits)
 //
 // Np = n_envs rounded up to 256; all planes live in one buffer so a checkpoint is one tensor.
 // Thread t of a CTA owns rocket tile * 256 + t of the tile the CTA is working on, so every
@@ -198,19 +200,21 @@ __device__ __forceinline__ void stats_flush(BlockStats& s, double* __restrict__ 
         atomicAdd(&g[(blockIdx.x % kStatSlots) * RL_STATS_WORDS + threadIdx.x], s.sum[threadIdx.x]);
 }
 
+__device__ __forceinline__ void unpack_rocket(const float4& a, const float4& b, float fuel_bits, float dry, Rocket& r) {
+    r.x = a.x; r.y = a.y; r.ang = __float_as_int(a.z); r.meta = __float_as_uint(a.w);
+    r.sx = __float_as_uint(b.x); r.sy = __float_as_uint(b.y); r.sang = b.z; r.ep_ret = b.w;
+    r.fuel = __float_as_int(fuel_bits);
+    r.dry = dry;
+}
+
 __device__ __forceinline__ void load_rocket(const StatePlanes& st, uint32_t i, Rocket& r) {
-    const float4 a = st.A[i];
-    const float4 b = st.B[i];
-    r.fuel = st.fuel[i];
-    r.dry = st.dry[i];
-    r.x = a.x; r.y = a.y; r.ang = a.z; r.meta = __float_as_uint(a.w);
-    r.sx = b.x; r.sy = b.y; r.sang = b.z; r.ep_ret = b.w;
+    unpack_rocket(st.A[i], st.B[i], st.fuel[i], st.dry[i], r);
 }
 
 __device__ __forceinline__ void store_rocket(const StatePlanes& st, uint32_t i, const Rocket& r, bool write_dry) {
-    st.A[i] = make_float4(r.x, r.y, r.ang, __uint_as_float(r.meta));
-    st.B[i] = make_float4(r.sx, r.sy, r.sang, r.ep_ret);
-    st.fuel[i] = r.fuel;
+    st.A[i] = make_float4(r.x, r.y, __int_as_float(r.ang), __uint_as_float(r.meta));
+    st.B[i] = make_float4(__uint_as_float(r.sx), __uint_as_float(r.sy), r.sang, r.ep_ret);
+    st.fuel[i] = __int_as_float(r.fuel);
     if (write_dry) st.dry[i] = r.dry;
 }
 
@@ -358,12 +362,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
         float2 act;
         {
             cp_async_wait<kStages - 2>();                   // this tile's group has landed
-            const float4 va = ring[s].A[tid];
-            const float4 vb = ring[s].B[tid];
-            r.fuel = ring[s].fuel[tid];
-            r.dry = ring[s].dry[tid];
-            r.x = va.x; r.y = va.y; r.ang = va.z; r.meta = __float_as_uint(va.w);
-            r.sx = vb.x; r.sy = vb.y; r.sang = vb.z; r.ep_ret = vb.w;
+            unpack_rocket(ring[s].A[tid], ring[s].B[tid], ring[s].fuel[tid], ring[s].dry[tid], r);
             act = ring[s].act[tid];
             // the shared-memory reads above are complete (their values are in registers) before the
             // copies below are issued by the same thread, so refilling a stage is hazard-free; issuing
@@ -444,30 +443,27 @@ __global__ void __launch_bounds__(kCtaThreads) reset_kernel(const __grid_constan
     epoch_bump(epoch_ctr, ticket);
 }
 
-// Public state format <-> planes (rl_set_state / rl_get_state).
+// Public state format <-> planes (rl_set_state / rl_get_state): the public words ARE the kernel's
+// words (raw 32-bit copies), so a get -> set round trip is lossless.
 __global__ void __launch_bounds__(kCtaThreads) set_state_kernel(StatePlanes st, const float* __restrict__ soa,
                                                                 const uint8_t* __restrict__ mask, uint32_t n) {
     const size_t N = n;
     for (uint32_t i = blockIdx.x * kCtaThreads + threadIdx.x; i < n; i += gridDim.x * kCtaThreads) {
         if (mask && !mask[i]) continue;
-        Rocket r;
-        r.x = soa[RL_W_X * N + i]; r.y = soa[RL_W_Y * N + i]; r.ang = soa[RL_W_ANGLE * N + i];
-        r.sx = soa[RL_W_SX * N + i]; r.sy = soa[RL_W_SY * N + i]; r.sang = soa[RL_W_SANGLE * N + i];
-        r.dry = soa[RL_W_DRY * N + i]; r.fuel = soa[RL_W_FUEL * N + i];
-        r.meta = __float_as_uint(soa[RL_W_META * N + i]); r.ep_ret = soa[RL_W_EPRET * N + i];
-        store_rocket(st, i, r, true);
+        st.A[i] = make_float4(soa[RL_W_X * N + i], soa[RL_W_Y * N + i], soa[RL_W_ANGLE * N + i], soa[RL_W_META * N + i]);
+        st.B[i] = make_float4(soa[RL_W_SX * N + i], soa[RL_W_SY * N + i], soa[RL_W_SANGLE * N + i], soa[RL_W_EPRET * N + i]);
+        st.fuel[i] = soa[RL_W_FUEL * N + i];
+        st.dry[i] = soa[RL_W_DRY * N + i];
     }
 }
 
 __global__ void __launch_bounds__(kCtaThreads) get_state_kernel(StatePlanes st, float* __restrict__ soa, uint32_t n) {
     const size_t N = n;
     for (uint32_t i = blockIdx.x * kCtaThreads + threadIdx.x; i < n; i += gridDim.x * kCtaThreads) {
-        Rocket r;
-        load_rocket(st, i, r);
-        soa[RL_W_X * N + i] = r.x; soa[RL_W_Y * N + i] = r.y; soa[RL_W_ANGLE * N + i] = r.ang;
-        soa[RL_W_SX * N + i] = r.sx; soa[RL_W_SY * N + i] = r.sy; soa[RL_W_SANGLE * N + i] = r.sang;
-        soa[RL_W_DRY * N + i] = r.dry; soa[RL_W_FUEL * N + i] = r.fuel;
-        soa[RL_W_META * N + i] = __uint_as_float(r.meta); soa[RL_W_EPRET * N + i] = r.ep_ret;
+        const float4 a = st.A[i], b = st.B[i];
+        soa[RL_W_X * N + i] = a.x; soa[RL_W_Y * N + i] = a.y; soa[RL_W_ANGLE * N + i] = a.z; soa[RL_W_META * N + i] = a.w;
+        soa[RL_W_SX * N + i] = b.x; soa[RL_W_SY * N + i] = b.y; soa[RL_W_SANGLE * N + i] = b.z; soa[RL_W_EPRET * N + i] = b.w;
+        soa[RL_W_FUEL * N + i] = st.fuel[i]; soa[RL_W_DRY * N + i] = st.dry[i];
     }
 }
 

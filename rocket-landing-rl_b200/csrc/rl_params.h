@@ -30,9 +30,24 @@ namespace rl {
 // Constants in fp32, derived on the host in double (derive_params).  Thresholds are rounded in
 // the direction that keeps the comparison exact for fp32 inputs: for a double threshold c,
 // `x > c` == `x > down(c)` and `x < c` == `x < up(c)` for every fp32 x.
+// Units of the fixed-point state words (DESIGN.md "Long-horizon accuracy"): errors in the
+// integrated words persist for the rest of an episode, so they carry 32 significant bits.
+constexpr double kAngleUnit = 360.0 / 4294967296.0;      // degrees per unit of the int32 angle: [-180, 180) = int32
+constexpr double kAngleInvUnit = 4294967296.0 / 360.0;
+constexpr double kDeltaUnit = 1.0 / 8388608.0;           // metres per unit of the int32 position deltas (2^-23 m)
+constexpr double kDeltaInvUnit = 8388608.0;
+
 struct DevParams {
     float dt, inv_dt, dt2, half_dt2;
-    double dt_d;               // time step in fp64 (precise-altitude mode)
+    // ---- extended-precision words (DESIGN.md "Long-horizon accuracy") ----------------------------
+    double dt_d;               // time step in fp64 (Verlet bootstrap of a FRESH rocket)
+    double damp_d;             // max(0, 1 - angular_damping dt) in fp64 (angle chain)
+    double alpha_dt2_d;        // alpha_k dt^2 in fp64: the angle delta gains cg alpha_dt2_d / m per step
+    double fuel_unit_d;        // kg per unit of the fixed-point fuel word (a power of two)
+    double alpha_min_mass_d;   // fp64 copy of the inertia gate
+    float dt2_units;           // dt^2 / kDeltaUnit: acceleration -> fixed-point delta increment
+    float burn_units;          // fuel_consumption_rate dt / fuel_unit: throttle -> fixed-point burn
+    float fuel_inv_unit;       // 1 / fuel_unit (reset: kg -> units)
     float gravity;
     float thrust_power;        // N at throttle 1
     float drag_k;              // 0.5 rho Cd A   (engine.py:88-94); drag force = -drag_k |v| v
@@ -67,6 +82,13 @@ struct DefaultParams {
     static constexpr double kDt = 0.1, kPi = 3.14159265358979323846;
     static constexpr float dt = (float)kDt;
     static constexpr double dt_d = kDt;
+    static constexpr double damp_d = 1.0 - 0.05 * kDt;
+    static constexpr double alpha_dt2_d = 7.0e4 * 1.85 / (0.5 * 1.85 * 1.85) * (180.0 / kPi) * (kDt * kDt);
+    static constexpr double fuel_unit_d = 1.0 / 4096.0;               // 410 000 kg < 2^19 -> 2^(19-31)
+    static constexpr double alpha_min_mass_d = 1e-6 / (0.5 * 1.85 * 1.85);
+    static constexpr float dt2_units = (float)(kDt * kDt * 8388608.0);
+    static constexpr float burn_units = (float)(1700.0 * kDt * 4096.0);
+    static constexpr float fuel_inv_unit = 4096.0f;
     static constexpr float inv_dt = (float)(1.0 / kDt);
     static constexpr float dt2 = (float)(kDt * kDt);
     static constexpr float half_dt2 = (float)(0.5 * kDt * kDt);
@@ -109,7 +131,9 @@ struct DefaultParams {
 
 inline bool matches_default(const DevParams& d) {
     using D = DefaultParams;
-    bool ok = d.dt == D::dt && d.dt_d == D::dt_d && d.inv_dt == D::inv_dt && d.dt2 == D::dt2 && d.half_dt2 == D::half_dt2 &&
+    bool ok = d.dt == D::dt && d.dt_d == D::dt_d && d.damp_d == D::damp_d && d.alpha_dt2_d == D::alpha_dt2_d &&
+              d.fuel_unit_d == D::fuel_unit_d && d.alpha_min_mass_d == D::alpha_min_mass_d &&
+              d.dt2_units == D::dt2_units && d.burn_units == D::burn_units && d.fuel_inv_unit == D::fuel_inv_unit && d.inv_dt == D::inv_dt && d.dt2 == D::dt2 && d.half_dt2 == D::half_dt2 &&
               d.gravity == D::gravity && d.thrust_power == D::thrust_power && d.drag_k == D::drag_k &&
               d.alpha_k == D::alpha_k && d.alpha_min_mass == D::alpha_min_mass && d.damp == D::damp &&
               d.burn_per_step == D::burn_per_step && d.mass_gate == D::mass_gate &&
@@ -151,6 +175,14 @@ inline float f32_up(double c) {
     return f;
 }
 
+// kg per unit of the (signed) fixed-point fuel word: 2^(k - 31) with 2^k the first power of two
+// ABOVE the largest fuel mass of the reset distribution (config.yaml:66-67: 410 000 kg -> 2^-12 kg)
+inline double fuel_unit_for(double max_fuel) {
+    int k = 0;
+    if (max_fuel >= 1.0) k = (int)floor(log2(max_fuel)) + 1;
+    return ldexp(1.0, k - 31);
+}
+
 inline int derive_params(const RlParams& p, DevParams& d, char* err, size_t err_len) {
     if (!(p.time_step > 0)) return derive_fail(err, err_len, "time_step must be positive");          // engine.py:35
     if (p.thrust_power < 0 || p.cold_gas_thrust_power < 0 || p.fuel_consumption_rate < 0)
@@ -158,7 +190,9 @@ inline int derive_params(const RlParams& p, DevParams& d, char* err, size_t err_
     if (!(p.radius > 0) || !(p.cold_gas_moment_arm > 0))
         return derive_fail(err, err_len, "radius and moment arm must be positive");                  // engine.py:45-46
     if (p.max_episode_steps < 1 || p.max_episode_steps > (int)RL_META_STEP_MASK)
-        return derive_fail(err, err_len, "max_episode_steps out of range");
+        return derive_fail(err, err_len, "max_episode_steps out of range (1 .. %d)", (int)RL_META_STEP_MASK);
+    if (!(p.reset_high[9] < 9.0e18))
+        return derive_fail(err, err_len, "reset_high[9] (fuel mass) out of range");
     const double pi = 3.14159265358979323846;
     const double dt = p.time_step;
     d.dt = (float)dt;
@@ -174,7 +208,16 @@ inline int derive_params(const RlParams& p, DevParams& d, char* err, size_t err_
     // engine.py:137-143: alpha = 0 when m <= 1e-6, radius <= 1e-6 or 0.5 m r^2 < 1e-6
     d.alpha_min_mass = (p.radius <= 1e-6) ? INFINITY : f32_up(1e-6 / half_r2);
     d.damp = (float)fmax(0.0, 1.0 - p.angular_damping * dt);
+    d.damp_d = fmax(0.0, 1.0 - p.angular_damping * dt);
+    d.alpha_dt2_d = p.cold_gas_thrust_power * p.cold_gas_moment_arm / half_r2 * (180.0 / pi) * (dt * dt);
+    d.alpha_min_mass_d = (p.radius <= 1e-6) ? INFINITY : 1e-6 / half_r2;
     d.burn_per_step = (float)(p.fuel_consumption_rate * dt);
+    // fixed-point fuel: the smallest power-of-two unit whose int32 range covers the largest
+    // fuel load the reset distribution can draw (fuel only ever decreases)
+    d.fuel_unit_d = fuel_unit_for(p.reset_high[9]);
+    d.fuel_inv_unit = (float)(1.0 / d.fuel_unit_d);
+    d.burn_units = (float)(p.fuel_consumption_rate * dt / d.fuel_unit_d);
+    d.dt2_units = (float)(dt * dt / kDeltaUnit);
     d.mass_gate = f32_down(1e-6);
     d.throttle_gate = f32_down(1e-6);
     d.speed2_gate = f32_down(1e-9);

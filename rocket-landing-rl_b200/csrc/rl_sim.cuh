@@ -41,14 +41,14 @@ __global__ void __launch_bounds__(kCtaThreads) sim_step_kernel(const __grid_cons
         const float th = clipf(act.x, 0.0f, 1.0f), cg = clipf(act.y, -1.0f, 1.0f);     // controls.py:72-73
         StepResult o;
         rocket_step(P, r, th, cg, o);                     // the reward sees the CLIPPED action here
-        const float vx = r.sx * P.inv_dt, vy = r.sy * P.inv_dt, om = r.sang * P.inv_dt;
+        const float vx = o.vx, vy = o.vy, om = o.om;      // (delta / dt of the state just written)
         const bool landed = o.terminated;                 // the truncation flag is ignored (controls.py:89)
         if (landed) r.meta |= kMetaLanded | ((uint32_t)o.landing << kMetaCodeShift);
         store_rocket(st, i, r, false);
         // protocol.py:78-96; the echoed action is the one just applied, zeros on the touchdown tick
         rec[0] = make_float4(r.x, r.y, vx, vy);
-        rec[1] = make_float4(o.ax, o.ay, r.ang, om);
-        rec[2] = make_float4(o.alpha, r.dry, r.fuel, o.reward);
+        rec[1] = make_float4(o.ax, o.ay, angle_deg(r.ang), om);
+        rec[2] = make_float4(o.alpha, r.dry, (float)((double)r.fuel * P.fuel_unit_d), o.reward);
         rec[3] = make_float4(landed ? 0.0f : act.x, landed ? 0.0f : act.y, (float)o.landing, 1.0f);
         if (reward) reward[i] = o.reward;
         if (done) done[i] = landed ? 1 : 0;

@@ -90,6 +90,7 @@ class RocketLandingVecEnv:
         _lib.check(self._L.rl_create(C.byref(self.params), n, int(env_id_offset), int(seed) & (2**64 - 1),
                                      dev_index, self.state_buffer.data_ptr(), C.byref(handle)), "rl_create")
         self._h = handle
+        self.fuel_unit = float(self._L.rl_fuel_unit(self._h))     # kg per unit of the fixed-point fuel word
         f32 = dict(dtype=torch.float32, device=self.device)
         self.obs = torch.zeros((n, 8), **f32)
         self.reward = torch.zeros((n,), **f32)
@@ -155,10 +156,11 @@ class RocketLandingVecEnv:
 
     # ------------------------------------------------------------------ state injection / checkpoint
     def set_state(self, state_soa, mask=None) -> None:
-        """Inject persistent state in the public format (float32 [10, N], see ``layout``)."""
+        """Inject persistent state in the public format (32-bit words [10, N] carried as float32,
+        see ``layout``)."""
         s = torch.as_tensor(state_soa)
         if s.dtype != torch.float32:
-            raise TypeError("state_soa must be float32 (the meta word carries raw int32 bits)")
+            raise TypeError("state_soa must be float32 (the integer words travel as raw bits)")
         s = s.to(self.device).contiguous()
         if s.shape != (10, self.num_envs):
             raise ValueError(f"state_soa must have shape (10, {self.num_envs})")
@@ -176,7 +178,7 @@ class RocketLandingVecEnv:
 
     def get_reference_state(self) -> dict:
         """Persistent state as the reference's ``Rocket.state`` words (float64 numpy)."""
-        return reference_view(self.get_state().cpu().numpy(), self.dt)
+        return reference_view(self.get_state().cpu().numpy(), self.dt, self.fuel_unit)
 
     def state_dict(self) -> dict:
         return {"state": self.state_buffer.clone(), "epoch": int(self._L.rl_get_epoch(self._h)),

@@ -1,47 +1,104 @@
 """Host-side helpers for the public state format of ``rl_set_state`` / ``rl_get_state``
-(float32 ``[10][N]``, words ``RL_W_*`` of include/rocket_landing_b200.h).
+(32-bit words ``[10][N]`` carried in a float32 array, words ``RL_W_*`` of
+include/rocket_landing_b200.h).
 
 The kernel does not store the reference's ``Rocket.state`` dict verbatim: it carries the
 Verlet DELTAS ``x(t) - x(t-dt)`` (from which ``v = delta / dt``, engine.py:193-194) instead of
 ``previous_state`` (base.py:171), and a FRESH flag instead of a bootstrapped previous state
-(base.py:65) -- see DESIGN.md "fp32 formulation".  These helpers convert in both directions,
-doing the subtractions in float64 so that nothing is lost before the float32 rounding.
+(base.py:65) -- see DESIGN.md "fp32 formulation".  The words that integrate over an episode are
+32-bit FIXED POINT (angle, position deltas, fuel) or carry 8 extra mantissa bits (angle delta),
+DESIGN.md "Long-horizon accuracy".  These helpers convert in both directions, in float64, so
+nothing is lost before the final rounding to the device word.
 """
 from __future__ import annotations
+
+import math
 
 import numpy as np
 
 STATE_WORDS = ("x", "y", "angle", "sx", "sy", "sangle", "dry_mass", "fuel", "meta", "ep_return")
 W_X, W_Y, W_ANGLE, W_SX, W_SY, W_SANGLE, W_DRY, W_FUEL, W_META, W_EPRET = range(10)
-META_STEP_MASK = 0x00FFFFFF
+META_STEP_MASK = 0x0000FFFF
+META_DLO_SHIFT = 16
 META_WRAP_SHIFT = 24
 META_FRESH = 0x80000000
+ANGLE_UNITS_PER_DEG = 4294967296.0 / 360.0       # int32 range == [-180, 180)
+DELTA_UNITS_PER_M = 8388608.0                    # 2^-23 m per unit
+DEFAULT_FUEL_UNIT = 1.0 / 4096.0                 # kg; reference config.yaml (fuel <= 410 000 kg)
 
 
-def _meta_bits(steps, wraps, fresh) -> np.ndarray:
+def fuel_unit_for(max_fuel: float) -> float:
+    """kg per unit of the signed fixed-point fuel word (``rl_fuel_unit_for``): 2^(k-31) with 2^k
+    the first power of two above the largest fuel load of the reset distribution."""
+    k = int(math.floor(math.log2(max_fuel))) + 1 if max_fuel >= 1.0 else 0
+    return math.ldexp(1.0, k - 31)
+
+
+def _bits(a: np.ndarray) -> np.ndarray:
+    """uint32 / int32 array -> the same bits as float32."""
+    return np.ascontiguousarray(a).view(np.float32)
+
+
+def _meta_bits(steps, wraps, fresh, dlo=0) -> np.ndarray:
     steps = np.asarray(steps, np.int64) & META_STEP_MASK
     wraps = (np.asarray(wraps, np.int64) & 7) << META_WRAP_SHIFT
-    bits = (steps | wraps | (META_FRESH if fresh else 0)).astype(np.uint32)
+    dlo = (np.asarray(dlo, np.int64) & 0xFF) << META_DLO_SHIFT
+    bits = (steps | wraps | dlo | (META_FRESH if fresh else 0)).astype(np.uint32)
     return bits.view(np.float32)
 
 
-def fresh_state_soa(x, y, vx, vy, angle, ang_vel, dry_mass, fuel, steps=0, ep_return=0.0) -> np.ndarray:
+def _angle_units(angle_deg: np.ndarray) -> np.ndarray:
+    """degrees in [-180, 180) -> int32 units (wraps like the kernel's integer add)."""
+    u = np.rint(np.asarray(angle_deg, np.float64) * ANGLE_UNITS_PER_DEG).astype(np.int64)
+    return (u & 0xFFFFFFFF).astype(np.uint32).view(np.int32)
+
+
+def _fuel_units(fuel_kg: np.ndarray, fuel_unit: float) -> np.ndarray:
+    u = np.rint(np.asarray(fuel_kg, np.float64) / fuel_unit)
+    return np.clip(u, -2147483648, 2147483647).astype(np.int32)
+
+
+def split_angle_delta(dang: np.ndarray):
+    """float64 angle delta -> (float32 high part, int low part in [-128, 127]); the low part
+    counts units of ulp(high) / 256 (``dtheta_split`` in csrc/rl_device.cuh)."""
+    dang = np.asarray(dang, np.float64)
+    hi = dang.astype(np.float32)
+    e = ((hi.view(np.uint32) >> 23) & 0xFF).astype(np.int64)
+    unit = np.ldexp(1.0, (e - 158).astype(np.int32))
+    lo = np.clip(np.rint((dang - hi.astype(np.float64)) / unit), -128, 127).astype(np.int64)
+    return hi, lo
+
+
+def join_angle_delta(hi: np.ndarray, lo: np.ndarray) -> np.ndarray:
+    hi = np.asarray(hi, np.float32)
+    e = ((hi.view(np.uint32) >> 23) & 0xFF).astype(np.int64)
+    return hi.astype(np.float64) + np.asarray(lo, np.float64) * np.ldexp(1.0, (e - 158).astype(np.int32))
+
+
+def fresh_state_soa(x, y, vx, vy, angle, ang_vel, dry_mass, fuel, steps=0, ep_return=0.0,
+                    fuel_unit: float = DEFAULT_FUEL_UNIT) -> np.ndarray:
     """A just-reset rocket (``Rocket.reset``, base.py:186): the kernel applies the Verlet
     bootstrap (base.py:65-130) itself on the first step.  All arguments are arrays [N]
-    (or scalars); returns float32 [10, N]."""
+    (or scalars); returns the public words as float32 [10, N]."""
     cols = np.broadcast_arrays(*[np.asarray(v, np.float64) for v in
                                  (x, y, angle, vx, vy, ang_vel, dry_mass, fuel)])
-    n = cols[0].size
+    cx, cy, cang, cvx, cvy, com, cdry, cfuel = [c.reshape(-1) for c in cols]
+    n = cx.size
     soa = np.zeros((10, n), np.float32)
-    for w, col in zip((W_X, W_Y, W_ANGLE, W_SX, W_SY, W_SANGLE, W_DRY, W_FUEL), cols):
-        soa[w] = col.reshape(n)
-    soa[W_META] = _meta_bits(np.broadcast_to(np.asarray(steps), (n,)), 0, True)
+    soa[W_X], soa[W_Y] = cx, cy
+    soa[W_ANGLE] = _bits(_angle_units(cang))
+    soa[W_SX], soa[W_SY] = cvx, cvy                            # velocities themselves while FRESH
+    om_hi, om_lo = split_angle_delta(com)                      # (omega with its 8 extra bits)
+    soa[W_SANGLE] = om_hi
+    soa[W_DRY] = cdry
+    soa[W_FUEL] = _bits(_fuel_units(cfuel, fuel_unit))
+    soa[W_META] = _meta_bits(np.broadcast_to(np.asarray(steps), (n,)), 0, True, om_lo)
     soa[W_EPRET] = np.broadcast_to(np.asarray(ep_return, np.float32), (n,))
     return soa
 
 
 def state_soa_from_reference(state: np.ndarray, prev: np.ndarray, steps, dt: float,
-                             ep_return=0.0) -> np.ndarray:
+                             ep_return=0.0, fuel_unit: float = DEFAULT_FUEL_UNIT) -> np.ndarray:
     """Mid-episode injection from the reference's dicts.
 
     ``state`` [N,10] float64 in the reference's word order (x y vx vy ax ay angle
@@ -53,31 +110,47 @@ def state_soa_from_reference(state: np.ndarray, prev: np.ndarray, steps, dt: flo
     prev = np.asarray(prev, np.float64)
     n = state.shape[0]
     soa = np.zeros((10, n), np.float32)
-    soa[W_X], soa[W_Y], soa[W_ANGLE] = state[:, 0], state[:, 1], state[:, 6]
-    soa[W_SX] = state[:, 0] - prev[:, 0]
-    soa[W_SY] = state[:, 1] - prev[:, 1]
+    soa[W_X], soa[W_Y] = state[:, 0], state[:, 1]
+    soa[W_ANGLE] = _bits(_angle_units(state[:, 6]))
+    soa[W_SX] = _bits(np.rint((state[:, 0] - prev[:, 0]) * DELTA_UNITS_PER_M).astype(np.int32))
+    soa[W_SY] = _bits(np.rint((state[:, 1] - prev[:, 1]) * DELTA_UNITS_PER_M).astype(np.int32))
     pre_wrap = state[:, 7] * dt
-    soa[W_SANGLE] = pre_wrap
+    hi, lo = split_angle_delta(pre_wrap)
+    soa[W_SANGLE] = hi
     wraps = np.rint((pre_wrap - (state[:, 6] - prev[:, 2])) / 360.0).astype(np.int64)
-    soa[W_DRY], soa[W_FUEL] = state[:, 8], state[:, 9]
-    soa[W_META] = _meta_bits(np.broadcast_to(np.asarray(steps), (n,)), wraps, False)
+    soa[W_DRY] = state[:, 8]
+    soa[W_FUEL] = _bits(_fuel_units(state[:, 9], fuel_unit))
+    soa[W_META] = _meta_bits(np.broadcast_to(np.asarray(steps), (n,)), wraps, False, lo)
     soa[W_EPRET] = np.broadcast_to(np.asarray(ep_return, np.float32), (n,))
     return soa
 
 
-def reference_view(soa: np.ndarray, dt: float) -> dict:
+def reference_view(soa: np.ndarray, dt: float, fuel_unit: float = DEFAULT_FUEL_UNIT) -> dict:
     """Public format -> the words of the reference's ``Rocket.state`` (float64 arrays) plus
     ``steps`` / ``fresh`` / ``wraps`` / ``ep_return``.  ``ax`` / ``ay`` are not persistent state
-    (they are outputs of a step) and are not included."""
+    (they are outputs of a step) and are not included.
+
+    Velocities and the angle are formed in float32 exactly as the kernel forms the values it
+    feeds its reward / termination tests (``delta * 2^-23 * (1/dt)``, ``units * 360/2^32``), so
+    that the reference's decision functions evaluated on this view agree with the kernel's flags
+    bit for bit."""
     soa = np.asarray(soa, np.float32)
     meta = soa[W_META].view(np.uint32)
     fresh = (meta & META_FRESH) != 0
     wraps = ((meta >> META_WRAP_SHIFT) & 7).astype(np.int64)
     wraps = np.where(wraps >= 4, wraps - 8, wraps)
     inv_dt = np.float32(1.0 / dt)
-    vel = lambda w: np.where(fresh, soa[w], soa[w] * inv_dt).astype(np.float64)   # noqa: E731
+    unit = np.float32(1.0 / DELTA_UNITS_PER_M)
+
+    def vel(w):
+        delta = soa[w].view(np.int32).astype(np.float32) * unit
+        return np.where(fresh, soa[w], delta * inv_dt).astype(np.float64)
+
+    ang = soa[W_ANGLE].view(np.int32).astype(np.float32) * np.float32(1.0 / ANGLE_UNITS_PER_DEG)
+    om = np.where(fresh, soa[W_SANGLE], soa[W_SANGLE] * inv_dt).astype(np.float64)
     return {"x": soa[W_X].astype(np.float64), "y": soa[W_Y].astype(np.float64),
-            "vx": vel(W_SX), "vy": vel(W_SY), "angle": soa[W_ANGLE].astype(np.float64),
-            "ang_vel": vel(W_SANGLE), "dry_mass": soa[W_DRY].astype(np.float64),
-            "fuel": soa[W_FUEL].astype(np.float64), "steps": (meta & META_STEP_MASK).astype(np.int64),
+            "vx": vel(W_SX), "vy": vel(W_SY), "angle": ang.astype(np.float64),
+            "ang_vel": om, "dry_mass": soa[W_DRY].astype(np.float64),
+            "fuel": soa[W_FUEL].view(np.int32).astype(np.float64) * fuel_unit,
+            "steps": (meta & META_STEP_MASK).astype(np.int64),
             "fresh": fresh, "wraps": wraps, "ep_return": soa[W_EPRET].astype(np.float64)}

@@ -24,10 +24,30 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline float __fdividef(float a, float b) { return a / b; }
 using std::min;
+using std::max;
+using std::fma;
+using std::floor;
 
 #include "../../rocket-landing-rl_b200/csrc/rl_device.cuh"
 
-// soa: float32 [10][n] public state format, updated in place.  Outputs as rl_step (no reset).
+static inline uint32_t w32(const float* soa, int64_t n, int w, int64_t i) { uint32_t u; std::memcpy(&u, &soa[w * n + i], 4); return u; }
+static inline void s32(float* soa, int64_t n, int w, int64_t i, uint32_t u) { std::memcpy(&soa[w * n + i], &u, 4); }
+static inline float wf(const float* soa, int64_t n, int w, int64_t i) { return soa[w * n + i]; }
+
+static void load_rocket(const float* soa, int64_t n, int64_t i, rl::Rocket& r) {
+    r.x = wf(soa, n, RL_W_X, i); r.y = wf(soa, n, RL_W_Y, i); r.ang = (int32_t)w32(soa, n, RL_W_ANGLE, i);
+    r.sx = w32(soa, n, RL_W_SX, i); r.sy = w32(soa, n, RL_W_SY, i); r.sang = wf(soa, n, RL_W_SANGLE, i);
+    r.dry = wf(soa, n, RL_W_DRY, i); r.fuel = (int32_t)w32(soa, n, RL_W_FUEL, i);
+    r.meta = w32(soa, n, RL_W_META, i); r.ep_ret = wf(soa, n, RL_W_EPRET, i);
+}
+static void store_rocket(float* soa, int64_t n, int64_t i, const rl::Rocket& r) {
+    soa[RL_W_X * n + i] = r.x; soa[RL_W_Y * n + i] = r.y; s32(soa, n, RL_W_ANGLE, i, (uint32_t)r.ang);
+    s32(soa, n, RL_W_SX, i, r.sx); s32(soa, n, RL_W_SY, i, r.sy); soa[RL_W_SANGLE * n + i] = r.sang;
+    soa[RL_W_DRY * n + i] = r.dry; s32(soa, n, RL_W_FUEL, i, (uint32_t)r.fuel);
+    s32(soa, n, RL_W_META, i, r.meta); soa[RL_W_EPRET * n + i] = r.ep_ret;
+}
+
+// soa: 32-bit words [10][n] public state format, updated in place.  Outputs as rl_step (no reset).
 // folded != 0 runs the instantiation with the reference's default constants folded in
 // (rl::DefaultParams), which the library only selects when matches_default() holds.
 template <class PP>
@@ -35,10 +55,7 @@ static void emu_step_impl(const PP& P, float* soa, int64_t n, const float* actio
                           uint8_t* terminated, uint8_t* truncated, int8_t* landing, int substeps) {
     for (int64_t i = 0; i < n; ++i) {
         rl::Rocket r;
-        r.x = soa[RL_W_X * n + i]; r.y = soa[RL_W_Y * n + i]; r.ang = soa[RL_W_ANGLE * n + i];
-        r.sx = soa[RL_W_SX * n + i]; r.sy = soa[RL_W_SY * n + i]; r.sang = soa[RL_W_SANGLE * n + i];
-        r.dry = soa[RL_W_DRY * n + i]; r.fuel = soa[RL_W_FUEL * n + i];
-        std::memcpy(&r.meta, &soa[RL_W_META * n + i], 4); r.ep_ret = soa[RL_W_EPRET * n + i];
+        load_rocket(soa, n, i, r);
         rl::StepResult o;
         float rew = 0.0f;
         for (int k = 0; k < substeps; ++k) {
@@ -46,10 +63,7 @@ static void emu_step_impl(const PP& P, float* soa, int64_t n, const float* actio
             rew += o.reward;
             if (o.terminated || o.truncated) break;
         }
-        soa[RL_W_X * n + i] = r.x; soa[RL_W_Y * n + i] = r.y; soa[RL_W_ANGLE * n + i] = r.ang;
-        soa[RL_W_SX * n + i] = r.sx; soa[RL_W_SY * n + i] = r.sy; soa[RL_W_SANGLE * n + i] = r.sang;
-        soa[RL_W_DRY * n + i] = r.dry; soa[RL_W_FUEL * n + i] = r.fuel;
-        std::memcpy(&soa[RL_W_META * n + i], &r.meta, 4); soa[RL_W_EPRET * n + i] = r.ep_ret;
+        store_rocket(soa, n, i, r);
         std::memcpy(obs + 8 * i, o.obs, 32);
         reward[i] = rew;
         terminated[i] = o.terminated; truncated[i] = o.truncated; landing[i] = (int8_t)o.landing;
@@ -72,33 +86,6 @@ int emu_step(const RlParams* p, float* soa, int64_t n, const float* actions, flo
     return 0;
 }
 
-// Precise-altitude mode (rocket_step<PP, true>): `lo` is float32 [2][n] = y_lo, sy_lo, in/out.
-int emu_step_precise(const RlParams* p, float* soa, float* lo, int64_t n, const float* actions, float* obs,
-                     float* reward, uint8_t* terminated, uint8_t* truncated, int8_t* landing) {
-    rl::DevParams P;
-    char err[256];
-    if (rl::derive_params(*p, P, err, sizeof(err)) != RL_OK) return -1;
-    for (int64_t i = 0; i < n; ++i) {
-        rl::Rocket r;
-        r.x = soa[RL_W_X * n + i]; r.y = soa[RL_W_Y * n + i]; r.ang = soa[RL_W_ANGLE * n + i];
-        r.sx = soa[RL_W_SX * n + i]; r.sy = soa[RL_W_SY * n + i]; r.sang = soa[RL_W_SANGLE * n + i];
-        r.dry = soa[RL_W_DRY * n + i]; r.fuel = soa[RL_W_FUEL * n + i];
-        std::memcpy(&r.meta, &soa[RL_W_META * n + i], 4); r.ep_ret = soa[RL_W_EPRET * n + i];
-        r.y_lo = lo[i]; r.sy_lo = lo[n + i];
-        rl::StepResult o;
-        rl::rocket_step<rl::DevParams, true>(P, r, actions[2 * i], actions[2 * i + 1], o);
-        soa[RL_W_X * n + i] = r.x; soa[RL_W_Y * n + i] = r.y; soa[RL_W_ANGLE * n + i] = r.ang;
-        soa[RL_W_SX * n + i] = r.sx; soa[RL_W_SY * n + i] = r.sy; soa[RL_W_SANGLE * n + i] = r.sang;
-        soa[RL_W_DRY * n + i] = r.dry; soa[RL_W_FUEL * n + i] = r.fuel;
-        std::memcpy(&soa[RL_W_META * n + i], &r.meta, 4); soa[RL_W_EPRET * n + i] = r.ep_ret;
-        lo[i] = r.y_lo; lo[n + i] = r.sy_lo;
-        std::memcpy(obs + 8 * i, o.obs, 32);
-        reward[i] = o.reward;
-        terminated[i] = o.terminated; truncated[i] = o.truncated; landing[i] = (int8_t)o.landing;
-    }
-    return 0;
-}
-
 // One simulation-mode tick (rl_sim.cuh semantics) on the host: soa in/out, telemetry [n][16].
 int emu_sim_step(const RlParams* p, float* soa, int64_t n, const float* actions, float* telemetry) {
     rl::DevParams P;
@@ -107,10 +94,7 @@ int emu_sim_step(const RlParams* p, float* soa, int64_t n, const float* actions,
     const uint32_t kLanded = 0x40000000u;
     for (int64_t i = 0; i < n; ++i) {
         rl::Rocket r;
-        r.x = soa[RL_W_X * n + i]; r.y = soa[RL_W_Y * n + i]; r.ang = soa[RL_W_ANGLE * n + i];
-        r.sx = soa[RL_W_SX * n + i]; r.sy = soa[RL_W_SY * n + i]; r.sang = soa[RL_W_SANGLE * n + i];
-        r.dry = soa[RL_W_DRY * n + i]; r.fuel = soa[RL_W_FUEL * n + i];
-        std::memcpy(&r.meta, &soa[RL_W_META * n + i], 4); r.ep_ret = soa[RL_W_EPRET * n + i];
+        load_rocket(soa, n, i, r);
         float* rec = telemetry + 16 * i;
         if (r.meta & kLanded) {
             for (int k = 0; k < 16; ++k) rec[k] = 0.0f;
@@ -124,12 +108,9 @@ int emu_sim_step(const RlParams* p, float* soa, int64_t n, const float* actions,
         rl::rocket_step(P, r, th, cg, o);
         const bool landed = o.terminated;
         if (landed) r.meta |= kLanded | ((uint32_t)o.landing << 27);
-        soa[RL_W_X * n + i] = r.x; soa[RL_W_Y * n + i] = r.y; soa[RL_W_ANGLE * n + i] = r.ang;
-        soa[RL_W_SX * n + i] = r.sx; soa[RL_W_SY * n + i] = r.sy; soa[RL_W_SANGLE * n + i] = r.sang;
-        soa[RL_W_FUEL * n + i] = r.fuel; std::memcpy(&soa[RL_W_META * n + i], &r.meta, 4);
-        soa[RL_W_EPRET * n + i] = r.ep_ret;
-        const float rv[16] = {r.x, r.y, r.sx * P.inv_dt, r.sy * P.inv_dt, o.ax, o.ay, r.ang, r.sang * P.inv_dt,
-                              o.alpha, r.dry, r.fuel, o.reward, landed ? 0.0f : actions[2 * i],
+        store_rocket(soa, n, i, r);
+        const float rv[16] = {r.x, r.y, o.vx, o.vy, o.ax, o.ay, rl::angle_deg(r.ang), o.om,
+                              o.alpha, r.dry, (float)((double)r.fuel * P.fuel_unit_d), o.reward, landed ? 0.0f : actions[2 * i],
                               landed ? 0.0f : actions[2 * i + 1], (float)o.landing, 1.0f};
         std::memcpy(rec, rv, sizeof(rv));
     }
@@ -152,10 +133,7 @@ int emu_reset(const RlParams* p, float* soa, int64_t n, int64_t gid0, uint64_t s
         rl::Rocket r;
         float ax0, ay0;
         rl::sample_reset(P, seed, (uint64_t)(gid0 + i), epoch, r, ax0, ay0);
-        soa[RL_W_X * n + i] = r.x; soa[RL_W_Y * n + i] = r.y; soa[RL_W_ANGLE * n + i] = r.ang;
-        soa[RL_W_SX * n + i] = r.sx; soa[RL_W_SY * n + i] = r.sy; soa[RL_W_SANGLE * n + i] = r.sang;
-        soa[RL_W_DRY * n + i] = r.dry; soa[RL_W_FUEL * n + i] = r.fuel;
-        std::memcpy(&soa[RL_W_META * n + i], &r.meta, 4); soa[RL_W_EPRET * n + i] = r.ep_ret;
+        store_rocket(soa, n, i, r);
         rl::fresh_obs(P, r, ax0, ay0, obs + 8 * i);
     }
     return 0;

@@ -19,7 +19,13 @@ reset state; errors accumulate over the episode, ~120 steps):
   injected reset re-synchronises it.
 * reward: ``|got - ref| <= max(FREE_REWARD_ATOL, FREE_REWARD_RTOL * |ref|)``.  Loose on purpose:
   the reward amplifies state error (``8 / max(y, 1)`` near the ground, reward.py:192;
-  ``effect**2``, reward.py:160), so this leg bounds the PROPAGATED error only.
+  ``effect**2``, reward.py:160), so this leg bounds the PROPAGATED error only.  The shaping
+  reward is DISCONTINUOUS in the state at a handful of thresholds (``REWARD_STEPS`` below); where
+  the reference's own decision variable sits inside the guard band of one of them the step is
+  counted (``reward_guard_events``) instead of compared -- a stabilising controller parks the
+  angle at 0 +- 1e-3 deg, where ``correct_direction`` (reward.py:130-146) flips the reward by
+  +-0.7 with the sign of an angle the two sides agree on to 1e-6 deg.  The TEACHER-FORCED leg
+  checks those very branches with no guard band.
 
 TEACHER-FORCED (the reference's reward / termination / landing functions evaluated in
 fp64 by the oracle on the stepper's OWN before/after state, widened from fp32):
@@ -51,15 +57,23 @@ RTOL = 1e-5
 SCALE = np.array([1500.0, 2000.0, 25.0, 200.0, 10.0, 10.0, 15.0, 10.0, 36000.0, 390000.0])
 FREE_REWARD_ATOL, FREE_REWARD_RTOL = 2e-2, 2e-3
 TF_REWARD_ATOL, TF_REWARD_RTOL = 2e-4, 1e-5
-GUARD = {"y": 1e-2, "v": 1e-3, "angle": 1e-3, "wrap": 1e-2, "bounds": 0.5}
+GUARD = {"y": 1e-2, "v": 1e-3, "angle": 1e-3, "wrap": 1e-2, "bounds": 0.5, "angle_sign": 5e-5}
+# Thresholds at which calculate_reward jumps (reward.py line -> decision variable -> threshold):
+#   :130      |angle_before| > 0.1, |omega_before| > 0.1   (dead band of the cold-gas term)
+#   :130-146  sign(angle_before)                            (correct_direction bonus vs penalty)
+#   :171-227  y_after > 0.1                                 (airborne terms; also the touchdown test)
+#   :205-219  |angle_after| > 10                            (tilt penalty 0.5 th -> th |a| / 90)
+#   :278      |angle_after| > 90                            (tip-over, -300)
+# (vy crossing 0 and |angle| crossing 5 are continuous: the terms they gate vanish there.)
+REWARD_STEPS = {"angle_before": (0.0, 0.1), "omega_before": (0.1,), "angle_after": (10.0, 90.0)}
 LAND_V = (30.0, 40.0, 100.0)
 LAND_A = (5.0, 8.0, 10.0)
 
 
-def _fresh_soa(states: np.ndarray, steps=0) -> np.ndarray:
+def _fresh_soa(states: np.ndarray, steps=0, fuel_unit=layout.DEFAULT_FUEL_UNIT) -> np.ndarray:
     s = np.asarray(states, np.float64)
     return layout.fresh_state_soa(s[:, 0], s[:, 1], s[:, 2], s[:, 3], s[:, 6], s[:, 7], s[:, 8],
-                                  s[:, 9], steps=steps)
+                                  s[:, 9], steps=steps, fuel_unit=fuel_unit)
 
 
 # ----------------------------------------------------------------------------------------
@@ -87,10 +101,11 @@ class HostEmuStepper:
         self.n = n
         self.params = params or load_params()
         self.dt = self.params.time_step
+        self.fuel_unit = layout.fuel_unit_for(self.params.reset_high[9])
         self.soa = np.zeros((10, n), np.float32)
 
     def inject_fresh(self, states: np.ndarray, mask=None, steps=0) -> None:
-        new = _fresh_soa(states, steps)
+        new = _fresh_soa(states, steps, self.fuel_unit)
         if mask is None:
             self.soa[:] = new
         else:
@@ -113,7 +128,7 @@ class HostEmuStepper:
         return obs, rew, term.astype(bool), trunc.astype(bool), land
 
     def view(self) -> dict:
-        return layout.reference_view(self.soa, self.dt)
+        return layout.reference_view(self.soa, self.dt, self.fuel_unit)
 
     def philox_reset(self, gid0: int, seed: int, epoch: int):
         obs = np.zeros((self.n, 8), np.float32)
@@ -144,7 +159,7 @@ class GpuStepper:
         self.dt = self.env.dt
 
     def inject_fresh(self, states: np.ndarray, mask=None, steps=0) -> None:
-        self.env.set_state(self.torch.from_numpy(_fresh_soa(states, steps)),
+        self.env.set_state(self.torch.from_numpy(_fresh_soa(states, steps, self.env.fuel_unit)),
                            None if mask is None else self.torch.from_numpy(np.asarray(mask, np.uint8)))
 
     def inject_soa(self, soa: np.ndarray) -> None:
@@ -174,6 +189,7 @@ class ParityReport:
     tf_steps: int = 0
     flag_guard_events: int = 0           # free-running disagreements inside a guard band
     wrap_guard_events: int = 0
+    reward_guard_events: int = 0         # steps whose free-running reward sits on a reward discontinuity
     flag_violations: list = field(default_factory=list)     # outside any guard band
     value_violations: list = field(default_factory=list)
     tf_violations: list = field(default_factory=list)       # teacher-forced: any disagreement
@@ -190,7 +206,8 @@ class ParityReport:
                 f"{self.episodes} episodes, landings(none,safe,good,ok,unsafe)={self.landing_counts.tolist()}; "
                 f"max err / tol: state[{errs}] obs={self.max_obs_err:.3f} free-reward="
                 f"{self.max_free_reward_err:.3f} tf-reward={self.max_tf_reward_err:.3f}; guard-band "
-                f"events: flags {self.flag_guard_events}, wraps {self.wrap_guard_events}; VIOLATIONS: "
+                f"events: flags {self.flag_guard_events}, wraps {self.wrap_guard_events}, reward steps "
+                f"{self.reward_guard_events}; VIOLATIONS: "
                 f"flags {len(self.flag_violations)}, values {len(self.value_violations)}, "
                 f"teacher-forced {len(self.tf_violations)}")
 
@@ -243,9 +260,12 @@ class LockstepChecker:
 
     # ---- free-running leg --------------------------------------------------------------------
     def compare(self, t, got_obs, got_rew, got_term, got_trunc, got_land, got_view,
-                ref_state, ref_obs, ref_rew, ref_term, ref_trunc, ref_landing, ref_y_before) -> None:
+                ref_state, ref_obs, ref_rew, ref_term, ref_trunc, ref_landing, ref_before) -> None:
+        """``ref_before`` [n,10]: the reference's state BEFORE this step (reference word order)."""
         rep = self.rep
         ref_state = np.asarray(ref_state, np.float64)
+        ref_before = np.asarray(ref_before, np.float64)
+        ref_y_before = ref_before[:, 1]
         x, y, vx, vy, ang = (ref_state[:, 0], ref_state[:, 1], ref_state[:, 2], ref_state[:, 3],
                              ref_state[:, 6])
         live = self.synced
@@ -307,6 +327,17 @@ class LockstepChecker:
             rtol = np.maximum(FREE_REWARD_ATOL, FREE_REWARD_RTOL * np.abs(ref_rew))
             rerr = np.abs(got_rew.astype(np.float64) - ref_rew) / rtol
             rerr = np.where(class_bad | ~np.isfinite(ref_rew), 0.0, rerr)
+            # reward discontinuities: the reference's decision variable inside a guard band
+            on_step = near_ground.copy()
+            ab, wb = np.abs(ref_before[:, 6]), np.abs(ref_before[:, 7])
+            for thr in REWARD_STEPS["angle_before"]:
+                on_step |= np.abs(ab - thr) < (GUARD["angle_sign"] if thr == 0.0 else GUARD["angle"])
+            for thr in REWARD_STEPS["omega_before"]:
+                on_step |= np.abs(wb - thr) < GUARD["angle"]
+            for thr in REWARD_STEPS["angle_after"]:
+                on_step |= np.abs(np.abs(ang) - thr) < GUARD["angle"]
+            rep.reward_guard_events += int((on_step[idx] & ~(ref_term[idx])).sum())
+            rerr = np.where(on_step & ~ref_term, 0.0, rerr)
             re_ = rerr[idx]
             rep.max_free_reward_err = max(rep.max_free_reward_err, float(re_.max()))
             for j in np.flatnonzero(re_ > 1.0):
@@ -331,7 +362,7 @@ def replay_golden_rollout(stepper, g: dict) -> ParityReport:
     assert stepper.n == E
     stepper.inject_fresh(g["init_state"])
     chk = LockstepChecker(E)
-    y_before = np.asarray(g["init_state"])[:, 1].copy()
+    ref_before = np.asarray(g["init_state"], np.float64).copy()
     before = stepper.view()
     for t in range(T):
         obs, rew, term, trunc, land = stepper.step(actions[t])
@@ -340,13 +371,13 @@ def replay_golden_rollout(stepper, g: dict) -> ParityReport:
         done = g["terminated"][t] | g["truncated"][t]
         ref_obs = np.where(done[:, None], g["terminal_obs"][t], g["obs"][t])
         chk.compare(t, obs, rew, term, trunc, land, after, g["state"][t], ref_obs, g["reward"][t],
-                    g["terminated"][t], g["truncated"][t], g["landing"][t], y_before)
-        y_before = g["state"][t][:, 1].copy()
+                    g["terminated"][t], g["truncated"][t], g["landing"][t], ref_before)
+        ref_before = np.asarray(g["state"][t], np.float64).copy()
         before = after
         if done.any():
             stepper.inject_fresh(g["reset_state"][t], mask=done)
             chk.resync(done)
-            y_before[done] = g["reset_state"][t][done, 1]
+            ref_before[done] = g["reset_state"][t][done]
             before = stepper.view()
     return chk.rep
 
@@ -358,15 +389,15 @@ def replay_edge_cases(stepper, g: dict) -> ParityReport:
     assert stepper.n == n
     stepper.inject_fresh(g["init_state"], steps=g["init_step"])
     chk = LockstepChecker(n)
-    y_before = g["init_state"][:, 1].copy()
+    ref_before = np.asarray(g["init_state"], np.float64).copy()
     before = stepper.view()
     for k in range(2):
         obs, rew, term, trunc, land = stepper.step(g["actions"])
         after = stepper.view()
         chk.teacher_forced(k, before, after, g["actions"], rew, term, trunc, land)
         chk.compare(k, obs, rew, term, trunc, land, after, g["state"][k], g["obs"][k], g["reward"][k],
-                    g["terminated"][k], g["truncated"][k], g["landing"][k], y_before)
-        y_before = g["state"][k][:, 1].copy()
+                    g["terminated"][k], g["truncated"][k], g["landing"][k], ref_before)
+        ref_before = np.asarray(g["state"][k], np.float64).copy()
         before = after
     return chk.rep
 
@@ -396,6 +427,34 @@ def braking_actions(t, oracle, rng):
     return a.astype(np.float32)
 
 
+def hover_actions(t, oracle, rng):
+    """Keeps every rocket aloft to the 1000-step limit (lander.py:237-241): descend to ~300 m, hold
+    it with a throttle loop, PD attitude loop, 2 % action noise.  The worst case for ACCUMULATED
+    error: the episode is ten times longer than a random-action one."""
+    r = oracle.rockets
+    y, vy, a, w = r["y"], r["vy"], r["angle"], r["ang_vel"]
+    m = r["dry_mass"] + r["fuel"]
+    tv = np.where(y > 400, -40.0, np.clip(-(y - 300) * 0.2, -20, 20))
+    th = (9.81 * m / 1e7) * (1 + np.clip((tv - vy) * 0.3, -1, 6))
+    cg = np.clip(-(a * 0.9 + w * 1.6), -1, 1)
+    return (np.stack([th, cg], 1) + rng.normal(0, 0.02, (oracle.n, 2))).astype(np.float32)
+
+
+def tilted_cruise_actions(t, oracle, rng):
+    """Hover while HOLDING a per-rocket tilt of up to +-12 deg (thrust has a large horizontal
+    component for the whole episode, so vx and x integrate every error of the angle and of T/m),
+    with a slow roll reversal; rockets drift sideways at tens of m/s."""
+    r = oracle.rockets
+    y, vy, a, w = r["y"], r["vy"], r["angle"], r["ang_vel"]
+    m = r["dry_mass"] + r["fuel"]
+    ids = np.arange(oracle.n)
+    target = 12.0 * np.sin(0.37 * ids + 1.0) * np.cos(2.0 * np.pi * t / 400.0)
+    tv = np.where(y > 600, -30.0, np.clip(-(y - 500) * 0.2, -20, 20))
+    th = (9.81 * m / 1e7) * (1 + np.clip((tv - vy) * 0.3, -1, 6)) / np.maximum(np.cos(np.deg2rad(a)), 0.5)
+    cg = np.clip(-((a - target) * 0.9 + w * 1.6), -1, 1)
+    return (np.stack([th, cg], 1) + rng.normal(0, 0.02, (oracle.n, 2))).astype(np.float32)
+
+
 def lockstep_vs_oracle(stepper, oracle, steps: int, seed: int = 0, action_fn=random_actions,
                        view_every: int = 1) -> ParityReport:
     """Free-running comparison against the C oracle (oracle.c_oracle.BatchOracle): both start
@@ -410,13 +469,13 @@ def lockstep_vs_oracle(stepper, oracle, steps: int, seed: int = 0, action_fn=ran
     before = stepper.view()
     for t in range(steps):
         a = action_fn(t, oracle, rng)
-        y_before = oracle.rockets["y"].copy()
+        ref_before = oracle.state()
         obs, rew, term, trunc, land = stepper.step(a)
         oobs, orew, oterm, otrunc, oland = oracle.step(a)
         after = stepper.view()
         chk.teacher_forced(t, before, after, a, rew, term, trunc, land)
         chk.compare(t, obs, rew, term, trunc, land, after, oracle.state(), oobs, orew, oterm,
-                    otrunc, oland, y_before)
+                    otrunc, oland, ref_before)
         before = after
         done = oterm | otrunc
         if done.any():

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert sorted(_lib.EXPORTS) == declared
-    assert lib.rl_abi_version() == 1
+    assert lib.rl_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_header_constants_match_python_layout():
@@ -44,6 +44,18 @@ def test_header_constants_match_python_layout():
         assert val(name) == idx
     assert val("RL_META_STEP_MASK") == layout.META_STEP_MASK
     assert val("RL_META_FRESH") == layout.META_FRESH
+    assert val("RL_META_DLO_SHIFT") == layout.META_DLO_SHIFT
+    assert val("RL_META_WRAP_SHIFT") == layout.META_WRAP_SHIFT
+    assert "RL_ANGLE_UNITS_PER_DEG (4294967296.0 / 360.0)" in text and layout.ANGLE_UNITS_PER_DEG == 4294967296.0 / 360.0
+    assert "RL_DELTA_UNITS_PER_M 8388608.0" in text and layout.DELTA_UNITS_PER_M == 8388608.0
+    # the fixed-point fuel unit: library and Python helper derive the same power of two
+    lib = _lib.load()
+    p = load_params()
+    assert lib.rl_fuel_unit_for(C.byref(p)) == layout.fuel_unit_for(p.reset_high[9]) == layout.DEFAULT_FUEL_UNIT
+    for hi in (0.5, 1.0, 3.0, 524287.0, 524288.0, 1.0e9):
+        p.reset_high[9] = hi
+        u = lib.rl_fuel_unit_for(C.byref(p))
+        assert u == layout.fuel_unit_for(hi) and hi / u < 2.0 ** 31 <= 4.0 * max(hi, 0.5) / u
     from rocket_landing_rl_b200.stats import SLOTS, STATS_WORDS
     assert val("RL_STATS_WORDS") == STATS_WORDS
     for i, slot in enumerate(SLOTS):
@@ -131,6 +143,22 @@ def test_fresh_state_round_trip():
     assert v["fresh"].all() and v["steps"].tolist() == [0, 7] and v["wraps"].tolist() == [0, 0]
     np.testing.assert_allclose(v["vy"], [-160.0, -170.0])
     np.testing.assert_allclose(v["ang_vel"], [1.0, -1.0])
+    np.testing.assert_allclose(v["angle"], [5.0, -5.0], atol=1e-7)
+    np.testing.assert_allclose(v["fuel"], [4e5, 3.9e5], atol=1e-4)
+
+
+def test_angle_delta_keeps_32_bits():
+    """The carried angle delta is fp32 + 8 low-order bits in the meta word (layout.split / join,
+    csrc/rl_device.cuh dtheta_split / dtheta_join): relative error <= 2^-32 (2^-31 for the 0.4 % of
+    values whose low part saturates at +127)."""
+    rng = np.random.default_rng(0)
+    v = np.concatenate([rng.uniform(-30, 30, 5000), rng.uniform(-1e-3, 1e-3, 5000), [0.0, 1.0, -1.0, 2.0 ** -140]])
+    hi, lo = layout.split_angle_delta(v)
+    assert lo.min() >= -128 and lo.max() <= 127
+    back = layout.join_angle_delta(hi, lo)
+    rel = np.abs(back - v) / np.maximum(np.abs(v), 1e-300)
+    assert rel.max() <= 2.0 ** -31 and np.mean(rel > 2.0 ** -32) < 0.01
+    assert np.abs(hi.astype(np.float64) - v).max() > 100 * np.abs(back - v).max()
 
 
 def test_mid_episode_state_from_reference_dicts(golden_dir):

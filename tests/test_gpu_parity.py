@@ -83,6 +83,33 @@ def test_controlled_descents_reach_every_landing_branch(torch):
     assert rep.landing_counts[1] > 100 and rep.landing_counts[2] > 10
 
 
+# ---- long horizon: episodes flown to the 1000-step limit (lander.py:237-241), word by word -------
+@pytest.mark.parametrize("action_fn", [parity.hover_actions, parity.tilted_cruise_actions])
+def test_thousand_step_episodes_against_oracle(torch, action_fn):
+    """north_star: trajectories "within a stated fp32-vs-fp64 tolerance (e.g. rel 1e-5 per step over
+    1000 steps)".  512 rockets kept aloft for the full 1000 steps, free-running against the fp64 C
+    oracle, RTOL = 1e-5 on every state / observation word of every step."""
+    n = 512
+    rep = parity.lockstep_vs_oracle(parity.GpuStepper(n), c_oracle.BatchOracle(n), 1000, seed=5,
+                                    action_fn=action_fn)
+    print(rep.summary())
+    rep.assert_ok(max_guard_events=0)
+    assert rep.steps_compared == n * 1000 and rep.episodes == n
+    assert rep.max_state_err.max() < 0.8 and rep.max_obs_err < 0.8
+
+
+@pytest.mark.parametrize("name", ["ref_long_agent_v3.npz", "ref_long_hover.npz"])
+def test_thousand_step_reference_trajectories(torch, golden_dir, name):
+    """Trajectories of the live reference flown by its own shipped v3 agent and by a hover
+    controller (tests/golden/make_long_horizon.py), replayed through the CUDA path."""
+    g = dict(np.load(os.path.join(golden_dir, name)))
+    rep = parity.replay_golden_rollout(parity.GpuStepper(8), g)
+    print(rep.summary())
+    rep.assert_ok(max_guard_events=1)
+    assert rep.steps_compared >= 8 * 1100 - 2
+    assert rep.max_state_err.max() < 0.8 and rep.max_obs_err < 0.8
+
+
 def test_gpu_and_host_build_of_the_device_math_agree(torch):
     """Same source (rl_device.cuh), two compilers: the Philox reset must be bit-identical,
     a step must agree to rounding."""
@@ -345,7 +372,7 @@ def test_full_size_properties_16m_rockets(torch, monkeypatch):
     assert bool(((obs >= lo) & (obs <= hi)).all())
     gen = torch.Generator(device="cuda").manual_seed(0)
     a = _rand_actions(torch, n, gen)
-    fuel_prev = env.get_state()[7].clone()
+    fuel_prev = env.get_state()[7].view(torch.int32).clone()       # fixed-point fuel word
     T = 130
     checksum = torch.zeros((), device="cuda", dtype=torch.int64)
     done_total = 0
@@ -356,11 +383,14 @@ def test_full_size_properties_16m_rockets(torch, monkeypatch):
         if t % 16 == 0:
             assert bool(((obs >= lo) & (obs <= hi)).all())           # observation clipping (lander.py:149)
             st = env.get_state()
-            assert bool(((st[2] >= -180.0) & (st[2] < 180.0)).all())   # angle normalisation (engine.py:230)
-            fuel = st[7]
+            # angle normalisation (engine.py:230): the int32 angle word spans exactly [-180, 180), so
+            # what remains to check is the value the observation reports
+            assert bool(((obs[:, 6] >= -15.0) & (obs[:, 6] <= 15.0)).all())
+            fuel = st[7].view(torch.int32)
             assert bool(((fuel <= fuel_prev) | done).all()) or t == 0   # fuel only burns within an episode
+            assert bool((fuel >= 0).all())
             assert bool(torch.isfinite(rew).all())
-        fuel_prev = env.get_state()[7].clone() if (t + 1) % 16 == 0 else fuel_prev
+        fuel_prev = env.get_state()[7].view(torch.int32).clone() if (t + 1) % 16 == 0 else fuel_prev
         checksum += obs.view(torch.int32).sum(dtype=torch.int64) + rew.view(torch.int32).sum(dtype=torch.int64)
     stats = env.stats()
     assert stats.env_steps == n * T and stats.episodes == done_total
