@@ -14,8 +14,12 @@ vector every --stats-interval steps and at the end of the timed region.
 Prints ONE JSON line (rank 0).  ``value`` = env-steps/s with everything resident in HBM;
 ``e2e`` = the same metric through the host-buffer VecEnv call (pinned numpy in/out, H2D and
 D2H copies inside the timed region); ``roofline`` = algorithmic HBM bytes of the step kernel /
-its CUDA-event duration against the measured copy bandwidth; ``cpu_baseline`` = the oracle
-port on this box's host cores (N = 1 only).  ``--impl reference`` times the oracle port only.
+its CUDA-event duration against the measured copy bandwidth; ``cpu_baseline`` = the reference's
+own environment (byte-compiled into ``oracle/_ref`` by ``oracle/make_ref.py``) on all host cores of
+this box (N = 1 only), with the C port's and the Python oracle's rates beside it; ``extra`` = the
+other BASELINE.json configurations measured after the headline (K = 8 fused substeps at 16 Mi
+rockets, device-resident PPO rollout collection at 1 Mi rockets).  ``--impl reference`` times the
+reference's environment only.
 """
 from __future__ import annotations
 
@@ -93,9 +97,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_port_rate(seconds_budget: float = 12.0, threads: int | None = None) -> dict:
-    """The oracle port (oracle/rocket_oracle.c: scalar fp64 restatement of the reference's step,
-    random actions, auto-reset) on all host cores, on a bounded sample of the workload."""
+REF_STEPS_PER_BENCH_STEP = 1024     # env steps each reference process runs per bench "step"
+
+
+def workload_config(args, world: int) -> dict:
+    """The `config` object: identical for the CUDA arm and the reference arm."""
+    per_launch = BYTES_PER_ENV_STEP * (args.rockets // world) / 1e9
+    return {"workload": f"{args.rockets} rockets total sharded over {world} GPU(s), random actions, auto-reset in steady "
+                        f"state, {args.substeps} substep(s) per launch, episode-statistics all-reduce every "
+                        f"{args.stats_interval} steps",
+            "l2": "inputs larger than L2: %.1f GB of state+action+output per launch per GPU vs 126 MB" % per_launch}
+
+
+def cpu_port_rate(seconds_budget: float = 6.0, threads: int | None = None) -> dict:
+    """The C port (oracle/rocket_oracle.c: scalar fp64 restatement of the reference's step, random
+    actions, auto-reset) on all host cores, on a bounded sample of the workload."""
     from oracle import c_oracle
     threads = threads or os.cpu_count() or 1
     per_thread = 4096
@@ -107,9 +123,9 @@ def cpu_port_rate(seconds_budget: float = 12.0, threads: int | None = None) -> d
                       f"C fp64 port of the reference step on {threads} host threads ({out['seconds']:.1f} s)"}
 
 
-def python_port_rate(steps: int = 20000) -> float:
-    """Single-core rate of the Python oracle (bit-identical restatement of the reference's
-    Python; the reference itself measured 14.3 k steps/s/core in the survey container)."""
+def python_oracle_rate(steps: int = 5000) -> float:
+    """Single-core rate of the Python ORACLE (oracle/rocket_oracle.py, a restatement -- NOT the
+    reference; the reference itself is `cpu_baseline.value / cores`)."""
     import numpy as np
     from oracle import rocket_oracle as ro
     env = ro.OracleEnv()
@@ -123,32 +139,136 @@ def python_port_rate(steps: int = 20000) -> float:
     return steps / (time.perf_counter() - t0)
 
 
+def reference_available() -> bool:
+    from oracle.ref_loader import reference_root
+    return reference_root(allow_compiled=True) is not None
+
+
+def cpu_baseline(seconds: float = 10.0) -> dict:
+    """The reference's own RocketLandingEnv on every host core of this box (kind "reference"), or,
+    where neither /root/reference nor oracle/_ref exists, the C port (kind "port")."""
+    from oracle import c_oracle
+    c_oracle.build()
+    port = cpu_port_rate()
+    extra = {"c_port_steps_per_s": port["value"], "c_port_threads": port["cores"],
+             "python_oracle_steps_per_s_1core": python_oracle_rate()}
+    if not reference_available():
+        port.update(extra)
+        return port
+    from oracle import ref_timing
+    r = ref_timing.time_reference(seconds=seconds)
+    out = {"value": r["steps_per_s"], "unit": UNIT, "cores": r["processes"], "kind": "reference",
+           "sample": f"{r['processes']} processes x one unmodified RocketLandingEnv (backend/envs/lander.py, from "
+                     f"{os.path.relpath(r['root'], ROOT) if r['root'].startswith(ROOT) else r['root']}), random actions, reset on "
+                     f"done, {r['steps']} env steps in {r['seconds']:.1f} s after a 4000-step warm-up each",
+           "steps_per_s_per_core": r["steps_per_s_per_core"], "cpu": r["cpu"]}
+    out.update(extra)
+    return out
+
+
 def run_reference(args) -> None:
+    """`--impl reference`: the reference's own CPU implementation of the path on all host cores.
+    One bench "step" = REF_STEPS_PER_BENCH_STEP env steps in each of P processes (a P x 1024-rocket
+    sample of the benchmark's batch; the reference has no batch dimension)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
     from oracle import c_oracle
     c_oracle.build()
-    sample = 32768 * threads                      # rockets per step: bounded sample of the 64 Mi workload
-    per_thread = sample // threads
-    if args.warmup > 0:
-        c_oracle.rollout_random(per_thread, args.warmup, threads, seed=1)
-    out = c_oracle.rollout_random(per_thread, args.steps, threads, seed=2)
-    value = out["steps_per_s"]
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    S = REF_STEPS_PER_BENCH_STEP
+    if reference_available():
+        from oracle import ref_timing
+        r = ref_timing.time_reference(timed_steps=args.steps * S, warm_steps=max(args.warmup, 1) * S)
+        value, seconds, cores, kind = r["steps_per_s"], r["seconds"], r["processes"], "reference"
+        sample = (f"{cores} processes x one unmodified RocketLandingEnv x {S} env steps per bench step "
+                  f"({r['steps']} env steps in {seconds:.2f} s), random actions, reset on done; {r['cpu']}")
+        dtype = "f64"
+    else:
+        threads = os.cpu_count() or 1
+        if args.warmup > 0:
+            c_oracle.rollout_random(S, args.warmup, threads, seed=1)
+        out = c_oracle.rollout_random(S, args.steps, threads, seed=2)
+        value, seconds, cores, kind = out["steps_per_s"], out["seconds"], threads, "port"
+        sample = f"{S * threads} rockets x {args.steps} steps on {threads} host threads, C fp64 port (oracle/rocket_oracle.c)"
+        dtype = "f64"
+    port = cpu_port_rate(3.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * out["seconds"] / max(args.steps, 1),
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"64Mi rockets, random actions, auto-reset, 1 substep (timed on a {sample}-rocket sample per step)"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{sample} rockets x {args.steps} steps on {threads} host threads, C fp64 port "
-                                   f"of the reference's Python step (oracle/rocket_oracle.c)",
-                         "python_port_steps_per_s_1core": python_port_rate(5000)},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "c_port_steps_per_s": port["value"], "c_port_threads": port["cores"],
+                         "python_oracle_steps_per_s_1core": python_oracle_rate()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def measure_extras(torch, dev) -> dict:
+    """The other BASELINE.json configurations, after the headline (N = 1 only):
+    configs[2] 16 Mi rockets with K = 8 fused substeps per launch (SM-issue-bound) and
+    configs[4] device-resident PPO rollout collection at 1 Mi rockets (env -> VecNormalize -> fused
+    tcgen05 policy + value nets -> [T,N] buffers -> GAE)."""
+    from rocket_landing_rl_b200 import (ActorCriticMLP, DeviceRolloutBuffer, DeviceVecNormalize, FusedActorCritic,
+                                        RocketLandingVecEnv, collect_rollout)
+    out = {}
+    n, K = 16 * 1024 * 1024, 8
+    env = RocketLandingVecEnv(n, device=dev, seed=0, substeps=K)
+    env.reset()
+    gen = torch.Generator(device=dev).manual_seed(7)
+    acts = []
+    for _ in range(4):
+        a = torch.rand((n, 2), device=dev, generator=gen)
+        a[:, 1].mul_(2.0).sub_(1.0)
+        acts.append(a)
+    for t in range(260):                                   # 2080 env steps: episodes desynchronised
+        env.step(acts[t % 4])
+    env.stats(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    launches = 40
+    e0.record()
+    for t in range(launches):
+        env.step(acts[t % 4])
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    st = env.stats()
+    out["k8_16Mi"] = {"env_steps_per_s": st.env_steps / (ms * 1e-3), "ms_per_launch": ms / launches, "launches": launches,
+                      "rockets": n, "substeps": K, "bound": "sm issue rate",
+                      "issue_active_source": "profiles/ (ncu smsp__issue_active of the K = 8 capture, see profiles/README.md)"}
+    env.close()
+    del acts
+    torch.cuda.empty_cache()
+
+    n, T = 1 << 20, 32
+    raw = RocketLandingVecEnv(n, device=dev, seed=0)
+    venv = DeviceVecNormalize(raw, gamma=0.99)
+    policy = FusedActorCritic(ActorCriticMLP().to(dev))
+    buf = DeviceRolloutBuffer(T, n, dev)
+    state = {"obs": venv.reset(), "starts": torch.ones(n, dtype=torch.bool, device=dev)}
+
+    def one_pass():
+        state["obs"], state["starts"] = collect_rollout(venv, policy, buf, state["obs"], state["starts"])
+
+    for _ in range(4):
+        one_pass()
+    torch.cuda.synchronize(dev)
+    passes = 3
+    e0.record()
+    for _ in range(passes):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / passes
+    out["rollout_1Mi"] = {"env_steps_per_s": n * T / (ms * 1e-3), "ms_per_collection_pass": ms, "rockets": n, "n_steps": T,
+                          "pipeline": "rl_step -> rl_vecnorm_step -> fused tcgen05 policy + value nets (rl_policy.cu) -> "
+                                      "[T,N] device buffers -> rl_gae"}
+    raw.close()
+    return out
 
 
 def main() -> None:
@@ -165,7 +285,8 @@ def main() -> None:
                          "(steady state: ~1/113 of the rockets reset per step, as in a long rollout)")
     ap.add_argument("--cooldown", type=float, default=0.0,
                     help="experiment only: idle this many seconds before the timed region (lets the board "
-                         "leave its power cap) and report the per-step times of the first and last steps")
+                         "leave its power cap)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the K = 8 and rollout-collection measurements")
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -176,7 +297,7 @@ def main() -> None:
 
     import torch
     import torch.distributed as dist
-    from rocket_landing_rl_b200 import RocketLandingSB3VecEnv, RocketLandingVecEnv, shard_range
+    from rocket_landing_rl_b200 import EpisodeStats, RocketLandingSB3VecEnv, RocketLandingVecEnv, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,28 +343,28 @@ def main() -> None:
         time.sleep(args.cooldown)
     if rank == 0:
         sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # the step kernel's own duration (roofline): an event pair around every 8th launch -- a pair
-    # around EVERY launch costs ~5 us of idle GPU per step, 3 % of a 0.18 ms launch
-    sampled = [t for t in range(args.steps) if t % 8 == 0]
-    k0 = {t: torch.cuda.Event(enable_timing=True) for t in sampled}
-    k1 = {t: torch.cuda.Event(enable_timing=True) for t in sampled}
+    ev0, ev1, evk = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    # Everything inside the timed region is ENQUEUED: K launches of the step kernel back to back on one
+    # stream, the statistics kernel + 128-byte all-reduce (NCCL) every --stats-interval steps and once
+    # at the end; the host reads the reduced statistics back after the closing event.
     ev0.record()
     for t in range(args.steps):
-        if t in k0:
-            k0[t].record()
         env.step(actions[t % n_sets])
-        if t in k1:
-            k1[t].record()
-        if (t + 1) % args.stats_interval == 0:
-            env.stats()                              # 128-byte all-reduce (NCCL)
-    final = env.stats()
+        if (t + 1) % args.stats_interval == 0 and t + 1 < args.steps:
+            env.stats_async()
+    evk.record()                                     # the K step-kernel launches end here
+    final_vec = env.stats_async()                    # rl_stats + all-reduce, enqueued
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else {}
+    final = EpisodeStats.from_vector(final_vec.cpu().tolist())
     elapsed_ms = ev0.elapsed_time(ev1)
-    per_step = [k0[t].elapsed_time(k1[t]) for t in sampled]
-    kernel_ms = sum(per_step) / max(len(per_step), 1)
+    # the step kernel's own average launch duration (roofline): the launches run back to back on the
+    # stream, so it is the span of the K launches / K -- no event pairs between launches (a pair around
+    # a launch leaves the GPU idle for ~5 us); the in-loop statistics kernels (one per
+    # --stats-interval steps, ~10 us) are inside this span.
+    kernel_ms = ev0.elapsed_time(evk) / max(args.steps, 1)
+    per_step = []
     launches = env.launch_count - launches0
     t_all = torch.tensor([elapsed_ms, kernel_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -307,25 +428,16 @@ def main() -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warmup, "ms_per_step": elapsed_ms / max(args.steps, 1), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.rockets} rockets total ({count} on this rank), random actions "
-                                   f"(4 pre-generated sets cycled), auto-reset (steady state after {args.spinup} "
-                                   f"untimed spin-up steps), {args.substeps} substep(s) per launch, "
-                                   f"stats all-reduce every {args.stats_interval} steps",
-                       "l2": "inputs larger than L2: %.1f GB of state+action+output per launch vs 126 MB"
-                             % (BYTES_PER_ENV_STEP * count / 1e9)},
+            "config": workload_config(args, world),
+            "setup": f"{count} rockets on this rank; 4 pre-generated action sets cycled; {args.spinup} untimed spin-up "
+                     f"steps desynchronise the episodes before the warm-up",
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "episodes": final.episodes, "mean_episode_length": final.mean_length,
         }
-        if args.cooldown > 0:
-            m = max(1, min(10, len(per_step) // 2))
-            line["cooldown"] = {"seconds": args.cooldown, "first_steps_ms": sum(per_step[:m]) / m,
-                                "last_steps_ms": sum(per_step[-m:]) / m}
+        if world == 1 and not args.no_extras:
+            line["extra"] = measure_extras(torch, dev)
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import c_oracle
-            c_oracle.build()
-            cb = cpu_port_rate()
-            cb["python_port_steps_per_s_1core"] = python_port_rate(5000)
-            line["cpu_baseline"] = cb
+            line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -19,8 +19,13 @@
  *    take HOST pointers and do the copies themselves.
  *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only
  *    ENQUEUE work on it and never synchronise (rl_*_host excepted); rl_step allocates
- *    nothing and is CUDA-graph capturable.  One handle per (device, stream); a handle is
- *    not thread-safe.
+ *    nothing and is CUDA-graph capturable.  A handle is not thread-safe.  The rl_*_host calls
+ *    (and rl_get_epoch / rl_set_epoch) run on private streams of the handle; they first wait
+ *    for everything the handle's device-API calls have enqueued on the stream of the LAST such
+ *    call, and return only when their own work is complete -- so the two families may be mixed
+ *    on one handle without explicit synchronisation as long as the device-API calls of a
+ *    handle use one stream at a time (work left on an EARLIER stream is the caller's to order;
+ *    a stream under CUDA-graph capture cannot be waited for).
  *  - layouts: actions [N,2] f32 row-major (throttle, cold gas); obs [N,8] f32 row-major
  *    (x, y, vx, vy, ax, ay, angle, angular velocity; lander.py:129-141); reward [N] f32;
  *    terminated / truncated [N] u8 (0/1).
@@ -42,12 +47,12 @@ extern "C" {
 #define RL_E_NOMEM (-3)     /* allocation failed                   */
 
 /* Words of the public state format used by rl_set_state / rl_get_state: 32-bit words [10][N]
- * (structure of arrays, word-major), passed as float32 buffers.  They are the kernel's own
- * persistent words, so a get -> set round trip is lossless.  Words that INTEGRATE over an
- * episode are 32-bit FIXED POINT (raw int32 / uint32 bits inside the float32 buffer): an fp32
- * rounding error in them would persist for the rest of the episode, and the reference runs
- * 1000-step episodes in fp64 (DESIGN.md "Long-horizon accuracy").  rocket-landing-rl_b200/layout.py
- * converts to and from the reference's Rocket.state words. */
+ * (structure of arrays, word-major) in a uint32 buffer; "f32" words hold IEEE-754 bits.  They are
+ * the kernel's own persistent words, so a get -> set round trip is lossless.  Words that INTEGRATE
+ * over an episode are 32-bit FIXED POINT: an fp32 rounding error in them would persist for the
+ * rest of the episode, and the reference runs 1000-step episodes in fp64 (DESIGN.md "Long-horizon
+ * accuracy").  rocket-landing-rl_b200/layout.py converts to and from the reference's Rocket.state
+ * words. */
 #define RL_STATE_WORDS 10
 #define RL_W_X 0        /* f32  m                                                              */
 #define RL_W_Y 1        /* f32  m                                                              */
@@ -179,8 +184,9 @@ int rl_uses_folded_constants(const RlEnv *env);
 /* Launch epoch: counts rl_reset / rl_step launches and is part of the Philox counter.  It
  * lives in device memory and is advanced by the kernels themselves, so a CUDA-graph replay
  * of rl_step advances the reset stream like an ordinary call.  Saving it with the state
- * buffer makes a checkpoint resume bit-identically.  Both calls synchronise the device. */
-uint64_t rl_get_epoch(const RlEnv *env);
+ * buffer makes a checkpoint resume bit-identically.  Both calls wait for the work this handle has
+ * enqueued (see "Conventions"), not for the whole device. */
+uint64_t rl_get_epoch(RlEnv *env);
 int rl_set_epoch(RlEnv *env, uint64_t epoch);
 
 /* Resample the initial state of every rocket (mask == NULL) or of the rockets with
@@ -201,16 +207,20 @@ int rl_reset(RlEnv *env, const uint8_t *mask, float *obs, void *stream);
  *   landing        [N] i8,  nullable:   landing class of this step for EVERY rocket: 0 = no
  *                                       touchdown, 1 safe, 2 good, 3 ok, 4 unsafe
  *                                       (evaluate_landing, utils.py:1; codes of protocol.py:31-41)
+ *   raw_accel      [N,2] f32, nullable: the UNCLIPPED accelerations (ax, ay) of this step for
+ *                                       every rocket -- what info["raw_state"] carries
+ *                                       (lander.py:157-166); the observation clips them to +-5
  * Replaces: RocketLandingEnv.step (lander.py:188) x n_envs. */
 int rl_step(RlEnv *env, const float *actions, float *obs, float *reward, uint8_t *terminated,
             uint8_t *truncated, float *terminal_obs, float *episode_return,
-            int32_t *episode_length, int8_t *landing, int substeps, int auto_reset, void *stream);
+            int32_t *episode_length, int8_t *landing, float *raw_accel, int substeps, int auto_reset,
+            void *stream);
 
-/* Inject / read back the persistent state in the public format (float32 [10][N], RL_W_*).
+/* Inject / read back the persistent state in the public format (uint32 [10][N], RL_W_*).
  * rl_set_state writes only rockets with mask[i] != 0 (mask == NULL: all).  Used for
  * deterministic replay against the reference and for checkpointing. */
-int rl_set_state(RlEnv *env, const float *state_soa, const uint8_t *mask, void *stream);
-int rl_get_state(RlEnv *env, float *state_soa, void *stream);
+int rl_set_state(RlEnv *env, const uint32_t *state_words, const uint8_t *mask, void *stream);
+int rl_get_state(RlEnv *env, uint32_t *state_words, void *stream);
 
 /* Copy the float64[16] statistics vector (RL_S_*) to the DEVICE buffer `out16` (ready for an
  * NCCL all-reduce on the same stream); reset_after != 0 zeroes the accumulators afterwards. */
@@ -221,11 +231,11 @@ int rl_stats(RlEnv *env, double *out16, int reset_after, void *stream);
  * memory (pinned memory makes the copies faster).  Nullable outputs as in rl_step. */
 int rl_step_host(RlEnv *env, const float *actions, float *obs, float *reward,
                  uint8_t *terminated, uint8_t *truncated, float *terminal_obs,
-                 float *episode_return, int32_t *episode_length, int8_t *landing, int substeps,
-                 int auto_reset);
+                 float *episode_return, int32_t *episode_length, int8_t *landing, float *raw_accel,
+                 int substeps, int auto_reset);
 int rl_reset_host(RlEnv *env, float *obs);
-/* rl_get_state into HOST memory (float32 [10][N]); synchronous. */
-int rl_get_state_host(RlEnv *env, float *state_soa);
+/* rl_get_state into HOST memory (uint32 [10][N]); synchronous. */
+int rl_get_state_host(RlEnv *env, uint32_t *state_words);
 
 /* Simulation mode -- the reference's second caller of the step, the UI loop: one tick of
  * SimulationController.step (backend/simulation/controller.py:223-269) over RocketControls.step
@@ -300,17 +310,20 @@ int rl_gae(const float *rewards, const float *values, const uint8_t *episode_sta
  * epilogue (what OnPolicyAlgorithm.collect_rollouts does around policy.forward): actions[n][2] =
  * mean + exp(log_std) eps, eps ~ N(0, 1) (unclipped: what the rollout buffer stores); clipped[n][2]
  * = actions clipped to the Box [low2, high2] (what env.step receives); log_prob[n]; mean[n][2]
- * optional (nullable).  eps is Philox4x32-10 keyed by `seed` at counter (row, draw) + Box-Muller:
- * pass a different `draw` on every call.  log_std is a DEVICE pointer to 2 floats; low2 / high2 are
- * HOST pointers to 2 floats. */
+ * optional (nullable).  eps is Philox4x32-10 at counter (row_offset + row, draw) + Box-Muller, keyed by
+ * `seed` xor a domain tag -- so the stream is independent of the environment's reset stream (key =
+ * seed, counter = (global id, epoch)) even for equal seeds: pass a different `draw` on every call and
+ * the shard's global id offset (rl_create's env_id_offset) as `row_offset`, so that ranks sharing a
+ * seed draw different noise.  log_std is a DEVICE pointer to 2 floats; low2 / high2 are HOST
+ * pointers to 2 floats. */
 #define RL_MLP_HIDDEN 256
 #define RL_MLP_BLOB_BYTES 143376
 const char *rl_policy_last_error(void);
 int64_t rl_mlp_blob_bytes(void);
 int rl_mlp_forward(const void *blob, const float *obs, float *out, int64_t n, int out_dim, void *stream);
 int rl_policy_sample(const void *blob, const float *obs, const float *log_std, uint64_t seed, uint64_t draw,
-                     const float *low2, const float *high2, float *actions, float *clipped, float *log_prob,
-                     float *mean, int64_t n, void *stream);
+                     int64_t row_offset, const float *low2, const float *high2, float *actions, float *clipped,
+                     float *log_prob, float *mean, int64_t n, void *stream);
 
 #ifdef __cplusplus
 }

@@ -33,10 +33,42 @@ import numpy as np
 _REF_CACHE = None
 
 
-def reference_root() -> str | None:
+_ARCHIVE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_backend.bin")
+_UNPACKED = None
+
+
+def _unpack_compiled() -> str | None:
+    """oracle/_ref/reference_backend.bin (byte-compiled by oracle/make_ref.py) unpacked into a scratch
+    directory, if it exists and was built by THIS interpreter version."""
+    global _UNPACKED
+    if _UNPACKED is not None:
+        return _UNPACKED or None
+    import importlib.util
+    import json
+    import tempfile
+    import zipfile
+    _UNPACKED = ""
+    try:
+        with zipfile.ZipFile(_ARCHIVE) as z:
+            if json.loads(z.read("BUILD.json"))["magic"] != importlib.util.MAGIC_NUMBER.hex():
+                return None
+            dest = tempfile.mkdtemp(prefix="rocket_ref_compiled_")
+            z.extractall(dest)
+        _UNPACKED = dest
+    except Exception:   # noqa: BLE001
+        return None
+    return _UNPACKED
+
+
+def reference_root(allow_compiled: bool = False) -> str | None:
+    """The reference checkout ($ROCKET_REF or /root/reference); with ``allow_compiled`` also the
+    byte-compiled copy in ``oracle/_ref`` (the only form that exists on the GPU box; used for TIMING
+    the reference there, never for parity -- the goldens under tests/golden are the parity anchor)."""
     for cand in (os.environ.get("ROCKET_REF"), "/root/reference"):
         if cand and os.path.isfile(os.path.join(cand, "backend", "envs", "lander.py")):
             return cand
+    if allow_compiled:
+        return _unpack_compiled()
     return None
 
 
@@ -112,13 +144,15 @@ def _install_stubs() -> None:
         _mod("stable_baselines3", PPO=_Dummy, common=common)
 
 
-def load_reference() -> SimpleNamespace:
+def load_reference(allow_compiled: bool = False, prefer_compiled: bool = False) -> SimpleNamespace:
     """Return the reference's own modules (``RocketLandingEnv``, ``Rocket``,
     ``PhysicsEngine``, ``calculate_reward``, ``evaluate_landing``, ``Config``)."""
     global _REF_CACHE
     if _REF_CACHE is not None:
         return _REF_CACHE
-    root = reference_root()
+    root = reference_root(allow_compiled)
+    if prefer_compiled and _unpack_compiled():
+        root = _unpack_compiled()
     if root is None:
         raise RuntimeError("reference checkout not found (set $ROCKET_REF)")
     _install_stubs()

@@ -66,11 +66,11 @@ def load():
     L.rl_get_epoch.restype = u64
     L.rl_set_epoch.argtypes = [vp, u64]
     L.rl_reset.argtypes = [vp, vp, vp, vp]
-    L.rl_step.argtypes = [vp] + [vp] * 9 + [i32, i32, vp]
+    L.rl_step.argtypes = [vp] + [vp] * 10 + [i32, i32, vp]
     L.rl_set_state.argtypes = [vp, vp, vp, vp]
     L.rl_get_state.argtypes = [vp, vp, vp]
     L.rl_stats.argtypes = [vp, vp, i32, vp]
-    L.rl_step_host.argtypes = [vp] + [vp] * 9 + [i32, i32]
+    L.rl_step_host.argtypes = [vp] + [vp] * 10 + [i32, i32]
     L.rl_reset_host.argtypes = [vp, vp]
     L.rl_get_state_host.argtypes = [vp, vp]
     L.rl_launch_count.argtypes = [vp]
@@ -93,7 +93,7 @@ def load():
     L.rl_policy_last_error.restype = C.c_char_p
     L.rl_mlp_blob_bytes.restype = i64
     L.rl_mlp_forward.argtypes = [vp, vp, vp, i64, i32, vp]
-    L.rl_policy_sample.argtypes = [vp, vp, vp, u64, u64, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp, vp, vp, i64, vp]
+    L.rl_policy_sample.argtypes = [vp, vp, vp, u64, u64, i64, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp, vp, vp, i64, vp]
     _lib = L
     return L
 

@@ -21,29 +21,35 @@ def default_config_path() -> str:
 
 
 class Config:
+    """Dotted-key view of a ``config.yaml`` with the reference's key paths.  Lookups are strict in
+    the same way as the reference's loader: an unknown key or a path through a non-mapping is a
+    ``KeyError``, a key that is present but empty is a ``ValueError``."""
+
     def __init__(self, path: str | None = None):
         import yaml
         self.config_path = path or default_config_path()
-        if not os.path.isfile(self.config_path):
-            raise FileNotFoundError(f"Config file not found: {self.config_path}")
         try:
             with open(self.config_path, "r") as fh:
-                self._config = yaml.safe_load(fh) or {}
+                tree = yaml.safe_load(fh)
+        except FileNotFoundError:
+            raise FileNotFoundError(f"no configuration file at {self.config_path}") from None
         except yaml.YAMLError as exc:
-            raise ValueError(f"Failed to parse YAML config: {exc}")
+            raise ValueError(f"{self.config_path} is not valid YAML: {exc}") from exc
+        self._config = tree if isinstance(tree, dict) else {}
 
     def get(self, key_path: str) -> Any:
         node: Any = self._config
-        parts = key_path.split(".")
-        for depth, part in enumerate(parts):
+        walked = []
+        for part in key_path.split("."):
             if not isinstance(node, dict):
-                raise KeyError(f"Invalid config path: '{'.'.join(parts[:depth])}' is not a dict. "
-                               f"Cannot access '{part}'.")
-            if part not in node:
-                raise KeyError(f"Missing config key: '{'.'.join(parts[:depth + 1])}'")
-            node = node[part]
+                raise KeyError(f"'{'.'.join(walked)}' is a leaf of {self.config_path}; it has no entry '{part}'")
+            walked.append(part)
+            try:
+                node = node[part]
+            except KeyError:
+                raise KeyError(f"'{'.'.join(walked)}' is not defined in {self.config_path}") from None
         if node is None:
-            raise ValueError(f"Config key '{key_path}' exists but has no value (None).")
+            raise ValueError(f"'{key_path}' is present in {self.config_path} but empty")
         return node
 
 

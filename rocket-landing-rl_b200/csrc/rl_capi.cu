@@ -58,6 +58,15 @@ struct RlEnv {
     int64_t small_host = 16384;       // rl_step_host: at most this many rockets take the zero-copy path
     cudaStream_t h_streams[2] = {nullptr, nullptr};
     cudaEvent_t h_events[2] = {nullptr, nullptr};
+    // Ordering between the two API families on one handle: the device API only enqueues on the
+    // caller's stream, the host API runs on the handle's private streams.  Every device-API call
+    // notes its stream here; a host-API call first makes its private stream wait for everything
+    // enqueued on that stream so far (order_after_device_api), so "rl_step on my stream, then
+    // rl_step_host / rl_get_state_host" needs no synchronisation by the caller.  The reverse order
+    // is safe by construction: host-API calls return only when their work is complete.
+    cudaStream_t last_stream = nullptr;
+    bool last_stream_valid = false;
+    cudaEvent_t order_event = nullptr;
 };
 
 namespace {
@@ -104,7 +113,7 @@ struct DeviceGuard {
 // lets only the last chunk advance it, so that it draws exactly the resets rl_step would.
 int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8_t* terminated,
                 uint8_t* truncated, float* terminal_obs, float* episode_return, int32_t* episode_length,
-                int8_t* landing, int substeps, int auto_reset, cudaStream_t stream, int64_t tile_begin = 0,
+                int8_t* landing, float* raw_accel, int substeps, int auto_reset, cudaStream_t stream, int64_t tile_begin = 0,
                 int64_t tile_end = -1, const unsigned long long* epoch_src = nullptr, bool bump = true) {
     rl::StepArgs a;
     const int64_t all_tiles = (e->n + rl::kCtaThreads - 1) / rl::kCtaThreads;
@@ -122,6 +131,7 @@ int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8
     a.episode_return = episode_return;
     a.episode_length = episode_length;
     a.landing = landing;
+    a.raw_accel = reinterpret_cast<float2*>(raw_accel);
     a.stats = e->stats;
     a.n = (uint32_t)e->n;
     a.gid0 = e->gid0;
@@ -152,6 +162,35 @@ int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8
 }
 
 bool misaligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) != 0; }
+
+int ensure_streams(RlEnv* e) {
+    if (e->h_streams[0]) return RL_OK;
+    for (int k = 0; k < 2; ++k) {
+        RL_CUDA(cudaStreamCreateWithFlags(&e->h_streams[k], cudaStreamNonBlocking));
+        RL_CUDA(cudaEventCreateWithFlags(&e->h_events[k], cudaEventDisableTiming));
+    }
+    RL_CUDA(cudaEventCreateWithFlags(&e->order_event, cudaEventDisableTiming));
+    return RL_OK;
+}
+
+// Make `hs` (a private host-path stream) wait for everything the device API has enqueued on the
+// caller's stream so far.  A stream that is being captured or has been destroyed cannot be waited
+// for: the error is cleared and the call proceeds unordered (the caller synchronises in that case).
+int order_after_device_api(RlEnv* e, cudaStream_t hs) {
+    if (!e->last_stream_valid) return RL_OK;
+    if (cudaEventRecord(e->order_event, e->last_stream) != cudaSuccess) {
+        cudaGetLastError();
+        e->last_stream_valid = false;
+        return RL_OK;
+    }
+    RL_CUDA(cudaStreamWaitEvent(hs, e->order_event, 0));
+    return RL_OK;
+}
+
+inline void note_stream(RlEnv* e, void* stream) {
+    e->last_stream = (cudaStream_t)stream;
+    e->last_stream_valid = true;
+}
 
 }  // namespace
 
@@ -288,6 +327,12 @@ int rl_create(const RlParams* params, int64_t n_envs, int64_t env_id_offset, uin
             }
             e->step_grid[ar][single] = e->sms * per_sm;
         }
+    // the zero-fills above ran on the legacy default stream, which a caller's non-blocking stream
+    // (and the handle's private host-path streams) does not wait for: finish them here, once
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        rl_destroy(e);
+        return fail(RL_E_CUDA, "rl_create: device initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
     *out = e;
     return RL_OK;
 }
@@ -301,6 +346,7 @@ int rl_destroy(RlEnv* e) {
     if (e->ticket) cudaFree(e->ticket);
     if (e->h_stage) cudaFree(e->h_stage);
     if (e->h_pinned) cudaFreeHost(e->h_pinned);
+    if (e->order_event) cudaEventDestroy(e->order_event);
     for (int k = 0; k < 2; ++k) {
         if (e->h_streams[k]) cudaStreamDestroy(e->h_streams[k]);
         if (e->h_events[k]) cudaEventDestroy(e->h_events[k]);
@@ -313,12 +359,15 @@ int64_t rl_num_envs(const RlEnv* e) { return e ? e->n : 0; }
 double rl_fuel_unit(const RlEnv* e) { return e ? e->dev.fuel_unit_d : 0.0; }
 double rl_fuel_unit_for(const RlParams* p) { return p ? rl::fuel_unit_for(p->reset_high[9]) : 0.0; }
 int rl_uses_folded_constants(const RlEnv* e) { return (e && e->folded) ? 1 : 0; }
-uint64_t rl_get_epoch(const RlEnv* e) {
+uint64_t rl_get_epoch(RlEnv* e) {
     if (!e) return 0;
     DeviceGuard guard(e->device);
     unsigned long long v = 0;
-    if (cudaDeviceSynchronize() != cudaSuccess ||
-        cudaMemcpy(&v, e->epoch, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
+    // ordered after everything this handle has enqueued (device API: the caller's last stream; host
+    // API: already complete); no device-wide synchronisation
+    if (ensure_streams(e) != RL_OK || order_after_device_api(e, e->h_streams[0]) != RL_OK ||
+        cudaMemcpyAsync(&v, e->epoch, sizeof(v), cudaMemcpyDeviceToHost, e->h_streams[0]) != cudaSuccess ||
+        cudaStreamSynchronize(e->h_streams[0]) != cudaSuccess) {
         fail(RL_E_CUDA, "rl_get_epoch: %s", cudaGetErrorString(cudaGetLastError()));
         return 0;
     }
@@ -328,8 +377,12 @@ int rl_set_epoch(RlEnv* e, uint64_t epoch) {
     if (!e) return fail(RL_E_INVALID, "rl_set_epoch: null handle");
     DeviceGuard guard(e->device);
     const unsigned long long v = epoch;
-    RL_CUDA(cudaDeviceSynchronize());
-    RL_CUDA(cudaMemcpy(e->epoch, &v, sizeof(v), cudaMemcpyHostToDevice));
+    int rc = ensure_streams(e);
+    if (rc != RL_OK) return rc;
+    rc = order_after_device_api(e, e->h_streams[0]);
+    if (rc != RL_OK) return rc;
+    RL_CUDA(cudaMemcpyAsync(e->epoch, &v, sizeof(v), cudaMemcpyHostToDevice, e->h_streams[0]));
+    RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));       // later device-API calls are enqueued after this returns
     return RL_OK;
 }
 int64_t rl_launch_count(const RlEnv* e) { return e ? e->launches : 0; }
@@ -338,6 +391,7 @@ int rl_reset(RlEnv* e, const uint8_t* mask, float* obs, void* stream) {
     if (!e) return fail(RL_E_INVALID, "rl_reset: null handle");
     if (obs && misaligned(obs, 16)) return fail(RL_E_INVALID, "rl_reset: obs must be 16-byte aligned");
     DeviceGuard guard(e->device);
+    note_stream(e, stream);
     rl::reset_kernel<<<grid_for(e, e->n), rl::kCtaThreads, 0, (cudaStream_t)stream>>>(
         e->dev, e->planes, mask, reinterpret_cast<float4*>(obs), (uint32_t)e->n, e->gid0, e->seed, e->epoch, e->ticket);
     e->launches += 1;
@@ -346,32 +400,35 @@ int rl_reset(RlEnv* e, const uint8_t* mask, float* obs, void* stream) {
 }
 
 int rl_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated,
-            float* terminal_obs, float* episode_return, int32_t* episode_length, int8_t* landing, int substeps,
-            int auto_reset, void* stream) {
+            float* terminal_obs, float* episode_return, int32_t* episode_length, int8_t* landing, float* raw_accel,
+            int substeps, int auto_reset, void* stream) {
     if (!e) return fail(RL_E_INVALID, "rl_step: null handle");
     if (!actions || !obs || !reward || !terminated || !truncated)
         return fail(RL_E_INVALID, "rl_step: actions, obs, reward, terminated and truncated are required");
     if (substeps < 1 || substeps > 4096) return fail(RL_E_INVALID, "rl_step: substeps must be in [1, 4096] (got %d)", substeps);
     if (misaligned(actions, 8) || misaligned(obs, 16) || misaligned(reward, 4) ||
-        (terminal_obs && misaligned(terminal_obs, 16)))
-        return fail(RL_E_INVALID, "rl_step: actions need 8-byte, obs / terminal_obs 16-byte alignment");
+        (terminal_obs && misaligned(terminal_obs, 16)) || (raw_accel && misaligned(raw_accel, 8)))
+        return fail(RL_E_INVALID, "rl_step: actions / raw_accel need 8-byte, obs / terminal_obs 16-byte alignment");
     DeviceGuard guard(e->device);
+    note_stream(e, stream);
     return launch_step(e, actions, obs, reward, terminated, truncated, terminal_obs, episode_return,
-                       episode_length, landing, substeps, auto_reset, (cudaStream_t)stream);
+                       episode_length, landing, raw_accel, substeps, auto_reset, (cudaStream_t)stream);
 }
 
-int rl_set_state(RlEnv* e, const float* state_soa, const uint8_t* mask, void* stream) {
+int rl_set_state(RlEnv* e, const uint32_t* state_soa, const uint8_t* mask, void* stream) {
     if (!e || !state_soa) return fail(RL_E_INVALID, "rl_set_state: null argument");
     DeviceGuard guard(e->device);
+    note_stream(e, stream);
     rl::set_state_kernel<<<grid_for(e, e->n), rl::kCtaThreads, 0, (cudaStream_t)stream>>>(e->planes, state_soa, mask, (uint32_t)e->n);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
     return RL_OK;
 }
 
-int rl_get_state(RlEnv* e, float* state_soa, void* stream) {
+int rl_get_state(RlEnv* e, uint32_t* state_soa, void* stream) {
     if (!e || !state_soa) return fail(RL_E_INVALID, "rl_get_state: null argument");
     DeviceGuard guard(e->device);
+    note_stream(e, stream);
     rl::get_state_kernel<<<grid_for(e, e->n), rl::kCtaThreads, 0, (cudaStream_t)stream>>>(e->planes, state_soa, (uint32_t)e->n);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
@@ -381,6 +438,7 @@ int rl_get_state(RlEnv* e, float* state_soa, void* stream) {
 int rl_stats(RlEnv* e, double* out16, int reset_after, void* stream) {
     if (!e || !out16) return fail(RL_E_INVALID, "rl_stats: null argument");
     DeviceGuard guard(e->device);
+    note_stream(e, stream);
     rl::stats_copy_kernel<<<1, RL_STATS_WORDS * 32, 0, (cudaStream_t)stream>>>(e->stats, out16, reset_after);
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
@@ -392,6 +450,7 @@ int rl_sim_step(RlEnv* e, const float* actions, float* telemetry, float* reward,
     if (!e || !actions || !telemetry) return fail(RL_E_INVALID, "rl_sim_step: actions and telemetry are required");
     if (misaligned(actions, 8) || misaligned(telemetry, 16)) return fail(RL_E_INVALID, "rl_sim_step: actions need 8-byte, telemetry 16-byte alignment");
     DeviceGuard guard(e->device);
+    note_stream(e, stream);
     if (e->folded)
         rl::sim_step_kernel<rl::DefaultParams><<<grid_for(e, e->n), rl::kCtaThreads, 0, (cudaStream_t)stream>>>(
             e->dev, e->planes, reinterpret_cast<const float2*>(actions), reinterpret_cast<float4*>(telemetry), reward, done, (uint32_t)e->n);
@@ -405,7 +464,7 @@ int rl_sim_step(RlEnv* e, const float* actions, float* telemetry, float* reward,
 
 // ---- host-buffer path ------------------------------------------------------------------
 // Device staging for one full batch: actions | obs | reward | terminated | truncated |
-// terminal_obs | episode_return | episode_length | landing, each 256-byte aligned.
+// terminal_obs | episode_return | episode_length | landing | raw_accel, each 256-byte aligned.
 // rl_step_host cuts the batch into chunks and runs them as a two-stream software pipeline:
 //   chunk c:  H2D(actions[c]) -> step(tiles of c) -> D2H(obs[c], reward[c], flags[c], ...)
 // so that the (dominant) device-to-host copy of chunk c overlaps the host-to-device copy and the
@@ -413,21 +472,22 @@ int rl_sim_step(RlEnv* e, const float* actions, float* telemetry, float* reward,
 // epoch and only the last one advances it: the call draws exactly the resets one rl_step would.
 namespace {
 struct Stage {
-    float *actions, *obs, *reward, *terminal_obs, *episode_return;
+    float *actions, *obs, *reward, *terminal_obs, *episode_return, *raw_accel;
     uint8_t *terminated, *truncated;
     int32_t* episode_length;
     int8_t* landing;
 };
+constexpr int kStageArrays = 10;
 size_t align256(size_t v) { return (v + 255) / 256 * 256; }
-size_t stage_sizes(const RlEnv* e, size_t sz[9]) {
+size_t stage_sizes(const RlEnv* e, size_t sz[kStageArrays]) {
     const size_t n = (size_t)e->n;
-    const size_t v[9] = {align256(8 * n), align256(32 * n), align256(4 * n), align256(n), align256(n),
-                         align256(32 * n), align256(4 * n), align256(4 * n), align256(n)};
+    const size_t v[kStageArrays] = {align256(8 * n), align256(32 * n), align256(4 * n), align256(n), align256(n),
+                                    align256(32 * n), align256(4 * n), align256(4 * n), align256(n), align256(8 * n)};
     size_t total = 256;                                   // + the epoch snapshot
-    for (int k = 0; k < 9; ++k) { sz[k] = v[k]; total += v[k]; }
+    for (int k = 0; k < kStageArrays; ++k) { sz[k] = v[k]; total += v[k]; }
     return total;
 }
-void carve_stage(char* p, const size_t sz[9], Stage& s) {
+void carve_stage(char* p, const size_t sz[kStageArrays], Stage& s) {
     p += 256;
     s.actions = (float*)p; p += sz[0];
     s.obs = (float*)p; p += sz[1];
@@ -437,18 +497,11 @@ void carve_stage(char* p, const size_t sz[9], Stage& s) {
     s.terminal_obs = (float*)p; p += sz[5];
     s.episode_return = (float*)p; p += sz[6];
     s.episode_length = (int32_t*)p; p += sz[7];
-    s.landing = (int8_t*)p;
-}
-int ensure_streams(RlEnv* e) {
-    if (e->h_streams[0]) return RL_OK;
-    for (int k = 0; k < 2; ++k) {
-        RL_CUDA(cudaStreamCreateWithFlags(&e->h_streams[k], cudaStreamNonBlocking));
-        RL_CUDA(cudaEventCreateWithFlags(&e->h_events[k], cudaEventDisableTiming));
-    }
-    return RL_OK;
+    s.landing = (int8_t*)p; p += sz[8];
+    s.raw_accel = (float*)p;
 }
 int ensure_stage(RlEnv* e, Stage& s) {
-    size_t sz[9];
+    size_t sz[kStageArrays];
     const size_t total = stage_sizes(e, sz);
     if (!e->h_stage) {
         if (cudaMalloc(&e->h_stage, total) != cudaSuccess) return fail(RL_E_NOMEM, "host path: cudaMalloc(%zu) failed", total);
@@ -463,7 +516,7 @@ int ensure_stage(RlEnv* e, Stage& s) {
 // Small batches: pinned host memory the device reads and writes directly (zero-copy over PCIe).
 // `host` are the CPU's pointers, `dev` the device's aliases of the same bytes.
 int ensure_pinned(RlEnv* e, Stage& host, Stage& dev) {
-    size_t sz[9];
+    size_t sz[kStageArrays];
     const size_t total = stage_sizes(e, sz);
     if (!e->h_pinned) {
         if (cudaHostAlloc(&e->h_pinned, total, cudaHostAllocMapped) != cudaSuccess)
@@ -481,8 +534,8 @@ int ensure_pinned(RlEnv* e, Stage& host, Stage& dev) {
 }  // namespace
 
 int rl_step_host(RlEnv* e, const float* actions, float* obs, float* reward, uint8_t* terminated, uint8_t* truncated,
-                 float* terminal_obs, float* episode_return, int32_t* episode_length, int8_t* landing, int substeps,
-                 int auto_reset) {
+                 float* terminal_obs, float* episode_return, int32_t* episode_length, int8_t* landing, float* raw_accel,
+                 int substeps, int auto_reset) {
     if (!e) return fail(RL_E_INVALID, "rl_step_host: null handle");
     if (!actions || !obs || !reward || !terminated || !truncated)
         return fail(RL_E_INVALID, "rl_step_host: actions, obs, reward, terminated and truncated are required");
@@ -496,11 +549,14 @@ int rl_step_host(RlEnv* e, const float* actions, float* obs, float* reward, uint
         Stage h, d;
         int rc = ensure_pinned(e, h, d);
         if (rc != RL_OK) return rc;
+        rc = order_after_device_api(e, e->h_streams[0]);
+        if (rc != RL_OK) return rc;
         const size_t m = (size_t)n;
         memcpy(h.actions, actions, 8 * m);
         rc = launch_step(e, d.actions, d.obs, d.reward, d.terminated, d.truncated, terminal_obs ? d.terminal_obs : nullptr,
                          episode_return ? d.episode_return : nullptr, episode_length ? d.episode_length : nullptr,
-                         landing ? d.landing : nullptr, substeps, auto_reset, e->h_streams[0]);
+                         landing ? d.landing : nullptr, raw_accel ? d.raw_accel : nullptr, substeps, auto_reset,
+                         e->h_streams[0]);
         if (rc != RL_OK) return rc;
         RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
         memcpy(obs, h.obs, 32 * m);
@@ -511,10 +567,13 @@ int rl_step_host(RlEnv* e, const float* actions, float* obs, float* reward, uint
         if (episode_return) memcpy(episode_return, h.episode_return, 4 * m);
         if (episode_length) memcpy(episode_length, h.episode_length, 4 * m);
         if (landing) memcpy(landing, h.landing, m);
+        if (raw_accel) memcpy(raw_accel, h.raw_accel, 8 * m);
         return RL_OK;
     }
     Stage s;
     int rc = ensure_stage(e, s);
+    if (rc != RL_OK) return rc;
+    rc = order_after_device_api(e, e->h_streams[0]);
     if (rc != RL_OK) return rc;
     const int64_t tiles = (n + rl::kCtaThreads - 1) / rl::kCtaThreads;
     // chunks of >= 1 Mi rockets (PCIe-efficient, and a full persistent grid), at most 16 of them
@@ -537,8 +596,8 @@ int rl_step_host(RlEnv* e, const float* actions, float* obs, float* reward, uint
         RL_CUDA(cudaMemcpyAsync(s.actions + 2 * lo, actions + 2 * lo, 8 * m, cudaMemcpyHostToDevice, st));
         rc = launch_step(e, s.actions, s.obs, s.reward, s.terminated, s.truncated,
                          terminal_obs ? s.terminal_obs : nullptr, episode_return ? s.episode_return : nullptr,
-                         episode_length ? s.episode_length : nullptr, landing ? s.landing : nullptr, substeps,
-                         auto_reset, st, t0, t1, e->h_epoch_snapshot, last);
+                         episode_length ? s.episode_length : nullptr, landing ? s.landing : nullptr,
+                         raw_accel ? s.raw_accel : nullptr, substeps, auto_reset, st, t0, t1, e->h_epoch_snapshot, last);
         if (rc != RL_OK) return rc;
         RL_CUDA(cudaMemcpyAsync(obs + 8 * lo, s.obs + 8 * lo, 32 * m, cudaMemcpyDeviceToHost, st));
         RL_CUDA(cudaMemcpyAsync(reward + lo, s.reward + lo, 4 * m, cudaMemcpyDeviceToHost, st));
@@ -548,6 +607,7 @@ int rl_step_host(RlEnv* e, const float* actions, float* obs, float* reward, uint
         if (episode_return) RL_CUDA(cudaMemcpyAsync(episode_return + lo, s.episode_return + lo, 4 * m, cudaMemcpyDeviceToHost, st));
         if (episode_length) RL_CUDA(cudaMemcpyAsync(episode_length + lo, s.episode_length + lo, 4 * m, cudaMemcpyDeviceToHost, st));
         if (landing) RL_CUDA(cudaMemcpyAsync(landing + lo, s.landing + lo, m, cudaMemcpyDeviceToHost, st));
+        if (raw_accel) RL_CUDA(cudaMemcpyAsync(raw_accel + 2 * lo, s.raw_accel + 2 * lo, 8 * m, cudaMemcpyDeviceToHost, st));
     }
     RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
     RL_CUDA(cudaStreamSynchronize(e->h_streams[1]));
@@ -564,6 +624,8 @@ int rl_sim_step_host(RlEnv* e, const float* actions, uint8_t* message) {
     if (rc != RL_OK) return rc;
     const size_t n = (size_t)e->n;
     cudaStream_t st = e->h_streams[0];
+    rc = order_after_device_api(e, st);
+    if (rc != RL_OK) return rc;
     // The 64 B / rocket of records occupy the staging span that starts at the obs area (obs 32 n +
     // reward 4 n + flags 2 n + terminal_obs 32 n >= 64 n bytes, contiguous); the gym-mode host path
     // and this one never run concurrently on a handle.
@@ -584,6 +646,8 @@ int rl_reset_host(RlEnv* e, float* obs) {
         Stage h, d;
         int rc = ensure_pinned(e, h, d);
         if (rc != RL_OK) return rc;
+        rc = order_after_device_api(e, e->h_streams[0]);
+        if (rc != RL_OK) return rc;
         rc = rl_reset(e, nullptr, obs ? d.obs : nullptr, e->h_streams[0]);
         if (rc != RL_OK) return rc;
         RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
@@ -593,6 +657,8 @@ int rl_reset_host(RlEnv* e, float* obs) {
     Stage s;
     int rc = ensure_stage(e, s);
     if (rc != RL_OK) return rc;
+    rc = order_after_device_api(e, e->h_streams[0]);
+    if (rc != RL_OK) return rc;
     rc = rl_reset(e, nullptr, obs ? s.obs : nullptr, e->h_streams[0]);
     if (rc != RL_OK) return rc;
     if (obs) RL_CUDA(cudaMemcpyAsync(obs, s.obs, 32 * (size_t)e->n, cudaMemcpyDeviceToHost, e->h_streams[0]));
@@ -600,9 +666,9 @@ int rl_reset_host(RlEnv* e, float* obs) {
     return RL_OK;
 }
 
-// rl_get_state into HOST memory (float32 [10][N], RL_W_*); synchronous.  Small batches go through
+// rl_get_state into HOST memory (uint32 [10][N], RL_W_*); synchronous.  Small batches go through
 // pinned, device-mapped memory (one launch + one synchronisation).
-int rl_get_state_host(RlEnv* e, float* state_soa) {
+int rl_get_state_host(RlEnv* e, uint32_t* state_soa) {
     if (!e || !state_soa) return fail(RL_E_INVALID, "rl_get_state_host: null argument");
     DeviceGuard guard(e->device);
     const size_t bytes = 40 * (size_t)e->n;
@@ -610,9 +676,11 @@ int rl_get_state_host(RlEnv* e, float* state_soa) {
         Stage h, d;
         int rc = ensure_pinned(e, h, d);
         if (rc != RL_OK) return rc;
+        rc = order_after_device_api(e, e->h_streams[0]);
+        if (rc != RL_OK) return rc;
         // 40 n bytes fit in the staging span that starts at the observation area (obs 32 n + reward 4 n +
         // flags 2 n + terminal observations 32 n, contiguous); host-path calls on a handle never overlap
-        rc = rl_get_state(e, d.obs, e->h_streams[0]);
+        rc = rl_get_state(e, reinterpret_cast<uint32_t*>(d.obs), e->h_streams[0]);
         if (rc != RL_OK) return rc;
         RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));
         memcpy(state_soa, h.obs, bytes);
@@ -621,7 +689,9 @@ int rl_get_state_host(RlEnv* e, float* state_soa) {
     Stage s;
     int rc = ensure_stage(e, s);
     if (rc != RL_OK) return rc;
-    rc = rl_get_state(e, s.obs, e->h_streams[0]);
+    rc = order_after_device_api(e, e->h_streams[0]);
+    if (rc != RL_OK) return rc;
+    rc = rl_get_state(e, reinterpret_cast<uint32_t*>(s.obs), e->h_streams[0]);
     if (rc != RL_OK) return rc;
     RL_CUDA(cudaMemcpyAsync(state_soa, s.obs, bytes, cudaMemcpyDeviceToHost, e->h_streams[0]));
     RL_CUDA(cudaStreamSynchronize(e->h_streams[0]));

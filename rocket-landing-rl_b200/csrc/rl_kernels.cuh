@@ -75,6 +75,7 @@ struct StepArgs {
     float* __restrict__ episode_return;   // nullable
     int32_t* __restrict__ episode_length; // nullable
     int8_t* __restrict__ landing;         // nullable
+    float2* __restrict__ raw_accel;       // nullable: unclipped (ax, ay) of the step (info["raw_state"], lander.py:157-166)
     double* __restrict__ stats;           // [RL_STATS_WORDS]
     uint32_t n;                           // rockets on this shard (< 2^31)
     int64_t gid0;                         // global id of rocket 0 (Philox counter)
@@ -414,6 +415,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
             out_store(&a.terminated[i], (uint8_t)(terminated ? 1 : 0));
             out_store(&a.truncated[i], (uint8_t)(truncated ? 1 : 0));
             if (a.landing) out_store(reinterpret_cast<uint8_t*>(&a.landing[i]), (uint8_t)landing);
+            if (a.raw_accel) out_store(&a.raw_accel[i], make_float2(o.ax, o.ay));
         }
     }
     cp_async_wait<0>();
@@ -445,9 +447,10 @@ __global__ void __launch_bounds__(kCtaThreads) reset_kernel(const __grid_constan
 
 // Public state format <-> planes (rl_set_state / rl_get_state): the public words ARE the kernel's
 // words (raw 32-bit copies), so a get -> set round trip is lossless.
-__global__ void __launch_bounds__(kCtaThreads) set_state_kernel(StatePlanes st, const float* __restrict__ soa,
+__global__ void __launch_bounds__(kCtaThreads) set_state_kernel(StatePlanes st, const uint32_t* __restrict__ words,
                                                                 const uint8_t* __restrict__ mask, uint32_t n) {
     const size_t N = n;
+    const float* soa = reinterpret_cast<const float*>(words);
     for (uint32_t i = blockIdx.x * kCtaThreads + threadIdx.x; i < n; i += gridDim.x * kCtaThreads) {
         if (mask && !mask[i]) continue;
         st.A[i] = make_float4(soa[RL_W_X * N + i], soa[RL_W_Y * N + i], soa[RL_W_ANGLE * N + i], soa[RL_W_META * N + i]);
@@ -457,8 +460,9 @@ __global__ void __launch_bounds__(kCtaThreads) set_state_kernel(StatePlanes st, 
     }
 }
 
-__global__ void __launch_bounds__(kCtaThreads) get_state_kernel(StatePlanes st, float* __restrict__ soa, uint32_t n) {
+__global__ void __launch_bounds__(kCtaThreads) get_state_kernel(StatePlanes st, uint32_t* __restrict__ words, uint32_t n) {
     const size_t N = n;
+    float* soa = reinterpret_cast<float*>(words);
     for (uint32_t i = blockIdx.x * kCtaThreads + threadIdx.x; i < n; i += gridDim.x * kCtaThreads) {
         const float4 a = st.A[i], b = st.B[i];
         soa[RL_W_X * N + i] = a.x; soa[RL_W_Y * N + i] = a.y; soa[RL_W_ANGLE * N + i] = a.z; soa[RL_W_META * N + i] = a.w;

@@ -95,15 +95,15 @@ __device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
 // Optional epilogue of the policy net (out_dim 2): draw the action the way SB3's DiagGaussian
 // distribution does -- action = mean + exp(log_std) eps, eps ~ N(0, 1); log-probability summed over
 // the two components; the Box-clipped copy that goes to env.step (SB3 clips before stepping and
-// stores the unclipped sample) -- with counter-based noise: Philox4x32-10 keyed by `seed`, counter
-// (row, draw), Box-Muller.  All null / zero: plain forward.
+// stores the unclipped sample) -- with counter-based noise: Philox4x32-10 keyed by `seed` xor a domain tag,
+// counter (global row, draw), Box-Muller.  All null / zero: plain forward.
 struct SampleArgs {
     const float* log_std;      // device [2]
     float* actions;            // [n][2] unclipped samples (null: no sampling)
     float* clipped;            // [n][2]
     float* log_prob;           // [n]
     float* mean;               // [n][2], nullable
-    unsigned long long seed, draw;
+    unsigned long long seed, draw, row_offset;
     float lo0, lo1, hi0, hi1;
 };
 
@@ -383,9 +383,13 @@ __global__ void __launch_bounds__(kTc5Threads, 1) mlp_forward_tc5_kernel(const u
                     for (int sl = 0; sl < kSplit; ++sl) v[o] += red[(sl * kM + tid) * 2 + o];
                 }
                 if (kOut == 2 && sa.actions != nullptr) {
-                    const uint4 bits = rl::philox4x32_10(make_uint4((uint32_t)r, (uint32_t)((uint64_t)r >> 32), (uint32_t)sa.draw,
+                    // counter (global row, draw); the KEY is the seed xor a domain tag, so that this stream is
+                    // independent of the environment's reset stream (key = seed, counter = (global id, epoch))
+                    // even when both are given the same seed
+                    const uint64_t gr = (uint64_t)r + sa.row_offset;
+                    const uint4 bits = rl::philox4x32_10(make_uint4((uint32_t)gr, (uint32_t)(gr >> 32), (uint32_t)sa.draw,
                                                                     (uint32_t)(sa.draw >> 32)),
-                                                         make_uint2((uint32_t)sa.seed, (uint32_t)(sa.seed >> 32)));
+                                                         make_uint2((uint32_t)sa.seed ^ 0x706F6C69u, (uint32_t)(sa.seed >> 32) ^ 0x63792E61u));
                     const float u1 = (float)((bits.x >> 8) + 1u) * 5.9604644775390625e-8f;      // (0, 1]
                     const float u2 = (float)(bits.y >> 8) * 5.9604644775390625e-8f;             // [0, 1)
                     const float rad = sqrtf(-2.0f * logf(u1));
@@ -459,20 +463,22 @@ int rl_mlp_forward(const void* blob, const float* obs, float* out, int64_t n, in
 // The policy net with SB3's action sampling fused into its epilogue: actions[n][2] = mean +
 // exp(log_std) eps (unclipped, what the rollout buffer stores), clipped[n][2] = the same clipped to
 // [low, high] (what env.step receives), log_prob[n]; mean[n][2] optional.  eps is Philox4x32-10 keyed
-// by `seed` at counter (row, draw): pass a different `draw` every call.  DEVICE pointers, enqueue only.
+// by `seed` (xor a domain tag) at counter (row_offset + row, draw): pass a different `draw` every call and the
+// shard's global id offset as row_offset.  DEVICE pointers, enqueue only.
 int rl_policy_sample(const void* blob, const float* obs, const float* log_std, uint64_t seed, uint64_t draw,
-                     const float* low2, const float* high2, float* actions, float* clipped, float* log_prob,
-                     float* mean, int64_t n, void* stream) {
+                     int64_t row_offset, const float* low2, const float* high2, float* actions, float* clipped,
+                     float* log_prob, float* mean, int64_t n, void* stream) {
     if (!blob || !obs || !log_std || !low2 || !high2 || !actions || !clipped || !log_prob)
         return po_fail(RL_E_INVALID, "rl_policy_sample: null argument");
     if (n < 1) return po_fail(RL_E_INVALID, "rl_policy_sample: n must be positive");
+    if (row_offset < 0) return po_fail(RL_E_INVALID, "rl_policy_sample: row_offset must be >= 0");
     if ((reinterpret_cast<uintptr_t>(blob) & 15) || (reinterpret_cast<uintptr_t>(obs) & 15) ||
         (reinterpret_cast<uintptr_t>(actions) & 7) || (reinterpret_cast<uintptr_t>(clipped) & 7) ||
         (mean && (reinterpret_cast<uintptr_t>(mean) & 7)))
         return po_fail(RL_E_INVALID, "rl_policy_sample: blob / obs need 16-byte, actions / clipped / mean 8-byte alignment");
     SampleArgs sa = {};
     sa.log_std = log_std; sa.actions = actions; sa.clipped = clipped; sa.log_prob = log_prob; sa.mean = mean;
-    sa.seed = seed; sa.draw = draw;
+    sa.seed = seed; sa.draw = draw; sa.row_offset = (unsigned long long)row_offset;
     sa.lo0 = low2[0]; sa.lo1 = low2[1]; sa.hi0 = high2[0]; sa.hi1 = high2[1];      // HOST pointers: two floats each
     return launch_mlp(blob, obs, actions, n, 2, sa, (cudaStream_t)stream);
 }

@@ -46,13 +46,16 @@ class RocketLandingVecEnv:
     auto_reset     reset done rockets inside the step and return their reset observation
                    (SB3 VecEnv contract); the terminal observation is in
                    ``info["terminal_observation"]``
+    raw_state      also report the step's UNCLIPPED accelerations as ``info["raw_accel"]`` [N,2]
+                   (with ``get_reference_state()`` that is every word of the reference's
+                   per-step ``info["raw_state"]``, lander.py:157-166; +8 B per rocket per step)
     """
 
     metadata: Dict[str, Any] = {"render_modes": []}
 
     def __init__(self, num_envs: int, device: Any = "cuda:0", seed: int = 0,
                  config: Config | str | None = None, env_id_offset: int = 0, substeps: int = 1,
-                 auto_reset: bool = True, params: RlParams | None = None):
+                 auto_reset: bool = True, params: RlParams | None = None, raw_state: bool = False):
         self._h = None
         self._L = _lib.load()
         if isinstance(device, int):
@@ -100,6 +103,7 @@ class RocketLandingVecEnv:
         self.episode_return = torch.zeros((n,), **f32)
         self.episode_length = torch.zeros((n,), dtype=torch.int32, device=self.device)
         self.landing = torch.zeros((n,), dtype=torch.int8, device=self.device)
+        self.raw_accel = torch.zeros((n, 2), **f32) if raw_state else None
         self._stats = torch.zeros((STATS_WORDS,), dtype=torch.float64, device=self.device)
         self._out_ptrs = None            # cached data_ptr()s of the output buffers (see step)
 
@@ -128,15 +132,17 @@ class RocketLandingVecEnv:
         if action.shape != (self.num_envs, 2):
             raise ValueError(f"action must have shape ({self.num_envs}, 2), got {tuple(action.shape)}")
         outs = (self.obs, self.reward, self.terminated, self.truncated, self.terminal_obs,
-                self.episode_return, self.episode_length, self.landing)
+                self.episode_return, self.episode_length, self.landing, self.raw_accel)
         if self._out_ptrs is None or self._out_ptrs[0] is not self.obs:      # buffers are persistent; a
-            self._out_ptrs = (self.obs, tuple(t.data_ptr() for t in outs))   # caller may swap self.obs
+            self._out_ptrs = (self.obs, tuple(_ptr(t) for t in outs))        # caller may swap self.obs
         rc = self._L.rl_step(self._h, action.data_ptr(), *self._out_ptrs[1], self.substeps,
                              int(self.auto_reset), self._stream())
         if rc != 0:
             _lib.check(rc, "rl_step")
         info = {"terminal_observation": self.terminal_obs, "episode_return": self.episode_return,
                 "episode_length": self.episode_length, "landing": self.landing}
+        if self.raw_accel is not None:
+            info["raw_accel"] = self.raw_accel
         return self.obs, self.reward, self.terminated, self.truncated, info
 
     def render(self):
@@ -155,15 +161,15 @@ class RocketLandingVecEnv:
             pass
 
     # ------------------------------------------------------------------ state injection / checkpoint
-    def set_state(self, state_soa, mask=None) -> None:
-        """Inject persistent state in the public format (32-bit words [10, N] carried as float32,
-        see ``layout``)."""
-        s = torch.as_tensor(state_soa)
-        if s.dtype != torch.float32:
-            raise TypeError("state_soa must be float32 (the integer words travel as raw bits)")
+    def set_state(self, state_words, mask=None) -> None:
+        """Inject persistent state in the public format (int32 words [10, N], see ``layout``)."""
+        s = torch.as_tensor(state_words)
+        if s.dtype != torch.int32:
+            raise TypeError("state words must be int32 [10, N] (float words travel as their IEEE-754 bits; "
+                            "see rocket_landing_rl_b200.layout)")
         s = s.to(self.device).contiguous()
         if s.shape != (10, self.num_envs):
-            raise ValueError(f"state_soa must have shape (10, {self.num_envs})")
+            raise ValueError(f"state words must have shape (10, {self.num_envs})")
         m = None
         if mask is not None:
             m = torch.as_tensor(mask).to(device=self.device, dtype=torch.uint8).contiguous()
@@ -172,8 +178,25 @@ class RocketLandingVecEnv:
         # the caching allocator reuses it on this stream, which is after the kernel.
 
     def get_state(self) -> torch.Tensor:
-        out = torch.empty((10, self.num_envs), dtype=torch.float32, device=self.device)
+        """The persistent words of every rocket, int32 [10, N] (lossless: ``set_state`` of it restores
+        the state bit for bit)."""
+        out = torch.empty((10, self.num_envs), dtype=torch.int32, device=self.device)
         _lib.check(self._L.rl_get_state(self._h, out.data_ptr(), self._stream()), "rl_get_state")
+        return out
+
+    def raw_state(self) -> dict:
+        """The reference's per-step ``info["raw_state"]`` (lander.py:157-166, ``Rocket.get_state``,
+        base.py:220-240) for every rocket, as float64 numpy arrays keyed by the reference's names.
+        ``ax`` / ``ay`` are the unclipped accelerations of the last step (needs ``raw_state=True``)."""
+        if self.raw_accel is None:
+            raise RuntimeError("construct the environment with raw_state=True")
+        v = self.get_reference_state()
+        acc = self.raw_accel.cpu().numpy().astype(np.float64)
+        out = {"x": v["x"], "y": v["y"], "vx": v["vx"], "vy": v["vy"], "ax": acc[:, 0], "ay": acc[:, 1],
+               "angle": v["angle"], "angularVelocity": v["ang_vel"], "mass": v["dry_mass"], "fuelMass": v["fuel"]}
+        out["speed"] = np.sqrt(out["vx"] ** 2 + out["vy"] ** 2)
+        out["relativeAngle"] = np.abs(out["angle"])
+        out["totalMass"] = out["mass"] + out["fuelMass"]
         return out
 
     def get_reference_state(self) -> dict:
@@ -195,6 +218,12 @@ class RocketLandingVecEnv:
         """float64[16] statistics of THIS shard, on the device (enqueue only)."""
         _lib.check(self._L.rl_stats(self._h, self._stats.data_ptr(), int(reset), self._stream()), "rl_stats")
         return self._stats
+
+    def stats_async(self, reset: bool = False, group=None) -> torch.Tensor:
+        """Enqueue the statistics kernel and the 128-byte all-reduce over ``group``; returns the
+        DEVICE tensor (float64[16]) without synchronising -- read it later with
+        ``EpisodeStats.from_vector(t.cpu().tolist())``."""
+        return allreduce_stats(self.stats_tensor(reset), group)
 
     def stats(self, reset: bool = False, group=None) -> EpisodeStats:
         """Episode statistics summed over all ranks of ``group`` (NCCL all-reduce of 128 B)."""

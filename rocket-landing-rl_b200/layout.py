@@ -1,6 +1,6 @@
 """Host-side helpers for the public state format of ``rl_set_state`` / ``rl_get_state``
-(32-bit words ``[10][N]`` carried in a float32 array, words ``RL_W_*`` of
-include/rocket_landing_b200.h).
+(32-bit words ``[10][N]`` in an int32 array -- ``f32`` words hold their IEEE-754 bits -- words
+``RL_W_*`` of include/rocket_landing_b200.h).
 
 The kernel does not store the reference's ``Rocket.state`` dict verbatim: it carries the
 Verlet DELTAS ``x(t) - x(t-dt)`` (from which ``v = delta / dt``, engine.py:193-194) instead of
@@ -34,9 +34,26 @@ def fuel_unit_for(max_fuel: float) -> float:
     return math.ldexp(1.0, k - 31)
 
 
-def _bits(a: np.ndarray) -> np.ndarray:
-    """uint32 / int32 array -> the same bits as float32."""
-    return np.ascontiguousarray(a).view(np.float32)
+def _bits(a) -> np.ndarray:
+    """float values -> the int32 words holding their float32 bits; integer arrays pass through."""
+    a = np.asarray(a)
+    if a.dtype.kind == "f":
+        return np.ascontiguousarray(a, np.float32).view(np.int32)
+    return np.ascontiguousarray(a).astype(np.int64).astype(np.uint32, casting="unsafe").view(np.int32) \
+        if a.dtype != np.int32 else a
+
+
+def as_words(soa) -> np.ndarray:
+    """Any 32-bit [10, N] array (int32 / uint32 / float32 bits) -> int32 words."""
+    soa = np.asarray(soa)
+    if soa.dtype.itemsize != 4:
+        raise TypeError("state words must be a 32-bit array")
+    return np.ascontiguousarray(soa).view(np.int32)
+
+
+def f32_word(words: np.ndarray, w: int) -> np.ndarray:
+    """Word ``w`` of an int32 state array as the float32 values it holds."""
+    return words[w].view(np.float32)
 
 
 def _meta_bits(steps, wraps, fresh, dlo=0) -> np.ndarray:
@@ -44,7 +61,7 @@ def _meta_bits(steps, wraps, fresh, dlo=0) -> np.ndarray:
     wraps = (np.asarray(wraps, np.int64) & 7) << META_WRAP_SHIFT
     dlo = (np.asarray(dlo, np.int64) & 0xFF) << META_DLO_SHIFT
     bits = (steps | wraps | dlo | (META_FRESH if fresh else 0)).astype(np.uint32)
-    return bits.view(np.float32)
+    return bits.view(np.int32)
 
 
 def _angle_units(angle_deg: np.ndarray) -> np.ndarray:
@@ -79,21 +96,21 @@ def fresh_state_soa(x, y, vx, vy, angle, ang_vel, dry_mass, fuel, steps=0, ep_re
                     fuel_unit: float = DEFAULT_FUEL_UNIT) -> np.ndarray:
     """A just-reset rocket (``Rocket.reset``, base.py:186): the kernel applies the Verlet
     bootstrap (base.py:65-130) itself on the first step.  All arguments are arrays [N]
-    (or scalars); returns the public words as float32 [10, N]."""
+    (or scalars); returns the public words as int32 [10, N]."""
     cols = np.broadcast_arrays(*[np.asarray(v, np.float64) for v in
                                  (x, y, angle, vx, vy, ang_vel, dry_mass, fuel)])
     cx, cy, cang, cvx, cvy, com, cdry, cfuel = [c.reshape(-1) for c in cols]
     n = cx.size
-    soa = np.zeros((10, n), np.float32)
-    soa[W_X], soa[W_Y] = cx, cy
-    soa[W_ANGLE] = _bits(_angle_units(cang))
-    soa[W_SX], soa[W_SY] = cvx, cvy                            # velocities themselves while FRESH
+    soa = np.zeros((10, n), np.int32)
+    soa[W_X], soa[W_Y] = _bits(cx), _bits(cy)
+    soa[W_ANGLE] = _angle_units(cang)
+    soa[W_SX], soa[W_SY] = _bits(cvx), _bits(cvy)              # velocities themselves while FRESH
     om_hi, om_lo = split_angle_delta(com)                      # (omega with its 8 extra bits)
-    soa[W_SANGLE] = om_hi
-    soa[W_DRY] = cdry
-    soa[W_FUEL] = _bits(_fuel_units(cfuel, fuel_unit))
+    soa[W_SANGLE] = _bits(om_hi)
+    soa[W_DRY] = _bits(cdry)
+    soa[W_FUEL] = _fuel_units(cfuel, fuel_unit)
     soa[W_META] = _meta_bits(np.broadcast_to(np.asarray(steps), (n,)), 0, True, om_lo)
-    soa[W_EPRET] = np.broadcast_to(np.asarray(ep_return, np.float32), (n,))
+    soa[W_EPRET] = _bits(np.broadcast_to(np.asarray(ep_return, np.float32), (n,)))
     return soa
 
 
@@ -109,19 +126,19 @@ def state_soa_from_reference(state: np.ndarray, prev: np.ndarray, steps, dt: flo
     state = np.asarray(state, np.float64)
     prev = np.asarray(prev, np.float64)
     n = state.shape[0]
-    soa = np.zeros((10, n), np.float32)
-    soa[W_X], soa[W_Y] = state[:, 0], state[:, 1]
-    soa[W_ANGLE] = _bits(_angle_units(state[:, 6]))
-    soa[W_SX] = _bits(np.rint((state[:, 0] - prev[:, 0]) * DELTA_UNITS_PER_M).astype(np.int32))
-    soa[W_SY] = _bits(np.rint((state[:, 1] - prev[:, 1]) * DELTA_UNITS_PER_M).astype(np.int32))
+    soa = np.zeros((10, n), np.int32)
+    soa[W_X], soa[W_Y] = _bits(state[:, 0]), _bits(state[:, 1])
+    soa[W_ANGLE] = _angle_units(state[:, 6])
+    soa[W_SX] = np.rint((state[:, 0] - prev[:, 0]) * DELTA_UNITS_PER_M).astype(np.int32)
+    soa[W_SY] = np.rint((state[:, 1] - prev[:, 1]) * DELTA_UNITS_PER_M).astype(np.int32)
     pre_wrap = state[:, 7] * dt
     hi, lo = split_angle_delta(pre_wrap)
-    soa[W_SANGLE] = hi
+    soa[W_SANGLE] = _bits(hi)
     wraps = np.rint((pre_wrap - (state[:, 6] - prev[:, 2])) / 360.0).astype(np.int64)
-    soa[W_DRY] = state[:, 8]
-    soa[W_FUEL] = _bits(_fuel_units(state[:, 9], fuel_unit))
+    soa[W_DRY] = _bits(state[:, 8])
+    soa[W_FUEL] = _fuel_units(state[:, 9], fuel_unit)
     soa[W_META] = _meta_bits(np.broadcast_to(np.asarray(steps), (n,)), wraps, False, lo)
-    soa[W_EPRET] = np.broadcast_to(np.asarray(ep_return, np.float32), (n,))
+    soa[W_EPRET] = _bits(np.broadcast_to(np.asarray(ep_return, np.float32), (n,)))
     return soa
 
 
@@ -134,23 +151,24 @@ def reference_view(soa: np.ndarray, dt: float, fuel_unit: float = DEFAULT_FUEL_U
     feeds its reward / termination tests (``delta * 2^-23 * (1/dt)``, ``units * 360/2^32``), so
     that the reference's decision functions evaluated on this view agree with the kernel's flags
     bit for bit."""
-    soa = np.asarray(soa, np.float32)
+    soa = as_words(soa)
     meta = soa[W_META].view(np.uint32)
     fresh = (meta & META_FRESH) != 0
     wraps = ((meta >> META_WRAP_SHIFT) & 7).astype(np.int64)
     wraps = np.where(wraps >= 4, wraps - 8, wraps)
     inv_dt = np.float32(1.0 / dt)
     unit = np.float32(1.0 / DELTA_UNITS_PER_M)
+    f = lambda w: soa[w].view(np.float32)                                   # noqa: E731
 
     def vel(w):
-        delta = soa[w].view(np.int32).astype(np.float32) * unit
-        return np.where(fresh, soa[w], delta * inv_dt).astype(np.float64)
+        delta = soa[w].astype(np.float32) * unit
+        return np.where(fresh, f(w), delta * inv_dt).astype(np.float64)
 
-    ang = soa[W_ANGLE].view(np.int32).astype(np.float32) * np.float32(1.0 / ANGLE_UNITS_PER_DEG)
-    om = np.where(fresh, soa[W_SANGLE], soa[W_SANGLE] * inv_dt).astype(np.float64)
-    return {"x": soa[W_X].astype(np.float64), "y": soa[W_Y].astype(np.float64),
+    ang = soa[W_ANGLE].astype(np.float32) * np.float32(1.0 / ANGLE_UNITS_PER_DEG)
+    om = np.where(fresh, f(W_SANGLE), f(W_SANGLE) * inv_dt).astype(np.float64)
+    return {"x": f(W_X).astype(np.float64), "y": f(W_Y).astype(np.float64),
             "vx": vel(W_SX), "vy": vel(W_SY), "angle": ang.astype(np.float64),
-            "ang_vel": om, "dry_mass": soa[W_DRY].astype(np.float64),
-            "fuel": soa[W_FUEL].view(np.int32).astype(np.float64) * fuel_unit,
+            "ang_vel": om, "dry_mass": f(W_DRY).astype(np.float64),
+            "fuel": soa[W_FUEL].astype(np.float64) * fuel_unit,
             "steps": (meta & META_STEP_MASK).astype(np.int64),
-            "fresh": fresh, "wraps": wraps, "ep_return": soa[W_EPRET].astype(np.float64)}
+            "fresh": fresh, "wraps": wraps, "ep_return": f(W_EPRET).astype(np.float64)}

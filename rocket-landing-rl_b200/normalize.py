@@ -35,13 +35,23 @@ def read_sb3_vecnormalize(path: str) -> dict:
         def __setstate__(self, state):
             self.__dict__.update(state if isinstance(state, dict) else {"state": state})
 
+    # exact (module, name) pairs a VecNormalize pickle needs besides the stand-ins; anything else --
+    # builtins.eval / exec / getattr / __import__ included -- is refused
+    allowed = {("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.multiarray", "_reconstruct"),
+               ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "_reconstruct"),
+               ("numpy._core.multiarray", "scalar"), ("numpy.core.numeric", "_frombuffer"),
+               ("numpy._core.numeric", "_frombuffer"), ("collections", "OrderedDict"),
+               ("builtins", "tuple"), ("builtins", "list"), ("builtins", "dict"), ("builtins", "set"),
+               ("builtins", "frozenset"), ("builtins", "slice"), ("builtins", "complex"),
+               ("builtins", "bytearray"), ("builtins", "object")}
+
     class _Unpickler(pickle.Unpickler):
         def find_class(self, module, name):
-            if module.startswith(("stable_baselines3", "gymnasium")):
+            if module.split(".")[0] in ("stable_baselines3", "gymnasium", "gym"):
                 return _Bag
-            if module.startswith("numpy") or module in ("builtins", "collections"):
+            if (module, name) in allowed:
                 return super().find_class(module, name)
-            raise pickle.UnpicklingError(f"unexpected global {module}.{name} in {path}")
+            raise pickle.UnpicklingError(f"refusing global {module}.{name} in {path}")
 
     with open(path, "rb") as fh:
         vn = _Unpickler(fh).load()

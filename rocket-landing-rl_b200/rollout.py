@@ -133,13 +133,15 @@ class FusedActorCritic:
     collection does not need gradients).  Call ``refresh()`` after the wrapped module's parameters
     change (an optimiser step) to re-pack the weights."""
 
-    def __init__(self, net: ActorCriticMLP, device="cuda", seed: int = 0, low=(0.0, -1.0), high=(1.0, 1.0)):
+    def __init__(self, net: ActorCriticMLP, device="cuda", seed: int = 0, low=(0.0, -1.0), high=(1.0, 1.0),
+                 row_offset: int = 0):
         import ctypes as C
         self._L = _lib.load()
         self.net = net
         self.device = torch.device(device)
         self.seed = int(seed) & (2**64 - 1)
         self.draw = 0                                   # Philox counter word: one per forward() call
+        self.row_offset = int(row_offset)               # global id of row 0 (the shard's env_id_offset)
         self._low = (C.c_float * 2)(*low)               # the env's Box (lander.py:65-69)
         self._high = (C.c_float * 2)(*high)
         assert int(self._L.rl_mlp_blob_bytes()) == MLP_BLOB_BYTES
@@ -188,7 +190,7 @@ class FusedActorCritic:
         mean = torch.empty((n, 2), **f32) if want_mean else None
         assert actions.is_contiguous() and log_prob.is_contiguous()
         rc = self._L.rl_policy_sample(self._pi.data_ptr(), obs.data_ptr(), self._log_std.data_ptr(), self.seed, self.draw,
-                                      self._low, self._high, actions.data_ptr(), clipped.data_ptr(), log_prob.data_ptr(),
+                                      self.row_offset, self._low, self._high, actions.data_ptr(), clipped.data_ptr(), log_prob.data_ptr(),
                                       mean.data_ptr() if mean is not None else None, n,
                                       torch.cuda.current_stream(obs.device).cuda_stream)
         if rc != 0:

@@ -47,8 +47,12 @@ class RocketSimulation:
         _lib.check(self._L.rl_reset_host(self._h, self._obs.ctypes.data), "rl_reset_host")
         return self._obs.copy()
 
-    def set_state(self, state_soa: np.ndarray) -> None:
-        t = torch.from_numpy(np.ascontiguousarray(state_soa, np.float32)).cuda()
+    def set_state(self, state_words: np.ndarray) -> None:
+        """Public state words, int32 [10, N] (``layout.fresh_state_soa``)."""
+        w = np.asarray(state_words)
+        if w.dtype != np.int32:
+            raise TypeError("state words must be int32 [10, N]")
+        t = torch.from_numpy(np.ascontiguousarray(w)).cuda()
         _lib.check(self._L.rl_set_state(self._h, t.data_ptr(), None, None), "rl_set_state")
         torch.cuda.synchronize()
 

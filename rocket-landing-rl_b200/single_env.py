@@ -50,7 +50,8 @@ class RocketLandingEnv:
         self._rew = np.zeros((1,), np.float32)
         self._term = np.zeros((1,), np.uint8)
         self._trunc = np.zeros((1,), np.uint8)
-        self._soa = np.zeros((10, 1), np.float32)
+        self._soa = np.zeros((10, 1), np.int32)
+        self._raw_accel = np.zeros((1, 2), np.float32)
         self._accel = (0.0, 0.0)            # ax, ay of the last step (or the sampled ones after a reset)
 
     # ---- the reference's surface ------------------------------------------------------------
@@ -68,10 +69,11 @@ class RocketLandingEnv:
         self._act[0] = a
         _lib.check(self._L.rl_step_host(self._h, self._act.ctypes.data, self._obs.ctypes.data, self._rew.ctypes.data,
                                         self._term.ctypes.data, self._trunc.ctypes.data, None, None, None, None,
-                                        1, 0), "rl_step_host")        # one substep, no auto-reset
+                                        self._raw_accel.ctypes.data, 1, 0), "rl_step_host")   # one substep, no auto-reset
         self.current_step += 1
         obs = self._obs[0].copy()
-        self._accel = (float(obs[4]), float(obs[5]))     # clipped to +-5 by the observation; raw_state reports these
+        # raw_state carries the UNCLIPPED accelerations of the step (lander.py:157-166; the observation clips to +-5)
+        self._accel = (float(self._raw_accel[0, 0]), float(self._raw_accel[0, 1]))
         return obs, float(self._rew[0]), bool(self._term[0]), bool(self._trunc[0]), self._get_info()
 
     def _get_info(self) -> Dict[str, Any]:

@@ -94,7 +94,7 @@ class RocketLandingSB3VecEnv:
             extra = (None, None, None, None)
         _lib.check(self._L.rl_step_host(
             self._h, self._actions.ctypes.data, self._obs.ctypes.data, self._rew.ctypes.data,
-            self._term.ctypes.data, self._trunc.ctypes.data, *extra, self.substeps, 1), "rl_step_host")
+            self._term.ctypes.data, self._trunc.ctypes.data, *extra, None, self.substeps, 1), "rl_step_host")
         dones = (self._term | self._trunc).astype(bool)
         infos: List[Dict[str, Any]] = self._infos(dones) if self.build_infos else []
         return self._obs.copy(), self._rew.copy(), dones, infos
@@ -108,7 +108,7 @@ class RocketLandingSB3VecEnv:
         output buffers (overwritten by the next call) and no per-rocket dicts."""
         _lib.check(self._L.rl_step_host(
             self._h, actions.ctypes.data, self._obs.ctypes.data, self._rew.ctypes.data,
-            self._term.ctypes.data, self._trunc.ctypes.data, None, None, None, None,
+            self._term.ctypes.data, self._trunc.ctypes.data, None, None, None, None, None,
             self.substeps, 1), "rl_step_host")
         return self._obs, self._rew, self._term, self._trunc
 

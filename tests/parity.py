@@ -102,7 +102,7 @@ class HostEmuStepper:
         self.params = params or load_params()
         self.dt = self.params.time_step
         self.fuel_unit = layout.fuel_unit_for(self.params.reset_high[9])
-        self.soa = np.zeros((10, n), np.float32)
+        self.soa = np.zeros((10, n), np.int32)
 
     def inject_fresh(self, states: np.ndarray, mask=None, steps=0) -> None:
         new = _fresh_soa(states, steps, self.fuel_unit)
@@ -112,7 +112,7 @@ class HostEmuStepper:
             self.soa[:, mask] = new[:, mask]
 
     def inject_soa(self, soa: np.ndarray) -> None:
-        self.soa[:] = soa
+        self.soa[:] = layout.as_words(soa)
 
     def step(self, actions: np.ndarray, substeps: int = 1):
         a = np.ascontiguousarray(actions, np.float32)
@@ -163,7 +163,7 @@ class GpuStepper:
                            None if mask is None else self.torch.from_numpy(np.asarray(mask, np.uint8)))
 
     def inject_soa(self, soa: np.ndarray) -> None:
-        self.env.set_state(self.torch.from_numpy(np.ascontiguousarray(soa, np.float32)))
+        self.env.set_state(self.torch.from_numpy(layout.as_words(soa)))
 
     def step(self, actions: np.ndarray, substeps: int = 1):
         self.env.substeps = substeps

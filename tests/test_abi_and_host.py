@@ -89,7 +89,7 @@ def test_create_fails_loudly_without_gpu_or_with_bad_args():
             pkg.RocketLandingVecEnv(16)
         with pytest.raises(_lib.RocketLibraryError):
             pkg.RocketLandingSB3VecEnv(16)
-    assert lib.rl_step(None, None, None, None, None, None, None, None, None, None, 1, 1, None) == -1
+    assert lib.rl_step(None, None, None, None, None, None, None, None, None, None, None, 1, 1, None) == -1
 
 
 def test_product_never_imports_the_oracle():

@@ -202,10 +202,8 @@ def test_plain_fp32_accumulators_would_drift():
         soa = st.soa
         # degrade: deltas, angle, fuel, angle-delta extension back to 24 significant bits
         for w in (L.W_SX, L.W_SY, L.W_ANGLE, L.W_FUEL):
-            v = soa[w].view(np.int32)
-            soa[w] = v.astype(np.float32).astype(np.int64).clip(-2**31, 2**31 - 1).astype(np.int32).view(np.float32)
-        meta = soa[L.W_META].view(np.uint32)
-        soa[L.W_META] = (meta & ~np.uint32(0xFF << L.META_DLO_SHIFT)).view(np.float32)
+            soa[w] = soa[w].astype(np.float32).astype(np.int64).clip(-2**31, 2**31 - 1).astype(np.int32)
+        soa[L.W_META] &= ~np.int32(0xFF << L.META_DLO_SHIFT)
         err = np.abs(st.view()["vx"] - orc.rockets["vx"]) / (parity.RTOL * np.maximum(np.abs(orc.rockets["vx"]), 25.0))
         worst = max(worst, float(err.max()))
     assert worst > 1.5, worst

@@ -291,6 +291,152 @@ def test_host_buffer_vecenv_api_matches_device_api(torch, monkeypatch, small_hos
     dev.close()
 
 
+def test_device_and_host_api_interleave_on_one_handle(torch):
+    """The device API enqueues on the caller's stream, the host API runs on private streams of the
+    handle (include/rocket_landing_b200.h, "Conventions"): a host-API call must see everything the
+    device API enqueued before it, with no synchronisation by the caller.  A long dependent chain
+    is enqueued on a side stream (a slow kernel first, so that the work is still pending when the
+    host call arrives), then the state is read through rl_get_state_host / stepped through
+    rl_step_host and compared with a twin driven through one API only."""
+    import ctypes as C
+    from rocket_landing_rl_b200 import RocketLandingVecEnv, _lib
+    L = _lib.load()
+    n = 1 << 16
+    mixed = RocketLandingVecEnv(n, seed=41)
+    twin = RocketLandingVecEnv(n, seed=41)
+    side = torch.cuda.Stream()
+    gen = torch.Generator(device="cuda").manual_seed(6)
+    acts = [_rand_actions(torch, n, gen) for _ in range(24)]
+    big = torch.randn((8192, 8192), device="cuda")
+    twin.reset()
+    for a in acts:
+        twin.step(a)
+    want_state = twin.get_state().cpu().numpy()
+    host_a = acts[0].cpu().numpy().copy()
+    want = [x.cpu().numpy().copy() for x in twin.step(acts[0])[:4]]
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        for _ in range(6):
+            big = big @ big * 1e-4                      # ~50 ms of work ahead of the env kernels on `side`
+        mixed.reset()
+        for a in acts:
+            mixed.step(a)
+    # no synchronisation here: the host API must order itself after `side`
+    got_state = np.zeros((10, n), np.int32)
+    _lib.check(L.rl_get_state_host(mixed._h, got_state.ctypes.data), "rl_get_state_host")
+    np.testing.assert_array_equal(got_state, want_state)
+    obs, rew = np.zeros((n, 8), np.float32), np.zeros(n, np.float32)
+    te, tr = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    _lib.check(L.rl_step_host(mixed._h, host_a.ctypes.data, obs.ctypes.data, rew.ctypes.data, te.ctypes.data,
+                              tr.ctypes.data, None, None, None, None, None, 1, 1), "rl_step_host")
+    np.testing.assert_array_equal(obs, want[0])
+    np.testing.assert_array_equal(rew, want[1])
+    np.testing.assert_array_equal(te.astype(bool), want[2])
+    # ... and back: a device-API call after the (synchronous) host call continues the same trajectory
+    with torch.cuda.stream(side):
+        o2 = mixed.step(acts[1])[0].clone()
+    side.synchronize()
+    assert torch.equal(o2, twin.step(acts[1])[0])
+    assert mixed._L.rl_get_epoch(mixed._h) == twin._L.rl_get_epoch(twin._h) == 27      # 1 reset + 26 steps
+    mixed.close()
+    twin.close()
+
+
+def test_reset_distribution_on_the_gpu(torch):
+    """a1, get_initial_state (simulation/config.py:20-53, config.yaml:53-67): ten independent
+    uniforms.  Through rl_reset AND through the in-step auto-reset, at 1 Mi rockets: per-word
+    Kolmogorov-Smirnov distance against the uniform on the config range, pairwise independence
+    of the ten words, and no draw repeated across (global id, epoch)."""
+    from rocket_landing_rl_b200 import RocketLandingVecEnv, layout
+    n = 1 << 20
+    p = RocketLandingVecEnv(8).params
+    lo = np.array(list(p.reset_low))
+    hi = np.array(list(p.reset_high))
+
+    def words(env, obs):
+        v = env.get_reference_state()
+        o = obs.cpu().numpy().astype(np.float64)
+        assert v["fresh"].all() and (v["steps"] == 0).all()
+        # x y vx vy (state) ax ay (only ever in the reset observation, Q10) angle omega dry fuel
+        return np.stack([v["x"], v["y"], v["vx"], v["vy"], o[:, 4], o[:, 5], v["angle"], v["ang_vel"],
+                         v["dry_mass"], v["fuel"]], axis=1)
+
+    def check(w, tag):
+        u = (w - lo) / (hi - lo)
+        assert u.min() >= 0.0 and u.max() <= 1.0, tag
+        m = u.shape[0]
+        grid = (np.arange(m) + 0.5) / m
+        for k in range(10):
+            ks = np.abs(np.sort(u[:, k]) - grid).max()
+            assert ks < 1.95 / np.sqrt(m), (tag, k, ks)            # P(KS > 1.95 / sqrt(m)) = 0.1 % per word
+        c = np.corrcoef(u.T)
+        assert np.abs(c - np.eye(10)).max() < 5.0 / np.sqrt(m), (tag, np.abs(c - np.eye(10)).max())
+        return u
+
+    env = RocketLandingVecEnv(n, seed=2024, env_id_offset=5_000_000)
+    obs, _ = env.reset()
+    w0 = words(env, obs)
+    u0 = check(w0, "rl_reset epoch 0")
+    obs, _ = env.reset()
+    w1 = words(env, obs)
+    check(w1, "rl_reset epoch 1")
+    # uniqueness across (id, epoch): the 24-bit x draws of two epochs coincide for ~n / 2^24 rockets by chance
+    assert (w0[:, 0] == w1[:, 0]).mean() < 3.0 / (1 << 24) + 1e-5
+    assert np.unique(np.round(u0[:, :4] * (1 << 24)).astype(np.int64), axis=0).shape[0] == n   # no two rockets alike
+    # auto-reset inside the step: collect the FRESH rockets of many steps
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    got = []
+    a = _rand_actions(torch, n, gen)
+    for t in range(140):
+        obs, _, term, trunc, _ = env.step(a)
+        if t >= 80:
+            done = (term | trunc).cpu().numpy()
+            if done.any():
+                v = env.get_reference_state()
+                o = obs.cpu().numpy().astype(np.float64)
+                got.append(np.stack([v["x"], v["y"], v["vx"], v["vy"], o[:, 4], o[:, 5], v["angle"], v["ang_vel"],
+                                     v["dry_mass"], v["fuel"]], axis=1)[done])
+    wa = np.concatenate(got)
+    assert wa.shape[0] > 200_000
+    check(wa, "auto-reset")
+    # a shard with the same seed and ids reproduces the words exactly; another seed does not
+    same = RocketLandingVecEnv(4096, seed=2024, env_id_offset=5_000_000)
+    np.testing.assert_array_equal(words(same, same.reset()[0]), w0[:4096])
+    other = RocketLandingVecEnv(4096, seed=2025, env_id_offset=5_000_000)
+    assert (words(other, other.reset()[0])[:, 0] != w0[:4096, 0]).mean() > 0.99
+    for e in (env, same, other):
+        e.close()
+
+
+def test_batched_raw_state_matches_the_oracle(torch):
+    """lander.py:157-166: info["raw_state"] of EVERY rocket after a step, the unclipped ax / ay
+    included (the observation clips them to +-5 while ay reaches +15 under thrust)."""
+    from rocket_landing_rl_b200 import RocketLandingVecEnv
+    n = 4096
+    env = RocketLandingVecEnv(n, seed=9, auto_reset=False, raw_state=True)
+    orc = c_oracle.BatchOracle(n)
+    rng = np.random.default_rng(1)
+    init = parity.sample_reset_states(rng, env.params, n)
+    env.set_state(torch.from_numpy(parity._fresh_soa(init, 0, env.fuel_unit)))
+    orc.inject(init)
+    big = 0
+    for t in range(40):
+        a = rng.uniform([0, -1], [1, 1], (n, 2)).astype(np.float32)
+        _, _, _, _, info = env.step(torch.from_numpy(a).cuda())
+        orc.step(a)
+        rs = env.raw_state()
+        ref = orc.state()
+        for k_, col, sc in (("x", 0, 1500.0), ("y", 1, 2000.0), ("vx", 2, 25.0), ("vy", 3, 200.0), ("ax", 4, 10.0),
+                            ("ay", 5, 10.0), ("angle", 6, 15.0), ("angularVelocity", 7, 10.0), ("mass", 8, 36000.0),
+                            ("fuelMass", 9, 390000.0)):
+            tol = parity.RTOL * np.maximum(np.abs(ref[:, col]), sc)
+            assert (np.abs(rs[k_] - ref[:, col]) <= tol).all(), (t, k_)
+        big += int((np.abs(rs["ay"]) > 5.0).sum())
+        np.testing.assert_allclose(rs["totalMass"], ref[:, 8] + ref[:, 9], rtol=1e-6)
+    assert big > 1000            # the unclipped values really are beyond the observation's +-5
+    env.close()
+
+
 def test_error_paths_through_the_abi(torch):
     from rocket_landing_rl_b200 import RocketLandingVecEnv, _lib
     env = RocketLandingVecEnv(64)

@@ -156,6 +156,44 @@ def test_fused_action_sampling():
 
 
 @pytest.mark.gpu
+def test_policy_noise_is_independent_of_the_reset_stream_for_equal_seeds():
+    """Both streams are Philox4x32-10 and both default to seed 0.  With the SAME key the policy's
+    counter (row, draw, 0) would coincide with the reset's counter (global id, epoch, block 0)
+    whenever draw == epoch -- which is exactly the first action of every episode in collect_rollout
+    -- making the exploration noise a function of the initial x, y the policy observes.  The
+    policy's key carries a domain tag: its uniforms must be uncorrelated with the reset's, and
+    shards that share a seed must draw different noise (row_offset)."""
+    import torch
+    from rocket_landing_rl_b200 import ActorCriticMLP, FusedActorCritic, RocketLandingVecEnv
+    n = 1 << 17
+    net = ActorCriticMLP(log_std_init=0.0).cuda()
+    with torch.no_grad():
+        for p_ in net.parameters():
+            p_.zero_()                                    # mean 0, std 1: actions == the noise itself
+    obs = torch.zeros((n, 8), device="cuda")
+    for epoch in (0, 3):
+        env = RocketLandingVecEnv(n, seed=0, auto_reset=False)
+        for _ in range(epoch + 1):
+            reset_obs = env.reset()[0].clone()            # the reset at launch epoch `epoch`
+        env.close()
+        ux = (reset_obs[:, 0] + 1500.0) / 3000.0          # u01(w[0]) of Philox block 0 (config.yaml:53)
+        uy = (reset_obs[:, 1] - 1800.0) / 400.0           # u01(w[1])
+        fused = FusedActorCritic(net, seed=0)
+        fused.draw = epoch
+        z, _, _, _ = fused.act(obs)
+        u1 = torch.exp(-0.5 * (z * z).sum(-1))            # Box-Muller radius -> its uniform
+        u2 = (torch.atan2(z[:, 1], z[:, 0]) / (2 * torch.pi)) % 1.0
+        for a_, b_ in ((u1, ux), (u2, uy), (u1, uy), (u2, ux)):
+            c = float(torch.corrcoef(torch.stack([a_, b_]))[0, 1])
+            assert abs(c) < 0.02, (epoch, c)              # same key: |c| = 1
+    shard = FusedActorCritic(net, seed=0, row_offset=n // 2)
+    whole = FusedActorCritic(net, seed=0)
+    zw, _, _, _ = whole.act(obs)
+    zs, _, _, _ = shard.act(obs[: n // 2].contiguous())
+    assert torch.equal(zs, zw[n // 2:]) and not torch.equal(zs, zw[: n // 2])
+
+
+@pytest.mark.gpu
 def test_time_limit_bootstrap_is_resolved_one_step_late_but_exactly():
     """collect_rollout adds gamma V(terminal observation) to the reward of steps that end by the time
     limit (SB3's TimeLimit.truncated handling) without a host synchronisation per step: the "any

@@ -54,6 +54,9 @@ def test_episodes_beside_the_oracle():
             assert np.all(np.abs(obs - wobs) <= parity.RTOL * np.maximum(np.abs(wobs), scale)), (episode, t)
             assert abs(rew - wrew) <= max(parity.FREE_REWARD_ATOL, parity.FREE_REWARD_RTOL * abs(wrew))
             assert info["steps"] == winfo["steps"]
+            # info["raw_state"] carries the UNCLIPPED accelerations (the engine fires: ay reaches +15 m/s^2)
+            for k_ in ("ax", "ay"):
+                assert abs(info["raw_state"][k_] - winfo["raw_state"][k_]) <= parity.RTOL * max(abs(winfo["raw_state"][k_]), 10.0)
             if term or trunc:
                 break
         assert term and 60 < t < 200          # random actions: every episode ends on the ground
