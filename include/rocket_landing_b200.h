@@ -58,11 +58,11 @@ extern "C" {
 #define RL_W_Y 1        /* f32  m                                                              */
 #define RL_W_ANGLE 2    /* i32  units of 360 / 2^32 deg: int32 range == [-180, 180), so integer
                            wrap-around IS normalize_angle_180 (engine.py:230)                  */
-#define RL_W_SX 3       /* i32  carried x delta x(t) - x(t-dt), units of 2^-23 m;
-                           f32 bits of vx itself while FRESH                                   */
-#define RL_W_SY 4       /* i32  carried y delta, units of 2^-23 m; f32 bits of vy while FRESH  */
+#define RL_W_SX 3       /* i32  carried x delta x(t) - x(t-dt), units of 2^-23 m, so vx = delta / dt
+                           (engine.py:193-194); while FRESH: vx dt                             */
+#define RL_W_SY 4       /* i32  carried y delta, units of 2^-23 m; while FRESH: vy dt          */
 #define RL_W_SANGLE 5   /* f32  carried pre-wrap angle delta in deg (high part; 8 more bits in
-                           RL_W_META); angular velocity in deg/s while FRESH                   */
+                           RL_W_META), so omega = delta / dt; while FRESH: omega dt            */
 #define RL_W_DRY 6      /* f32  kg                                                             */
 #define RL_W_FUEL 7     /* i32  units of rl_fuel_unit() kg (2^-12 kg for the reference config) */
 #define RL_W_META 8     /* u32 bits: [0,16) episode step count (lander.py:229),
@@ -72,8 +72,8 @@ extern "C" {
                            normalisation (engine.py:226 stores the normalised angle as the
                            next step's "previous" angle, base.py:171),
                            [27,30) landing code and bit 30 "landed" (simulation mode only),
-                           bit 31 FRESH = just reset, Verlet bootstrap (base.py:65) not
-                           applied yet                                                         */
+                           bit 31 FRESH = just reset: the first step still has to subtract the
+                           Verlet bootstrap term a0 dt^2 / 2 from the deltas (base.py:65-130)  */
 #define RL_W_EPRET 9    /* f32  running episode return                                         */
 
 #define RL_META_STEP_MASK 0x0000FFFFu

@@ -44,8 +44,8 @@ namespace rl {
 struct Rocket {                // the ten persistent words (RL_W_*)
     float x, y;
     int32_t ang;               // units of kAngleUnit deg
-    uint32_t sx, sy;           // int32 deltas in units of kDeltaUnit m; fp32 bits of vx, vy while FRESH
-    float sang;                // carried pre-wrap angle delta (high part); angular velocity while FRESH
+    int32_t sx, sy;            // x - x_prev, y - y_prev in units of kDeltaUnit m (v dt while FRESH: bootstrap pending)
+    float sang;                // carried pre-wrap angle delta, high part (omega dt while FRESH)
     float dry;
     int32_t fuel;              // units of P.fuel_unit_d kg (signed: an injected negative load acts like the
                                // reference's, base.py:138-144)
@@ -178,39 +178,6 @@ __device__ __forceinline__ uint4 reset_counter(uint64_t gid, uint64_t epoch, uin
 // 24 random bits -> [0, 1) exactly representable in fp32
 __device__ __forceinline__ float u01(uint32_t bits) { return (float)(bits >> 8) * 5.9604644775390625e-8f; }
 
-// get_initial_state (simulation/config.py:26-53): ten independent uniforms lo + span u, in the
-// reference's draw order x, y, vx, vy, ax, ay, angle, angular velocity, dry mass, fuel mass, from
-// the ten random words w[0..9].  Returns the sampled ax, ay (they only ever appear in the reset
-// observation, lander.py:182).
-template <class PP>
-__device__ __forceinline__ void rocket_from_words(const PP& P, const uint32_t* w, Rocket& r,
-                                                  float& ax0, float& ay0) {
-    r.x = fmaf(P.reset_span(0), u01(w[0]), P.reset_lo(0));
-    r.y = fmaf(P.reset_span(1), u01(w[1]), P.reset_lo(1));
-    r.sx = rl_f2u(fmaf(P.reset_span(2), u01(w[2]), P.reset_lo(2)));      // vx while FRESH
-    r.sy = rl_f2u(fmaf(P.reset_span(3), u01(w[3]), P.reset_lo(3)));      // vy while FRESH
-    ax0 = fmaf(P.reset_span(4), u01(w[4]), P.reset_lo(4));
-    ay0 = fmaf(P.reset_span(5), u01(w[5]), P.reset_lo(5));
-    r.ang = rl_f2i(fmaf(P.reset_span(6), u01(w[6]), P.reset_lo(6)) * (float)kAngleInvUnit);
-    r.sang = fmaf(P.reset_span(7), u01(w[7]), P.reset_lo(7));    // angular velocity while FRESH
-    r.dry = fmaf(P.reset_span(8), u01(w[8]), P.reset_lo(8));
-    r.fuel = rl_f2i(fmaf(P.reset_span(9), u01(w[9]), P.reset_lo(9)) * P.fuel_inv_unit);
-    r.ep_ret = 0.0f;
-    r.meta = RL_META_FRESH;                                      // current_step = 0 (lander.py:180)
-}
-
-// One thread draws all three Philox blocks keyed by (seed, global rocket id, epoch).
-template <class PP>
-__device__ __forceinline__ void sample_reset(const PP& P, uint64_t seed, uint64_t gid,
-                                             uint64_t epoch, Rocket& r, float& ax0, float& ay0) {
-    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
-    const uint4 a = philox4x32_10(reset_counter(gid, epoch, 0u), key);
-    const uint4 b = philox4x32_10(reset_counter(gid, epoch, 1u), key);
-    const uint4 c = philox4x32_10(reset_counter(gid, epoch, 2u), key);
-    const uint32_t w[10] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
-    rocket_from_words(P, w, r, ax0, ay0);
-}
-
 __device__ __forceinline__ float clipf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
 // _get_obs (lander.py:124-150)
@@ -227,11 +194,48 @@ __device__ __forceinline__ void clip_obs(const PP& P, float x, float y, float vx
     obs[7] = clipf(om, P.obs_lo(7), P.obs_hi(7));
 }
 
-// Observation of a FRESH rocket (reset observation).
+// get_initial_state (simulation/config.py:26-53): ten independent uniforms lo + span u, in the
+// reference's draw order x, y, vx, vy, ax, ay, angle, angular velocity, dry mass, fuel mass, from
+// the ten random words w[0..9].  Writes the clipped reset observation (lander.py:182: the sampled
+// ax, ay only ever appear there) when obs != nullptr.
+// A FRESH rocket carries v dt in its delta slots (so v = delta / dt like any other rocket) and
+// omega dt in the angle-delta slot; the Verlet bootstrap correction -a0 dt^2 / 2 (base.py:65-130) is
+// applied by its first step, which evaluates the zero-control acceleration a0 anyway.
 template <class PP>
-__device__ __forceinline__ void fresh_obs(const PP& P, const Rocket& r, float ax0, float ay0,
-                                          float* obs) {
-    clip_obs(P, r.x, r.y, rl_u2f(r.sx), rl_u2f(r.sy), ax0, ay0, angle_deg(r.ang), r.sang, obs);
+__device__ __forceinline__ void rocket_from_words(const PP& P, const uint32_t* w, Rocket& r, float* obs) {
+    const float vx = fmaf(P.reset_span(2), u01(w[2]), P.reset_lo(2));
+    const float vy = fmaf(P.reset_span(3), u01(w[3]), P.reset_lo(3));
+    const float ax0 = fmaf(P.reset_span(4), u01(w[4]), P.reset_lo(4));
+    const float ay0 = fmaf(P.reset_span(5), u01(w[5]), P.reset_lo(5));
+    const float ang = fmaf(P.reset_span(6), u01(w[6]), P.reset_lo(6));
+    const float om = fmaf(P.reset_span(7), u01(w[7]), P.reset_lo(7));
+    r.x = fmaf(P.reset_span(0), u01(w[0]), P.reset_lo(0));
+    r.y = fmaf(P.reset_span(1), u01(w[1]), P.reset_lo(1));
+    r.sx = rl_f2i(vx * P.dt_units);
+    r.sy = rl_f2i(vy * P.dt_units);
+    r.ang = rl_f2i(ang * (float)kAngleInvUnit);
+    r.sang = om * P.dt;
+    r.dry = fmaf(P.reset_span(8), u01(w[8]), P.reset_lo(8));
+    r.fuel = rl_f2i(fmaf(P.reset_span(9), u01(w[9]), P.reset_lo(9)) * P.fuel_inv_unit);
+    r.ep_ret = 0.0f;
+    r.meta = RL_META_FRESH;                                      // current_step = 0 (lander.py:180)
+    // the observation reads the STORED words back (as lander.py:124-150 reads Rocket.state), so it is
+    // exactly the state the first step starts from
+    if (obs)
+        clip_obs(P, r.x, r.y, ((float)r.sx * (float)kDeltaUnit) * P.inv_dt, ((float)r.sy * (float)kDeltaUnit) * P.inv_dt,
+                 ax0, ay0, angle_deg(r.ang), r.sang * P.inv_dt, obs);
+}
+
+// One thread draws all three Philox blocks keyed by (seed, global rocket id, epoch).
+template <class PP>
+__device__ __forceinline__ void sample_reset(const PP& P, uint64_t seed, uint64_t gid,
+                                             uint64_t epoch, Rocket& r, float* obs) {
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint4 a = philox4x32_10(reset_counter(gid, epoch, 0u), key);
+    const uint4 b = philox4x32_10(reset_counter(gid, epoch, 1u), key);
+    const uint4 c = philox4x32_10(reset_counter(gid, epoch, 2u), key);
+    const uint32_t w[10] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
+    rocket_from_words(P, w, r, obs);
 }
 
 // Potential of reward.py:231-264.
@@ -273,11 +277,9 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_
 
     // ---- state before the action (Rocket.get_state, base.py:220) --------------------------
     const float y_b = r.y, ang_b = angle_deg(r.ang);
-    const float dx_b = (float)(int32_t)r.sx * (float)kDeltaUnit;     // (the scaling is exact)
-    const float dy_b = (float)(int32_t)r.sy * (float)kDeltaUnit;
-    const float vx_b = fresh ? rl_u2f(r.sx) : dx_b * P.inv_dt;       // slots hold v while FRESH, deltas after
-    const float vy_b = fresh ? rl_u2f(r.sy) : dy_b * P.inv_dt;
-    const float om_b = fresh ? r.sang : r.sang * P.inv_dt;
+    const float vx_b = ((float)r.sx * (float)kDeltaUnit) * P.inv_dt;        // v = delta / dt (engine.py:193-194);
+    const float vy_b = ((float)r.sy * (float)kDeltaUnit) * P.inv_dt;        // the unit scaling is exact
+    const float om_b = r.sang * P.inv_dt;
 
     // ---- Rocket.apply_action (base.py:132-184) -----------------------------------------------
     const int32_t fuel_now = r.fuel;
@@ -308,19 +310,19 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_
         alpha = torque ? cg * P.alpha_k * inv_m : 0.0f;        // (telemetry only)
 
         // carried deltas (x - x_prev, y - y_prev in fixed point; angle - angle_prev in fp64)
-        int32_t dx = (int32_t)r.sx, dy = (int32_t)r.sy;
+        int32_t dx = r.sx, dy = r.sy;
         double dang_d = dtheta_join(r.sang, lo_prev);
         if (k_prev != 0) dang_d -= 360.0 * (double)k_prev;     // both angles normalised (base.py:171)
         if (fresh) {
-            // Verlet bootstrap (base.py:65-130): x - x_prev = v dt - a0 dt^2 / 2 and, alpha0 being 0,
-            // angle - angle_prev = omega dt, the previous angle normalised (base.py:117).  In fp64:
-            // whatever is lost here stays in the velocity for the whole episode.
-            const double dtd = P.dt_d, h = 0.5 * dtd * dtd;
-            dx = rl_d2i(((double)vx_b * dtd - h * (double)a0x) * kDeltaInvUnit);
-            dy = rl_d2i(((double)vy_b * dtd - h * (double)a0y) * kDeltaInvUnit);
-            const double back = dang_d * dtd;                  // (the slot holds omega, all 32 bits of it)
-            const double prev = (double)r.ang * kAngleUnit - back;
-            dang_d = back + 360.0 * floor((prev + 180.0) * (1.0 / 360.0));
+            // Verlet bootstrap (base.py:65-130): x - x_prev = v dt - a0 dt^2 / 2 (the slots hold v dt)
+            // and, alpha0 being 0, angle - angle_prev = omega dt with the previous angle normalised
+            // (base.py:117), which only matters within one step of +-180
+            dx -= rl_f2i(a0x * P.half_dt2_units);
+            dy -= rl_f2i(a0y * P.half_dt2_units);
+            if (!(fabsf(ang_b) + fabsf(r.sang) < 179.0f)) {
+                const double prev = (double)r.ang * kAngleUnit - dang_d;
+                dang_d += 360.0 * floor((prev + 180.0) * (1.0 / 360.0));
+            }
         }
         // engine.py:181-222
         const int32_t ndx = dx + rl_f2i(ax * P.dt2_units);
@@ -350,8 +352,8 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_
             k = (int)((sum - (long long)na) >> 32);
             r.ang = na;
         }
-        r.sx = (uint32_t)ndx;
-        r.sy = (uint32_t)ndy;
+        r.sx = ndx;
+        r.sy = ndy;
         r.sang = hi;
         const int32_t burn = rl_f2i(th * P.burn_units);        // engine.py:239-243, base.py:174-175 (th >= 0)
         r.fuel = max(fuel_now - burn, 0);

@@ -203,7 +203,7 @@ __device__ __forceinline__ void stats_flush(BlockStats& s, double* __restrict__ 
 
 __device__ __forceinline__ void unpack_rocket(const float4& a, const float4& b, float fuel_bits, float dry, Rocket& r) {
     r.x = a.x; r.y = a.y; r.ang = __float_as_int(a.z); r.meta = __float_as_uint(a.w);
-    r.sx = __float_as_uint(b.x); r.sy = __float_as_uint(b.y); r.sang = b.z; r.ep_ret = b.w;
+    r.sx = __float_as_int(b.x); r.sy = __float_as_int(b.y); r.sang = b.z; r.ep_ret = b.w;
     r.fuel = __float_as_int(fuel_bits);
     r.dry = dry;
 }
@@ -214,7 +214,7 @@ __device__ __forceinline__ void load_rocket(const StatePlanes& st, uint32_t i, R
 
 __device__ __forceinline__ void store_rocket(const StatePlanes& st, uint32_t i, const Rocket& r, bool write_dry) {
     st.A[i] = make_float4(r.x, r.y, __int_as_float(r.ang), __uint_as_float(r.meta));
-    st.B[i] = make_float4(__uint_as_float(r.sx), __uint_as_float(r.sy), r.sang, r.ep_ret);
+    st.B[i] = make_float4(__int_as_float(r.sx), __int_as_float(r.sy), r.sang, r.ep_ret);
     st.fuel[i] = __int_as_float(r.fuel);
     if (write_dry) st.dry[i] = r.dry;
 }
@@ -293,9 +293,7 @@ __device__ __forceinline__ void warp_episode_end(const PP& P, const StepArgs& a,
             w[6] = __shfl_sync(0xffffffffu, blk.z, 1); w[7] = __shfl_sync(0xffffffffu, blk.w, 1);
             w[8] = __shfl_sync(0xffffffffu, blk.x, 2); w[9] = __shfl_sync(0xffffffffu, blk.y, 2);
             if (lane == src) {
-                float ax0, ay0;
-                rocket_from_words(P, w, r, ax0, ay0);
-                fresh_obs(P, r, ax0, ay0, o.obs);        // SB3 VecEnv contract: return the reset observation
+                rocket_from_words(P, w, r, o.obs);       // SB3 VecEnv contract: return the reset observation
                 a.st.dry[i] = r.dry;                     // dry mass only ever changes here
             }
         }
@@ -433,11 +431,10 @@ __global__ void __launch_bounds__(kCtaThreads) reset_kernel(const __grid_constan
     for (uint32_t i = blockIdx.x * kCtaThreads + threadIdx.x; i < n; i += gridDim.x * kCtaThreads) {
         if (mask && !mask[i]) continue;
         Rocket r;
-        float ax0, ay0, o[8];
-        sample_reset(P, seed, (uint64_t)gid0 + i, epoch, r, ax0, ay0);
+        float o[8];
+        sample_reset(P, seed, (uint64_t)gid0 + i, epoch, r, o);
         store_rocket(st, i, r, true);
         if (obs) {
-            fresh_obs(P, r, ax0, ay0, o);
             obs[2 * (size_t)i] = make_float4(o[0], o[1], o[2], o[3]);
             obs[2 * (size_t)i + 1] = make_float4(o[4], o[5], o[6], o[7]);
         }

@@ -46,6 +46,8 @@ struct DevParams {
     double fuel_unit_d;        // kg per unit of the fixed-point fuel word (a power of two)
     double alpha_min_mass_d;   // fp64 copy of the inertia gate
     float dt2_units;           // dt^2 / kDeltaUnit: acceleration -> fixed-point delta increment
+    float half_dt2_units;      // dt^2 / 2 / kDeltaUnit: Verlet bootstrap correction of a FRESH rocket
+    float dt_units;            // dt / kDeltaUnit: velocity -> fixed-point delta (reset)
     float burn_units;          // fuel_consumption_rate dt / fuel_unit: throttle -> fixed-point burn
     float fuel_inv_unit;       // 1 / fuel_unit (reset: kg -> units)
     float gravity;
@@ -87,6 +89,8 @@ struct DefaultParams {
     static constexpr double fuel_unit_d = 1.0 / 4096.0;               // 410 000 kg < 2^19 -> 2^(19-31)
     static constexpr double alpha_min_mass_d = 1e-6 / (0.5 * 1.85 * 1.85);
     static constexpr float dt2_units = (float)(kDt * kDt * 8388608.0);
+    static constexpr float half_dt2_units = (float)(0.5 * kDt * kDt * 8388608.0);
+    static constexpr float dt_units = (float)(kDt * 8388608.0);
     static constexpr float burn_units = (float)(1700.0 * kDt * 4096.0);
     static constexpr float fuel_inv_unit = 4096.0f;
     static constexpr float inv_dt = (float)(1.0 / kDt);
@@ -133,7 +137,7 @@ inline bool matches_default(const DevParams& d) {
     using D = DefaultParams;
     bool ok = d.dt == D::dt && d.dt_d == D::dt_d && d.damp_d == D::damp_d && d.alpha_dt2_d == D::alpha_dt2_d &&
               d.fuel_unit_d == D::fuel_unit_d && d.alpha_min_mass_d == D::alpha_min_mass_d &&
-              d.dt2_units == D::dt2_units && d.burn_units == D::burn_units && d.fuel_inv_unit == D::fuel_inv_unit && d.inv_dt == D::inv_dt && d.dt2 == D::dt2 && d.half_dt2 == D::half_dt2 &&
+              d.dt2_units == D::dt2_units && d.half_dt2_units == D::half_dt2_units && d.dt_units == D::dt_units && d.burn_units == D::burn_units && d.fuel_inv_unit == D::fuel_inv_unit && d.inv_dt == D::inv_dt && d.dt2 == D::dt2 && d.half_dt2 == D::half_dt2 &&
               d.gravity == D::gravity && d.thrust_power == D::thrust_power && d.drag_k == D::drag_k &&
               d.alpha_k == D::alpha_k && d.alpha_min_mass == D::alpha_min_mass && d.damp == D::damp &&
               d.burn_per_step == D::burn_per_step && d.mass_gate == D::mass_gate &&
@@ -218,6 +222,8 @@ inline int derive_params(const RlParams& p, DevParams& d, char* err, size_t err_
     d.fuel_inv_unit = (float)(1.0 / d.fuel_unit_d);
     d.burn_units = (float)(p.fuel_consumption_rate * dt / d.fuel_unit_d);
     d.dt2_units = (float)(dt * dt / kDeltaUnit);
+    d.half_dt2_units = (float)(0.5 * dt * dt / kDeltaUnit);
+    d.dt_units = (float)(dt / kDeltaUnit);
     d.mass_gate = f32_down(1e-6);
     d.throttle_gate = f32_down(1e-6);
     d.speed2_gate = f32_down(1e-9);

@@ -5,7 +5,8 @@
 The kernel does not store the reference's ``Rocket.state`` dict verbatim: it carries the
 Verlet DELTAS ``x(t) - x(t-dt)`` (from which ``v = delta / dt``, engine.py:193-194) instead of
 ``previous_state`` (base.py:171), and a FRESH flag instead of a bootstrapped previous state
-(base.py:65) -- see DESIGN.md "fp32 formulation".  The words that integrate over an episode are
+(base.py:65): a FRESH rocket's deltas are ``v dt``, and its first step subtracts the bootstrap
+term ``a0 dt^2 / 2`` -- see DESIGN.md "fp32 formulation".  The words that integrate over an episode are
 32-bit FIXED POINT (angle, position deltas, fuel) or carry 8 extra mantissa bits (angle delta),
 DESIGN.md "Long-horizon accuracy".  These helpers convert in both directions, in float64, so
 nothing is lost before the final rounding to the device word.
@@ -93,7 +94,7 @@ def join_angle_delta(hi: np.ndarray, lo: np.ndarray) -> np.ndarray:
 
 
 def fresh_state_soa(x, y, vx, vy, angle, ang_vel, dry_mass, fuel, steps=0, ep_return=0.0,
-                    fuel_unit: float = DEFAULT_FUEL_UNIT) -> np.ndarray:
+                    fuel_unit: float = DEFAULT_FUEL_UNIT, dt: float = 0.1) -> np.ndarray:
     """A just-reset rocket (``Rocket.reset``, base.py:186): the kernel applies the Verlet
     bootstrap (base.py:65-130) itself on the first step.  All arguments are arrays [N]
     (or scalars); returns the public words as int32 [10, N]."""
@@ -104,8 +105,10 @@ def fresh_state_soa(x, y, vx, vy, angle, ang_vel, dry_mass, fuel, steps=0, ep_re
     soa = np.zeros((10, n), np.int32)
     soa[W_X], soa[W_Y] = _bits(cx), _bits(cy)
     soa[W_ANGLE] = _angle_units(cang)
-    soa[W_SX], soa[W_SY] = _bits(cvx), _bits(cvy)              # velocities themselves while FRESH
-    om_hi, om_lo = split_angle_delta(com)                      # (omega with its 8 extra bits)
+    dt = float(dt)
+    soa[W_SX] = np.rint(cvx * dt * DELTA_UNITS_PER_M).astype(np.int32)      # v dt while FRESH: the first step
+    soa[W_SY] = np.rint(cvy * dt * DELTA_UNITS_PER_M).astype(np.int32)      # subtracts the bootstrap term a0 dt^2 / 2
+    om_hi, om_lo = split_angle_delta(com * dt)                 # (omega dt with its 8 extra bits)
     soa[W_SANGLE] = _bits(om_hi)
     soa[W_DRY] = _bits(cdry)
     soa[W_FUEL] = _fuel_units(cfuel, fuel_unit)
@@ -160,12 +163,11 @@ def reference_view(soa: np.ndarray, dt: float, fuel_unit: float = DEFAULT_FUEL_U
     unit = np.float32(1.0 / DELTA_UNITS_PER_M)
     f = lambda w: soa[w].view(np.float32)                                   # noqa: E731
 
-    def vel(w):
-        delta = soa[w].astype(np.float32) * unit
-        return np.where(fresh, f(w), delta * inv_dt).astype(np.float64)
+    def vel(w):                                   # (also while FRESH: the slots then hold v dt)
+        return ((soa[w].astype(np.float32) * unit) * inv_dt).astype(np.float64)
 
     ang = soa[W_ANGLE].astype(np.float32) * np.float32(1.0 / ANGLE_UNITS_PER_DEG)
-    om = np.where(fresh, f(W_SANGLE), f(W_SANGLE) * inv_dt).astype(np.float64)
+    om = (f(W_SANGLE) * inv_dt).astype(np.float64)
     return {"x": f(W_X).astype(np.float64), "y": f(W_Y).astype(np.float64),
             "vx": vel(W_SX), "vy": vel(W_SY), "angle": ang.astype(np.float64),
             "ang_vel": om, "dry_mass": f(W_DRY).astype(np.float64),

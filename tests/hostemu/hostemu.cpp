@@ -36,13 +36,13 @@ static inline float wf(const float* soa, int64_t n, int w, int64_t i) { return s
 
 static void load_rocket(const float* soa, int64_t n, int64_t i, rl::Rocket& r) {
     r.x = wf(soa, n, RL_W_X, i); r.y = wf(soa, n, RL_W_Y, i); r.ang = (int32_t)w32(soa, n, RL_W_ANGLE, i);
-    r.sx = w32(soa, n, RL_W_SX, i); r.sy = w32(soa, n, RL_W_SY, i); r.sang = wf(soa, n, RL_W_SANGLE, i);
+    r.sx = (int32_t)w32(soa, n, RL_W_SX, i); r.sy = (int32_t)w32(soa, n, RL_W_SY, i); r.sang = wf(soa, n, RL_W_SANGLE, i);
     r.dry = wf(soa, n, RL_W_DRY, i); r.fuel = (int32_t)w32(soa, n, RL_W_FUEL, i);
     r.meta = w32(soa, n, RL_W_META, i); r.ep_ret = wf(soa, n, RL_W_EPRET, i);
 }
 static void store_rocket(float* soa, int64_t n, int64_t i, const rl::Rocket& r) {
     soa[RL_W_X * n + i] = r.x; soa[RL_W_Y * n + i] = r.y; s32(soa, n, RL_W_ANGLE, i, (uint32_t)r.ang);
-    s32(soa, n, RL_W_SX, i, r.sx); s32(soa, n, RL_W_SY, i, r.sy); soa[RL_W_SANGLE * n + i] = r.sang;
+    s32(soa, n, RL_W_SX, i, (uint32_t)r.sx); s32(soa, n, RL_W_SY, i, (uint32_t)r.sy); soa[RL_W_SANGLE * n + i] = r.sang;
     soa[RL_W_DRY * n + i] = r.dry; s32(soa, n, RL_W_FUEL, i, (uint32_t)r.fuel);
     s32(soa, n, RL_W_META, i, r.meta); soa[RL_W_EPRET * n + i] = r.ep_ret;
 }
@@ -131,10 +131,8 @@ int emu_reset(const RlParams* p, float* soa, int64_t n, int64_t gid0, uint64_t s
     if (rl::derive_params(*p, P, err, sizeof(err)) != RL_OK) return -1;
     for (int64_t i = 0; i < n; ++i) {
         rl::Rocket r;
-        float ax0, ay0;
-        rl::sample_reset(P, seed, (uint64_t)(gid0 + i), epoch, r, ax0, ay0);
+        rl::sample_reset(P, seed, (uint64_t)(gid0 + i), epoch, r, obs + 8 * i);
         store_rocket(soa, n, i, r);
-        rl::fresh_obs(P, r, ax0, ay0, obs + 8 * i);
     }
     return 0;
 }

@@ -363,7 +363,7 @@ def test_reset_distribution_on_the_gpu(torch):
 
     def check(w, tag):
         u = (w - lo) / (hi - lo)
-        assert u.min() >= 0.0 and u.max() <= 1.0, tag
+        assert u.min() >= -1e-6 and u.max() <= 1.0 + 1e-6, tag        # (v = fixed-point delta / dt)
         m = u.shape[0]
         grid = (np.arange(m) + 0.5) / m
         for k in range(10):
