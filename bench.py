@@ -422,6 +422,40 @@ def main() -> None:
                "h2d_bytes_per_step": 8 * count, "d2h_bytes_per_step": (32 + 4 + 1 + 1) * count,
                "steps": args.e2e_steps, "api": "RocketLandingSB3VecEnv.step_raw -> rl_step_host (pinned numpy in/out)"}
         henv.close()
+        # The e2e path is bound by the host<->device copies, not by the kernel: measure the box's copy
+        # ceiling for exactly these bytes -- every rank copies 38 B per rocket device->host and 8 B per
+        # rocket host->device between ITS GPU and pinned memory, all ranks at the same time.
+        d_out = torch.empty(38 * count, dtype=torch.uint8, device=dev)
+        h_out = torch.empty(38 * count, dtype=torch.uint8).pin_memory()
+        d_in = torch.empty(8 * count, dtype=torch.uint8, device=dev)
+        s_out, s_in = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+        def copies():
+            with torch.cuda.stream(s_out):
+                h_out.copy_(d_out, non_blocking=True)
+            with torch.cuda.stream(s_in):
+                d_in.copy_(hact.view(torch.uint8).reshape(-1), non_blocking=True)
+
+        copies()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            copies()
+        torch.cuda.current_stream(dev).wait_stream(s_out)
+        torch.cuda.current_stream(dev).wait_stream(s_in)
+        c1.record()
+        torch.cuda.synchronize(dev)
+        t_c = torch.tensor([c0.elapsed_time(c1) / 3.0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
+        ceiling = float(args.rockets) * args.substeps / (float(t_c[0]) * 1e-3)
+        e2e["copy_ceiling"] = {"env_steps_per_s": ceiling, "d2h_gbs_aggregate": 38.0 * args.rockets / (float(t_c[0]) * 1e-3) / 1e9,
+                               "h2d_gbs_aggregate": 8.0 * args.rockets / (float(t_c[0]) * 1e-3) / 1e9,
+                               "how": "all ranks at once: cudaMemcpyAsync of 38 B/rocket D2H + 8 B/rocket H2D, pinned memory, "
+                                      "two streams, slowest rank"}
+        e2e["frac_of_copy_ceiling"] = e2e["value"] / ceiling
+        del d_out, h_out, d_in
 
     if rank == 0:
         line = {

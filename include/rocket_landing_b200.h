@@ -79,6 +79,7 @@ extern "C" {
 #define RL_META_STEP_MASK 0x0000FFFFu
 #define RL_META_DLO_SHIFT 16
 #define RL_META_WRAP_SHIFT 24
+#define RL_META_SIM_MASK 0x78000000u   /* bits [27,31): simulation-mode landing code + landed flag */
 #define RL_META_FRESH 0x80000000u
 #define RL_ANGLE_UNITS_PER_DEG (4294967296.0 / 360.0)
 #define RL_DELTA_UNITS_PER_M 8388608.0

@@ -63,6 +63,22 @@ struct StepResult {
     int landing;               // 0 none, 1 safe, 2 good, 3 ok, 4 unsafe (protocol.py:31-41)
 };
 
+// What a step needs of the state BEFORE it, derived from the persistent words: computed once when a
+// rocket is loaded (flight_begin) and handed from one fused substep to the next by rocket_advance --
+// every field is produced by the very expression flight_begin would evaluate on the stored words, so
+// carrying it changes no bit of the results (the fused and the repeated single step are tested to be
+// identical).  The meta word is unpacked here and packed back by flight_end.
+struct Flight {
+    float vx, vy, om;          // velocities: delta / dt (engine.py:193-194, :220-222)
+    float ang;                 // angle in degrees
+    float phi;                 // potential of this state (reward.py:231-264)
+    int steps;                 // episode step count (lander.py:229)
+    int k;                     // 360-degree turns the last normalisation removed (base.py:171)
+    int lo;                    // low-order 8 bits of the carried angle delta
+    bool fresh;                // bootstrap term still to be subtracted (base.py:65-130)
+    uint32_t sim_bits;         // simulation-mode bits of the meta word, passed through
+};
+
 // ---- small math helpers (plain-C versions in the host build of tests/hostemu) ------------------
 #ifndef RL_HOST_EMULATION
 // 1/x: MUFU.RCP + one Newton step (< 1 ulp); __frcp_rn costs ~10 instructions for the last half ulp
@@ -131,11 +147,19 @@ __device__ __forceinline__ double dtheta_join(float hi, int lo) {
     const uint32_t E = (rl_f2u(hi) >> 23) & 0xffu;
     return fma((double)lo, rl_pow2_bits(E + (1023u - 158u)), (double)hi);
 }
+// (angle - previous angle) when the previous normalisation removed k turns; kept out of line of the
+// compiler's if-conversion: wraps are rare and the fp64 work should not run on every step
+__device__ __forceinline__ double rl_unwrap(double dang, int k) {
+#ifndef RL_HOST_EMULATION
+    asm volatile("");
+#endif
+    return dang - 360.0 * (double)k;
+}
 __device__ __forceinline__ void dtheta_split(double v, float& hi, int& lo) {
     hi = (float)v;
     const uint32_t E = (rl_f2u(hi) >> 23) & 0xffu;
     lo = rl_d2i((v - (double)hi) * rl_pow2_bits((1023u + 158u) - E));
-    lo = lo > 127 ? 127 : (lo < -128 ? -128 : lo);
+    lo = min(max(lo, -128), 127);
 }
 
 // sin and cos of the fixed-point angle (the reference does np.sin(np.deg2rad(a)), engine.py:64-73).
@@ -260,26 +284,42 @@ __device__ __forceinline__ float landing_reward(const PP& P, float avx, float av
     return P.r_crash * (0.7f + 0.3f * fminf(1.0f, (avy * 0.05f + aa * (1.0f / 45.0f)) * 0.5f));
 }
 
+// Unpack the meta word and derive the before-state of the next step from the persistent words.
+template <class PP>
+__device__ __forceinline__ void flight_begin(const PP& P, const Rocket& r, Flight& f) {
+    f.fresh = (r.meta & RL_META_FRESH) != 0u;
+    f.steps = (int)(r.meta & RL_META_STEP_MASK);
+    f.k = ((int)(r.meta << 5)) >> 29;                          // bits [24,27) sign-extended
+    f.lo = ((int)(r.meta << 8)) >> 24;                         // bits [16,24) sign-extended
+    f.sim_bits = r.meta & RL_META_SIM_MASK;
+    f.vx = ((float)r.sx * (float)kDeltaUnit) * P.inv_dt;       // (the unit scaling is exact)
+    f.vy = ((float)r.sy * (float)kDeltaUnit) * P.inv_dt;
+    f.om = r.sang * P.inv_dt;
+    f.ang = angle_deg(r.ang);
+    f.phi = potential(r.y, f.vx, f.vy, f.ang, f.om);
+}
+
+__device__ __forceinline__ void flight_end(Rocket& r, const Flight& f) {
+    r.meta = (f.fresh ? RL_META_FRESH : 0u) | f.sim_bits | (((uint32_t)f.k & 7u) << RL_META_WRAP_SHIFT) |
+             (((uint32_t)f.lo & 0xffu) << RL_META_DLO_SHIFT) | (uint32_t)f.steps;
+}
+
 // One env step (lander.py:188-255) of one rocket, no reset.  th_raw / cg_raw are the raw
 // action: physics clips it (base.py:135-136), the reward does not (reward.py:69-70).
 //
-// rocket_advance does everything except the observation.  With have_phi, o.phi must hold the
-// potential of the CURRENT state (it does after a previous rocket_advance on the same rocket):
-// the fused-substep loop then evaluates the potential once per substep instead of twice, with
-// bit-identical results (same expression, same operands).
+// rocket_advance does everything except the observation and the meta word: `f` describes the state
+// before the step on entry and the state after it on return (ready for the next fused substep).
 template <class PP>
-__device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_raw, float cg_raw,
-                                               StepResult& o, bool have_phi) {
-    const bool fresh = (r.meta & RL_META_FRESH) != 0u;
-    const int steps = min((int)(r.meta & RL_META_STEP_MASK) + 1, (int)RL_META_STEP_MASK);   // lander.py:229
-    const int k_prev = ((int)(r.meta << 5)) >> 29;             // bits [24,27) sign-extended
-    const int lo_prev = ((int)(r.meta << 8)) >> 24;            // bits [16,24) sign-extended
+__device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, Flight& f, float th_raw, float cg_raw,
+                                               StepResult& o) {
+    const bool fresh = f.fresh;
+    const int steps = min(f.steps + 1, (int)RL_META_STEP_MASK);                 // lander.py:229
+    const int k_prev = f.k, lo_prev = f.lo;
 
     // ---- state before the action (Rocket.get_state, base.py:220) --------------------------
-    const float y_b = r.y, ang_b = angle_deg(r.ang);
-    const float vx_b = ((float)r.sx * (float)kDeltaUnit) * P.inv_dt;        // v = delta / dt (engine.py:193-194);
-    const float vy_b = ((float)r.sy * (float)kDeltaUnit) * P.inv_dt;        // the unit scaling is exact
-    const float om_b = r.sang * P.inv_dt;
+    const float y_b = r.y, ang_b = f.ang;
+    const float vx_b = f.vx, vy_b = f.vy, om_b = f.om;
+    const int32_t ang_units_b = r.ang;
 
     // ---- Rocket.apply_action (base.py:132-184) -----------------------------------------------
     const int32_t fuel_now = r.fuel;
@@ -305,14 +345,14 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_
         ax = fmaf(t, s, a0x);
         ay = fmaf(t, c, a0y);
         // cold-gas torque (engine.py:125-155): alpha dt^2 in fp64 -- it accumulates into the angle delta
-        const bool torque = m_d >= P.alpha_min_mass_d;
+        const bool torque = (P.alpha_min_mass_d <= 1e-6) || (m_d >= P.alpha_min_mass_d);   // (folds away: m_d > 1e-6 here)
         const double adt2_d = torque ? (double)cg * P.alpha_dt2_d * inv_m_d : 0.0;
         alpha = torque ? cg * P.alpha_k * inv_m : 0.0f;        // (telemetry only)
 
         // carried deltas (x - x_prev, y - y_prev in fixed point; angle - angle_prev in fp64)
         int32_t dx = r.sx, dy = r.sy;
         double dang_d = dtheta_join(r.sang, lo_prev);
-        if (k_prev != 0) dang_d -= 360.0 * (double)k_prev;     // both angles normalised (base.py:171)
+        if (k_prev != 0) dang_d = rl_unwrap(dang_d, k_prev);  // both angles normalised (base.py:171); rare: a real branch
         if (fresh) {
             // Verlet bootstrap (base.py:65-130): x - x_prev = v dt - a0 dt^2 / 2 (the slots hold v dt)
             // and, alpha0 being 0, angle - angle_prev = omega dt with the previous angle normalised
@@ -357,12 +397,13 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_
         r.sang = hi;
         const int32_t burn = rl_f2i(th * P.burn_units);        // engine.py:239-243, base.py:174-175 (th >= 0)
         r.fuel = max(fuel_now - burn, 0);
-        r.meta = (((uint32_t)k & 7u) << RL_META_WRAP_SHIFT) | (((uint32_t)lo & 0xffu) << RL_META_DLO_SHIFT) |
-                 (uint32_t)steps;                              // FRESH cleared
+        f.k = k;
+        f.lo = lo;
+        f.fresh = false;
     } else {
         r.fuel = max(fuel_now, 0);                             // base.py:139-141 happens before the early return
-        r.meta = (r.meta & ~RL_META_STEP_MASK) | (uint32_t)steps;
     }
+    f.steps = steps;
 
     const float x_a = r.x, y_a = r.y, ang_a = angle_deg(r.ang);
     const float aa = fabsf(ang_a), avy = fabsf(vy_a);
@@ -375,7 +416,7 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_
     // cold-gas direction term (reward.py:130-167); cold gas is the RAW action
     const bool need = (ab > P.dead_band) || (wb > P.dead_band);
     // (angle > 0 and cg < 0) or (angle < 0 and cg > 0): both non-zero with opposite signs
-    const bool correct = (ang_b != 0.0f) && (cg_raw != 0.0f) && ((int32_t)(rl_f2u(ang_b) ^ rl_f2u(cg_raw)) < 0);
+    const bool correct = (ang_units_b != 0) && (cg_raw != 0.0f) && ((int32_t)((uint32_t)ang_units_b ^ rl_f2u(cg_raw)) < 0);
     const float effect = d_ang + d_om;
     const float amp = (need && effect > 0.0f) ? fmaf(effect, effect, 1.0f) : 1.0f;
     const float gain = need ? (ab + wb) * (correct ? P.k_direction : -P.k_direction) : -0.3f;
@@ -398,7 +439,7 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_
     const float t5 = vy_a * 0.5f * rl_sat(y_a * 1e-3f) * (1.0f + rl_sat(vy_a * 0.2f));
     total -= (airborne && vy_a > 0.0f) ? t5 : 0.0f;
     // 6. potential shaping (reward.py:267-270)
-    const float phi_b = have_phi ? o.phi : potential(y_b, vx_b, vy_b, ang_b, om_b);
+    const float phi_b = f.phi;
     const float phi_a = potential(y_a, vx_a, vy_a, ang_a, om_a);
     total += fmaf(P.gamma, phi_a, -phi_b);
     // truncation penalties (reward.py:274-279); tip-over never ends the episode
@@ -428,6 +469,11 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_
     o.vy = vy_a;
     o.om = om_a;
     o.phi = phi_a;
+    f.vx = vx_a;
+    f.vy = vy_a;
+    f.om = om_a;
+    f.ang = ang_a;
+    f.phi = phi_a;
     // NaN / Inf, or a position delta about to leave the fixed-point range (+-256 m per step)
     o.nonfinite = !(fabsf(total) <= 3.0e38f) || !(fabsf(y_a) <= 3.0e38f) || (speed_chk > 250.0f);
     r.ep_ret += total;
@@ -435,15 +481,18 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, float th_
 
 // _get_obs of the state rocket_advance left behind (lander.py:243)
 template <class PP>
-__device__ __forceinline__ void step_obs(const PP& P, const Rocket& r, StepResult& o) {
-    clip_obs(P, r.x, r.y, o.vx, o.vy, o.ax, o.ay, angle_deg(r.ang), o.om, o.obs);
+__device__ __forceinline__ void step_obs(const PP& P, const Rocket& r, const Flight& f, StepResult& o) {
+    clip_obs(P, r.x, r.y, f.vx, f.vy, o.ax, o.ay, f.ang, f.om, o.obs);
 }
 
 template <class PP>
 __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw, float cg_raw,
                                             StepResult& o) {
-    rocket_advance(P, r, th_raw, cg_raw, o, false);
-    step_obs(P, r, o);
+    Flight f;
+    flight_begin(P, r, f);
+    rocket_advance(P, r, f, th_raw, cg_raw, o);
+    flight_end(r, f);
+    step_obs(P, r, f, o);
 }
 
 }  // namespace rl

@@ -257,11 +257,16 @@ __device__ __forceinline__ void store_obs(ObsStage& st, float4* __restrict__ obs
 // Episode end + reset of the done lanes of one warp (rare: ~1 rocket in 113 per step; inlined
 // into a cold branch -- an out-of-line call would force the rocket's registers onto the stack).
 // Records the finished episode, hands the terminal observation / return / length to the
-// caller's buffers, and -- with auto-reset -- resamples the rocket: for every done lane (uniform
-// loop over the ballot) lanes 0..2 compute the three Philox blocks of that rocket in parallel
-// and the ten words are shuffled to the lane that owns it.  Same counters and words as
-// sample_reset(), one third of the serial Philox latency.
-template <bool kAutoReset, class PP>
+// caller's buffers, and -- with auto-reset -- resamples the rocket.  Lanes compute the three
+// Philox4x32-10 blocks of a done rocket side by side and the ten words are shuffled to the lane that
+// owns it: same counters and words as sample_reset(), one third of the serial Philox latency.
+//   kManyDone = false (one substep per launch: ~1.3 done rockets in the 27 % of warps that have any):
+//     the done lanes are walked one by one, lanes 0..2 serving each -- fewest registers, and the
+//     single-step kernel must stay at 64 to keep four CTAs per SM resident;
+//   kManyDone = true (fused substeps: K times as many rockets finish per launch): up to TEN done
+//     rockets per pass, the j-th served by lanes 3j, 3j + 1, 3j + 2 -- a warp instruction costs one
+//     issue slot however many lanes it serves, and this kernel is issue-bound.
+template <bool kAutoReset, bool kManyDone, class PP>
 __device__ __forceinline__ void warp_episode_end(const PP& P, const StepArgs& a, BlockStats& bs, ThreadStats& ts,
                                                  unsigned done_mask, bool done, uint32_t i, uint64_t epoch,
                                                  Rocket& r, StepResult& o) {
@@ -282,19 +287,50 @@ __device__ __forceinline__ void warp_episode_end(const PP& P, const StepArgs& a,
         const unsigned lane = threadIdx.x & 31u;
         const uint64_t gid_lane0 = (uint64_t)a.gid0 + (uint64_t)(i - lane);
         const uint2 key = make_uint2((uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-        while (done_mask) {
-            const unsigned src = (unsigned)__ffs((int)done_mask) - 1u;
-            done_mask &= done_mask - 1u;
-            const uint4 blk = philox4x32_10(reset_counter(gid_lane0 + src, epoch, lane & 3u), key);
-            uint32_t w[10];
-            w[0] = __shfl_sync(0xffffffffu, blk.x, 0); w[1] = __shfl_sync(0xffffffffu, blk.y, 0);
-            w[2] = __shfl_sync(0xffffffffu, blk.z, 0); w[3] = __shfl_sync(0xffffffffu, blk.w, 0);
-            w[4] = __shfl_sync(0xffffffffu, blk.x, 1); w[5] = __shfl_sync(0xffffffffu, blk.y, 1);
-            w[6] = __shfl_sync(0xffffffffu, blk.z, 1); w[7] = __shfl_sync(0xffffffffu, blk.w, 1);
-            w[8] = __shfl_sync(0xffffffffu, blk.x, 2); w[9] = __shfl_sync(0xffffffffu, blk.y, 2);
-            if (lane == src) {
-                rocket_from_words(P, w, r, o.obs);       // SB3 VecEnv contract: return the reset observation
-                a.st.dry[i] = r.dry;                     // dry mass only ever changes here
+        if constexpr (!kManyDone) {
+            while (done_mask) {
+                const unsigned src = (unsigned)__ffs((int)done_mask) - 1u;
+                done_mask &= done_mask - 1u;
+                const uint4 blk = philox4x32_10(reset_counter(gid_lane0 + src, epoch, lane & 3u), key);
+                uint32_t w[10];
+                w[0] = __shfl_sync(0xffffffffu, blk.x, 0); w[1] = __shfl_sync(0xffffffffu, blk.y, 0);
+                w[2] = __shfl_sync(0xffffffffu, blk.z, 0); w[3] = __shfl_sync(0xffffffffu, blk.w, 0);
+                w[4] = __shfl_sync(0xffffffffu, blk.x, 1); w[5] = __shfl_sync(0xffffffffu, blk.y, 1);
+                w[6] = __shfl_sync(0xffffffffu, blk.z, 1); w[7] = __shfl_sync(0xffffffffu, blk.w, 1);
+                w[8] = __shfl_sync(0xffffffffu, blk.x, 2); w[9] = __shfl_sync(0xffffffffu, blk.y, 2);
+                if (lane == src) {
+                    rocket_from_words(P, w, r, o.obs);       // SB3 VecEnv contract: return the reset observation
+                    a.st.dry[i] = r.dry;                     // dry mass only ever changes here
+                }
+            }
+        } else {
+            const unsigned group = lane / 3u, member = lane - 3u * group;      // lanes 30, 31: group 10, idle
+            unsigned pending = done_mask;
+            while (pending) {
+                const int served = min(__popc(pending), 10);
+                // the rocket this lane's group serves: the group-th set bit of `pending`
+                unsigned m = pending;
+                for (int t = 0; t + 1 < served; ++t)                            // (uniform trip count)
+                    if ((unsigned)t < group) m &= m - 1u;
+                const unsigned src = (unsigned)__ffs((int)m) - 1u;
+                uint4 blk = make_uint4(0u, 0u, 0u, 0u);
+                if (group < (unsigned)served) blk = philox4x32_10(reset_counter(gid_lane0 + src, epoch, member), key);
+                // my own rocket, if it is served in this pass, sits in group `rank`
+                const unsigned rank = (unsigned)__popc(pending & ((1u << lane) - 1u));
+                const bool mine = ((pending >> lane) & 1u) != 0u && rank < 10u;
+                const int g0 = (int)(3u * (rank < 10u ? rank : 0u));
+                uint32_t w[10];
+                w[0] = __shfl_sync(0xffffffffu, blk.x, g0); w[1] = __shfl_sync(0xffffffffu, blk.y, g0);
+                w[2] = __shfl_sync(0xffffffffu, blk.z, g0); w[3] = __shfl_sync(0xffffffffu, blk.w, g0);
+                w[4] = __shfl_sync(0xffffffffu, blk.x, g0 + 1); w[5] = __shfl_sync(0xffffffffu, blk.y, g0 + 1);
+                w[6] = __shfl_sync(0xffffffffu, blk.z, g0 + 1); w[7] = __shfl_sync(0xffffffffu, blk.w, g0 + 1);
+                w[8] = __shfl_sync(0xffffffffu, blk.x, g0 + 2); w[9] = __shfl_sync(0xffffffffu, blk.y, g0 + 2);
+                if (mine) {
+                    rocket_from_words(P, w, r, o.obs);
+                    a.st.dry[i] = r.dry;
+                }
+                // drop the served (lowest) set bits
+                for (int t = 0; t < served; ++t) pending &= pending - 1u;
             }
         }
     }
@@ -339,6 +375,9 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
         cp_async_8_zfill(&ring[s].act[tid], a.actions + (in ? j : 0u), in ? 8u : 0u);
     };
 
+    // which optional outputs the caller wants: decided once, not per tile
+    const bool want_landing = a.landing != nullptr, want_accel = a.raw_accel != nullptr;
+
     stats_init(bs);
 #pragma unroll
     for (uint32_t d = 0; d + 1 < (uint32_t)kStages; ++d) {   // prologue: the first kStages - 1 tiles
@@ -374,10 +413,12 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
         }
 
         StepResult o;
+        Flight f;
         float reward;
         bool done;
+        flight_begin(P, r, f);
         if constexpr (kSingleStep) {
-            rocket_step(P, r, act.x, act.y, o);
+            rocket_advance(P, r, f, act.x, act.y, o);
             reward = o.reward;
             // (padding rockets beyond n hold the all-zero state rl_create wrote and nothing ever
             // overwrites: massless, never tipped, never non-finite -- only the counts need `valid`)
@@ -388,23 +429,26 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
         } else {
             reward = 0.0f;
             done = false;
-            for (int k = 0; k < a.substeps; ++k) {
-                rocket_advance(P, r, act.x, act.y, o, k > 0);     // potential carried across substeps
+            int tipped = 0, bad = 0, k = 0;
+            for (; k < a.substeps && !done; ++k) {       // stop integrating at the first done
+                rocket_advance(P, r, f, act.x, act.y, o);  // the before-state (and its potential) is carried in f
                 reward += o.reward;
-                ts.env_steps += valid ? 1 : 0;
-                ts.tip_steps += o.tipped ? 1 : 0;
-                ts.nonfinite += o.nonfinite ? 1 : 0;
+                tipped += o.tipped ? 1 : 0;
+                bad += o.nonfinite ? 1 : 0;
                 done = valid && (o.terminated || o.truncated);
-                if (done) break;                         // stop integrating at the first done
             }
-            step_obs(P, r, o);                           // the observation is only needed once
+            ts.env_steps += valid ? k : 0;
+            ts.tip_steps += tipped;
+            ts.nonfinite += bad;
         }
+        flight_end(r, f);
+        step_obs(P, r, f, o);                            // the observation is only needed once
         ts.reward_sum += valid ? reward : 0.0f;
 
         const unsigned done_mask = __ballot_sync(0xffffffffu, done);
         const bool terminated = o.terminated, truncated = o.truncated;
         const int landing = o.landing;
-        if (done_mask) warp_episode_end<kAutoReset>(P, a, bs, ts, done_mask, done, i, epoch, r, o);
+        if (done_mask) warp_episode_end<kAutoReset, !kSingleStep>(P, a, bs, ts, done_mask, done, i, epoch, r, o);
 
         store_obs(obs_stage[tid >> 5], a.obs, i, a.n, o.obs);
         if (valid) {
@@ -412,8 +456,8 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
             out_store(&a.reward[i], reward);
             out_store(&a.terminated[i], (uint8_t)(terminated ? 1 : 0));
             out_store(&a.truncated[i], (uint8_t)(truncated ? 1 : 0));
-            if (a.landing) out_store(reinterpret_cast<uint8_t*>(&a.landing[i]), (uint8_t)landing);
-            if (a.raw_accel) out_store(&a.raw_accel[i], make_float2(o.ax, o.ay));
+            if (want_landing) out_store(reinterpret_cast<uint8_t*>(&a.landing[i]), (uint8_t)landing);
+            if (want_accel) out_store(&a.raw_accel[i], make_float2(o.ax, o.ay));
         }
     }
     cp_async_wait<0>();

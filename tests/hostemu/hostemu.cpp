@@ -57,12 +57,16 @@ static void emu_step_impl(const PP& P, float* soa, int64_t n, const float* actio
         rl::Rocket r;
         load_rocket(soa, n, i, r);
         rl::StepResult o;
+        rl::Flight f;
         float rew = 0.0f;
-        for (int k = 0; k < substeps; ++k) {
-            rl::rocket_step(P, r, actions[2 * i], actions[2 * i + 1], o);
+        rl::flight_begin(P, r, f);
+        for (int k = 0; k < substeps; ++k) {           // as the fused-substep loop of the step kernel
+            rl::rocket_advance(P, r, f, actions[2 * i], actions[2 * i + 1], o);
             rew += o.reward;
             if (o.terminated || o.truncated) break;
         }
+        rl::flight_end(r, f);
+        rl::step_obs(P, r, f, o);
         store_rocket(soa, n, i, r);
         std::memcpy(obs + 8 * i, o.obs, 32);
         reward[i] = rew;
