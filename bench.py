@@ -344,6 +344,13 @@ def main() -> None:
     if rank == 0:
         sampler.start()
     ev0, ev1, evk = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    if world > 1:
+        # The host threads leave the barrier above up to ~1 ms apart (8 processes on one VM), and the
+        # closing all-reduce makes every rank wait for the last one to START: align the GPUs themselves
+        # with one more (tiny, on-stream) all-reduce, so that every rank's clock starts within
+        # microseconds of the others'.  It is part of the opening barrier, not of the timed region.
+        align = torch.zeros(1, device=dev)
+        dist.all_reduce(align)
     # Everything inside the timed region is ENQUEUED: K launches of the step kernel back to back on one
     # stream, the statistics kernel + 128-byte all-reduce (NCCL) every --stats-interval steps and once
     # at the end; the host reads the reduced statistics back after the closing event.
