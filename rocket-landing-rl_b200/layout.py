@@ -97,7 +97,9 @@ def fresh_state_soa(x, y, vx, vy, angle, ang_vel, dry_mass, fuel, steps=0, ep_re
                     fuel_unit: float = DEFAULT_FUEL_UNIT, dt: float = 0.1) -> np.ndarray:
     """A just-reset rocket (``Rocket.reset``, base.py:186): the kernel applies the Verlet
     bootstrap (base.py:65-130) itself on the first step.  All arguments are arrays [N]
-    (or scalars); returns the public words as int32 [10, N]."""
+    (or scalars); returns the public words as int32 [10, N].  ``dt`` and ``fuel_unit`` must be
+    the environment's (``env.dt``, ``env.fuel_unit``): the delta slots of a FRESH rocket hold
+    ``v * dt``."""
     cols = np.broadcast_arrays(*[np.asarray(v, np.float64) for v in
                                  (x, y, angle, vx, vy, ang_vel, dry_mass, fuel)])
     cx, cy, cang, cvx, cvy, com, cdry, cfuel = [c.reshape(-1) for c in cols]

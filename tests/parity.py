@@ -70,10 +70,10 @@ LAND_V = (30.0, 40.0, 100.0)
 LAND_A = (5.0, 8.0, 10.0)
 
 
-def _fresh_soa(states: np.ndarray, steps=0, fuel_unit=layout.DEFAULT_FUEL_UNIT) -> np.ndarray:
+def _fresh_soa(states: np.ndarray, steps=0, fuel_unit=layout.DEFAULT_FUEL_UNIT, dt=0.1) -> np.ndarray:
     s = np.asarray(states, np.float64)
     return layout.fresh_state_soa(s[:, 0], s[:, 1], s[:, 2], s[:, 3], s[:, 6], s[:, 7], s[:, 8],
-                                  s[:, 9], steps=steps, fuel_unit=fuel_unit)
+                                  s[:, 9], steps=steps, fuel_unit=fuel_unit, dt=dt)
 
 
 # ----------------------------------------------------------------------------------------
@@ -105,7 +105,7 @@ class HostEmuStepper:
         self.soa = np.zeros((10, n), np.int32)
 
     def inject_fresh(self, states: np.ndarray, mask=None, steps=0) -> None:
-        new = _fresh_soa(states, steps, self.fuel_unit)
+        new = _fresh_soa(states, steps, self.fuel_unit, self.dt)
         if mask is None:
             self.soa[:] = new
         else:
@@ -159,7 +159,7 @@ class GpuStepper:
         self.dt = self.env.dt
 
     def inject_fresh(self, states: np.ndarray, mask=None, steps=0) -> None:
-        self.env.set_state(self.torch.from_numpy(_fresh_soa(states, steps, self.env.fuel_unit)),
+        self.env.set_state(self.torch.from_numpy(_fresh_soa(states, steps, self.env.fuel_unit, self.dt)),
                            None if mask is None else self.torch.from_numpy(np.asarray(mask, np.uint8)))
 
     def inject_soa(self, soa: np.ndarray) -> None:
@@ -231,10 +231,11 @@ def _near_landing_threshold(vx, vy, ang) -> np.ndarray:
 class LockstepChecker:
     """Feed one step of (got, ref) at a time; keeps the per-rocket "in sync" mask."""
 
-    def __init__(self, n: int):
+    def __init__(self, n: int, constants=None):
         self.n = n
         self.synced = np.ones(n, bool)
         self.rep = ParityReport()
+        self.constants = constants          # oracle EnvConstants of a non-default configuration (None: config.yaml)
 
     def resync(self, mask) -> None:
         self.synced[mask] = True
@@ -243,7 +244,7 @@ class LockstepChecker:
     def teacher_forced(self, t, before_view, after_view, actions, got_rew, got_term, got_trunc,
                        got_land) -> None:
         rep = self.rep
-        rew, term, trunc, land = c_oracle.reward_on_states(before_view, after_view, actions)
+        rew, term, trunc, land = c_oracle.reward_on_states(before_view, after_view, actions, self.constants)
         bad = (term != got_term) | (trunc != got_trunc) | (land != got_land)
         for i in np.flatnonzero(bad):
             rep.tf_violations.append((t, int(i), "tf-flags", (bool(got_term[i]), bool(got_trunc[i]), int(got_land[i])),
@@ -427,6 +428,43 @@ def braking_actions(t, oracle, rng):
     return a.astype(np.float32)
 
 
+def constants_from_params(p: RlParams):
+    """The oracle's EnvConstants for an arbitrary RlParams (non-default configurations)."""
+    from oracle.rocket_oracle import EnvConstants
+    return EnvConstants(
+        dt=p.time_step, gravity=p.gravity, air_density=p.air_density, thrust_power=p.thrust_power,
+        cold_gas_thrust_power=p.cold_gas_thrust_power, fuel_rate=p.fuel_consumption_rate, radius=p.radius,
+        moment_arm=p.cold_gas_moment_arm, reference_area=p.reference_area, drag_coefficient=p.drag_coefficient,
+        angular_damping=p.angular_damping,
+        reset_ranges=tuple((float(lo), float(hi)) for lo, hi in zip(p.reset_low, p.reset_high)),
+        land_perfect=tuple(p.land_perfect), land_good=tuple(p.land_good), land_ok=tuple(p.land_ok),
+        max_episode_steps=int(p.max_episode_steps), max_horizontal_position=p.max_horizontal_position,
+        max_altitude=p.max_altitude, tip_over_angle=p.tip_over_angle, r_landing_perfect=p.landing_perfect,
+        r_landing_good=p.landing_good, r_landing_ok=p.landing_ok, r_crash_ground=p.crash_ground,
+        r_out_of_bounds=p.out_of_bounds, r_tipped_over=p.tipped_over,
+        throttle_descent_reward_scale=p.throttle_descent_reward_scale, cold_gas_reward_scale=p.cold_gas_reward_scale,
+        free_fall_penalty_scale=p.free_fall_penalty_scale, angle_aware_throttle_scale=p.angle_aware_throttle_scale,
+        correct_direction_bonus=p.correct_direction_bonus, gamma=p.gamma,
+        obs_low=tuple(p.obs_low), obs_high=tuple(p.obs_high))
+
+
+def other_config() -> RlParams:
+    """A configuration that shares NO derived constant with the reference's config.yaml: half the
+    time step, a heavier rocket with a bigger engine and tank (another fixed-point fuel unit),
+    stronger cold gas and damping, a 1500-step time limit.  Exercises the run-time-constant kernels."""
+    p = load_params()
+    p.time_step = 0.05
+    p.thrust_power = 2.4e7
+    p.cold_gas_thrust_power = 1.1e5
+    p.fuel_consumption_rate = 2900.0
+    p.angular_damping = 0.08
+    p.drag_coefficient = 0.7
+    p.reset_low[8], p.reset_high[8] = 52000.0, 61000.0
+    p.reset_low[9], p.reset_high[9] = 600000.0, 900000.0
+    p.max_episode_steps = 1500
+    return p
+
+
 def hover_actions(t, oracle, rng):
     """Keeps every rocket aloft to the 1000-step limit (lander.py:237-241): descend to ~300 m, hold
     it with a throttle loop, PD attitude loop, 2 % action noise.  The worst case for ACCUMULATED
@@ -435,7 +473,7 @@ def hover_actions(t, oracle, rng):
     y, vy, a, w = r["y"], r["vy"], r["angle"], r["ang_vel"]
     m = r["dry_mass"] + r["fuel"]
     tv = np.where(y > 400, -40.0, np.clip(-(y - 300) * 0.2, -20, 20))
-    th = (9.81 * m / 1e7) * (1 + np.clip((tv - vy) * 0.3, -1, 6))
+    th = (9.81 * m / oracle.c.thrust_power) * (1 + np.clip((tv - vy) * 0.3, -1, 6))
     cg = np.clip(-(a * 0.9 + w * 1.6), -1, 1)
     return (np.stack([th, cg], 1) + rng.normal(0, 0.02, (oracle.n, 2))).astype(np.float32)
 
@@ -465,7 +503,7 @@ def lockstep_vs_oracle(stepper, oracle, steps: int, seed: int = 0, action_fn=ran
     init = sample_reset_states(rng, stepper.params, n)
     stepper.inject_fresh(init)
     oracle.inject(init)
-    chk = LockstepChecker(n)
+    chk = LockstepChecker(n, oracle.c)
     before = stepper.view()
     for t in range(steps):
         a = action_fn(t, oracle, rng)

@@ -183,6 +183,20 @@ def test_thousand_step_reference_trajectories_replayed(golden_dir, name):
     assert rep.max_state_err.max() < 0.8 and rep.max_obs_err < 0.8, rep.summary()
 
 
+def test_another_configuration_flown_to_its_time_limit():
+    """Nothing in the long-horizon scheme is tuned to config.yaml: a configuration with other
+    constants everywhere (dt 0.05, another fuel unit, 1500-step limit) against the oracle given the
+    same constants, every rocket kept aloft to step 1500."""
+    p = parity.other_config()
+    n = 128
+    st = parity.HostEmuStepper(n, params=p)
+    assert st.fuel_unit == 2.0 ** -11 and st.L.emu_matches_default(__import__("ctypes").addressof(p)) == 0
+    rep = parity.lockstep_vs_oracle(st, c_oracle.BatchOracle(n, parity.constants_from_params(p)), 1500, seed=9,
+                                    action_fn=parity.hover_actions)
+    rep.assert_ok(max_guard_events=0)                     # (x reaches 0.9 of the tolerance: 1500 steps of fp32 x rounding)
+    assert rep.steps_compared == n * 1500 and rep.episodes == n
+
+
 def test_plain_fp32_accumulators_would_drift():
     """Why the integrating words are 32-bit fixed point / 32-bit mantissa (DESIGN.md "Long-horizon
     accuracy"): rounding the SAME trajectories' carried words to fp32 after every step -- what the

@@ -110,6 +110,21 @@ def test_thousand_step_reference_trajectories(torch, golden_dir, name):
     assert rep.max_state_err.max() < 0.8 and rep.max_obs_err < 0.8
 
 
+def test_another_configuration_flown_to_its_time_limit(torch):
+    """The run-time-constant kernels on a configuration that shares no derived constant with
+    config.yaml (dt 0.05, another fixed-point fuel unit, 1500-step limit): every rocket kept aloft to
+    step 1500 against the oracle given the same constants."""
+    p = parity.other_config()
+    n = 256
+    st = parity.GpuStepper(n, params=p)
+    assert not st.env.uses_folded_constants and st.env.fuel_unit == 2.0 ** -11
+    rep = parity.lockstep_vs_oracle(st, c_oracle.BatchOracle(n, parity.constants_from_params(p)), 1500, seed=9,
+                                    action_fn=parity.hover_actions)
+    print(rep.summary())
+    rep.assert_ok(max_guard_events=0)
+    assert rep.steps_compared == n * 1500 and rep.episodes == n
+
+
 def test_gpu_and_host_build_of_the_device_math_agree(torch):
     """Same source (rl_device.cuh), two compilers: the Philox reset must be bit-identical,
     a step must agree to rounding."""
@@ -417,7 +432,7 @@ def test_batched_raw_state_matches_the_oracle(torch):
     orc = c_oracle.BatchOracle(n)
     rng = np.random.default_rng(1)
     init = parity.sample_reset_states(rng, env.params, n)
-    env.set_state(torch.from_numpy(parity._fresh_soa(init, 0, env.fuel_unit)))
+    env.set_state(torch.from_numpy(parity._fresh_soa(init, 0, env.fuel_unit, env.dt)))
     orc.inject(init)
     big = 0
     for t in range(40):
