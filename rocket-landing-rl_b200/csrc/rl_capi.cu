@@ -132,6 +132,7 @@ int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8
     a.episode_length = episode_length;
     a.landing = landing;
     a.raw_accel = reinterpret_cast<float2*>(raw_accel);
+    a.optional = (landing ? 1u : 0u) | (raw_accel ? 2u : 0u);
     a.stats = e->stats;
     a.n = (uint32_t)e->n;
     a.gid0 = e->gid0;

@@ -319,7 +319,6 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, Flight& f
     // ---- state before the action (Rocket.get_state, base.py:220) --------------------------
     const float y_b = r.y, ang_b = f.ang;
     const float vx_b = f.vx, vy_b = f.vy, om_b = f.om;
-    const int32_t ang_units_b = r.ang;
 
     // ---- Rocket.apply_action (base.py:132-184) -----------------------------------------------
     const int32_t fuel_now = r.fuel;
@@ -415,8 +414,10 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, Flight& f
     float total = fmaf(d_ang, 0.5f, d_om * 0.1f);
     // cold-gas direction term (reward.py:130-167); cold gas is the RAW action
     const bool need = (ab > P.dead_band) || (wb > P.dead_band);
-    // (angle > 0 and cg < 0) or (angle < 0 and cg > 0): both non-zero with opposite signs
-    const bool correct = (ang_units_b != 0) && (cg_raw != 0.0f) && ((int32_t)((uint32_t)ang_units_b ^ rl_f2u(cg_raw)) < 0);
+    // (angle > 0 and cg < 0) or (angle < 0 and cg > 0): both non-zero with opposite signs, i.e. a
+    // strictly negative product (|angle| >= 8.4e-8 where non-zero, so only a cold-gas command below
+    // 1e-38 could underflow it -- where the term it gates is below 1e-36 anyway)
+    const bool correct = ang_b * cg_raw < 0.0f;
     const float effect = d_ang + d_om;
     const float amp = (need && effect > 0.0f) ? fmaf(effect, effect, 1.0f) : 1.0f;
     const float gain = need ? (ab + wb) * (correct ? P.k_direction : -P.k_direction) : -0.3f;

@@ -84,6 +84,8 @@ struct StepArgs {
     unsigned long long* __restrict__ epoch_bump;    // device: epoch to advance when the launch ends, or null
     unsigned int* __restrict__ ticket;              // device: CTAs finished in this launch
     uint32_t tile_begin, tile_end;                  // tiles of 256 rockets this launch steps ([0, ceil(n/256)) = all)
+    uint32_t optional;                              // bit 0: landing != null, bit 1: raw_accel != null (tested per tile:
+                                                    // one bit test on a uniform register instead of two 64-bit compares)
     uint32_t chunk;                                 // consecutive tiles per CTA (grid = ceil(tiles / chunk)); 0 = persistent
                                                     // grid, CTA b walks tiles b, b + gridDim.x, ...
     int substeps;
@@ -375,9 +377,6 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
         cp_async_8_zfill(&ring[s].act[tid], a.actions + (in ? j : 0u), in ? 8u : 0u);
     };
 
-    // which optional outputs the caller wants: decided once, not per tile
-    const bool want_landing = a.landing != nullptr, want_accel = a.raw_accel != nullptr;
-
     stats_init(bs);
 #pragma unroll
     for (uint32_t d = 0; d + 1 < (uint32_t)kStages; ++d) {   // prologue: the first kStages - 1 tiles
@@ -456,8 +455,8 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
             out_store(&a.reward[i], reward);
             out_store(&a.terminated[i], (uint8_t)(terminated ? 1 : 0));
             out_store(&a.truncated[i], (uint8_t)(truncated ? 1 : 0));
-            if (want_landing) out_store(reinterpret_cast<uint8_t*>(&a.landing[i]), (uint8_t)landing);
-            if (want_accel) out_store(&a.raw_accel[i], make_float2(o.ax, o.ay));
+            if (a.optional & 1u) out_store(reinterpret_cast<uint8_t*>(&a.landing[i]), (uint8_t)landing);
+            if (a.optional & 2u) out_store(&a.raw_accel[i], make_float2(o.ax, o.ay));
         }
     }
     cp_async_wait<0>();
