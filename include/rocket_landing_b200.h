@@ -54,13 +54,13 @@ extern "C" {
  * accuracy").  rocket-landing-rl_b200/layout.py converts to and from the reference's Rocket.state
  * words. */
 #define RL_STATE_WORDS 10
-#define RL_W_X 0        /* f32  m                                                              */
-#define RL_W_Y 1        /* f32  m                                                              */
+#define RL_W_X 0        /* i32  units of rl_pos_unit() m (2^-15 m for the reference's +-50 km world)   */
+#define RL_W_Y 1        /* i32  units of rl_pos_unit() m                                       */
 #define RL_W_ANGLE 2    /* i32  units of 360 / 2^32 deg: int32 range == [-180, 180), so integer
                            wrap-around IS normalize_angle_180 (engine.py:230)                  */
-#define RL_W_SX 3       /* i32  carried x delta x(t) - x(t-dt), units of 2^-23 m, so vx = delta / dt
-                           (engine.py:193-194); while FRESH: vx dt                             */
-#define RL_W_SY 4       /* i32  carried y delta, units of 2^-23 m; while FRESH: vy dt          */
+#define RL_W_SX 3       /* i32  carried x delta x(t) - x(t-dt), units of rl_pos_unit() / 256 m (2^-23 m),
+                           so vx = delta / dt (engine.py:193-194); while FRESH: vx dt          */
+#define RL_W_SY 4       /* i32  carried y delta, same units; while FRESH: vy dt                */
 #define RL_W_SANGLE 5   /* f32  carried pre-wrap angle delta in deg (high part; 8 more bits in
                            RL_W_META), so omega = delta / dt; while FRESH: omega dt            */
 #define RL_W_DRY 6      /* f32  kg                                                             */
@@ -82,7 +82,7 @@ extern "C" {
 #define RL_META_SIM_MASK 0x78000000u   /* bits [27,31): simulation-mode landing code + landed flag */
 #define RL_META_FRESH 0x80000000u
 #define RL_ANGLE_UNITS_PER_DEG (4294967296.0 / 360.0)
-#define RL_DELTA_UNITS_PER_M 8388608.0
+#define RL_DELTA_UNITS_PER_POS_UNIT 256
 
 /* Slots of the statistics vector (float64 [16]) returned by rl_stats. */
 #define RL_STATS_WORDS 16
@@ -174,6 +174,13 @@ int64_t rl_num_envs(const RlEnv *env);
  * rl_fuel_unit_for computes the same from a parameter set without a handle. */
 double rl_fuel_unit(const RlEnv *env);
 double rl_fuel_unit_for(const RlParams *params);
+
+/* metres per unit of the fixed-point position words RL_W_X / RL_W_Y: 2^(k-31), 2^k being the first
+ * power of two above 1.3 x max(max_horizontal_position, max_altitude, |reset range of x, y|) -- the
+ * bounds check (reward.py:274-276) ends an episode before a rocket can leave that range; positions
+ * saturate at its edge.  The deltas RL_W_SX / RL_W_SY count 1/256 of it. */
+double rl_pos_unit(const RlEnv *env);
+double rl_pos_unit_for(const RlParams *params);
 
 /* 1 if this handle runs the kernel instantiation with the reference's config.yaml constants
  * folded in at compile time (chosen only when every derived constant is bit-identical to those

@@ -17,7 +17,7 @@ ABI_VERSION = 2
 
 # every symbol include/rocket_landing_b200.h declares
 EXPORTS = ("rl_abi_version", "rl_last_error", "rl_params_default", "rl_state_bytes", "rl_create",
-           "rl_destroy", "rl_num_envs", "rl_fuel_unit", "rl_fuel_unit_for", "rl_uses_folded_constants", "rl_get_epoch", "rl_set_epoch", "rl_reset", "rl_step",
+           "rl_destroy", "rl_num_envs", "rl_fuel_unit", "rl_fuel_unit_for", "rl_pos_unit", "rl_pos_unit_for", "rl_uses_folded_constants", "rl_get_epoch", "rl_set_epoch", "rl_reset", "rl_step",
            "rl_set_state", "rl_get_state", "rl_stats", "rl_step_host", "rl_reset_host", "rl_get_state_host",
            "rl_launch_count", "rl_vecnorm_last_error", "rl_vecnorm_create", "rl_vecnorm_destroy",
            "rl_vecnorm_reset", "rl_vecnorm_step", "rl_vecnorm_normalize_obs", "rl_vecnorm_get_stats",
@@ -61,6 +61,10 @@ def load():
     L.rl_fuel_unit.restype = C.c_double
     L.rl_fuel_unit_for.argtypes = [C.POINTER(RlParams)]
     L.rl_fuel_unit_for.restype = C.c_double
+    L.rl_pos_unit.argtypes = [vp]
+    L.rl_pos_unit.restype = C.c_double
+    L.rl_pos_unit_for.argtypes = [C.POINTER(RlParams)]
+    L.rl_pos_unit_for.restype = C.c_double
     L.rl_uses_folded_constants.argtypes = [vp]
     L.rl_get_epoch.argtypes = [vp]
     L.rl_get_epoch.restype = u64

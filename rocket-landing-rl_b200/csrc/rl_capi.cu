@@ -359,6 +359,8 @@ int rl_destroy(RlEnv* e) {
 int64_t rl_num_envs(const RlEnv* e) { return e ? e->n : 0; }
 double rl_fuel_unit(const RlEnv* e) { return e ? e->dev.fuel_unit_d : 0.0; }
 double rl_fuel_unit_for(const RlParams* p) { return p ? rl::fuel_unit_for(p->reset_high[9]) : 0.0; }
+double rl_pos_unit(const RlEnv* e) { return e ? (double)e->dev.pos_unit : 0.0; }
+double rl_pos_unit_for(const RlParams* p) { return p ? rl::pos_unit_for(*p) : 0.0; }
 int rl_uses_folded_constants(const RlEnv* e) { return (e && e->folded) ? 1 : 0; }
 uint64_t rl_get_epoch(RlEnv* e) {
     if (!e) return 0;

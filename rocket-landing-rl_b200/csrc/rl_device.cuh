@@ -19,7 +19,9 @@
 // of up to 1000 steps -- carry 32 significant bits instead of fp32's 24, at no extra bytes:
 //   angle     int32, 360 / 2^32 deg per unit: the int32 range IS [-180, 180), wrap-around is the
 //             normalisation, resolution 8.4e-8 deg everywhere;
-//   dx, dy    int32, 2^-23 m per unit (+-256 m per step);
+//   x, y      int32, P.pos_unit m per unit (2^-15 m for the reference's +-50 km world): fp32 positions
+//             at 2 km round by 1.2e-4 m every step, a random walk of 4e-3 m over 1000 steps;
+//   dx, dy    int32, pos_unit / 256 per unit (2^-23 m: +-256 m per step);
 //   fuel      int32, P.fuel_unit kg per unit (2^-12 kg for the reference's tanks);
 //   dtheta    fp32 + 8 low-order bits kept in the meta word (a 32-bit mantissa), updated in fp64
 //             together with 1 / m and alpha dt^2: an error e in dtheta decays only by the 0.995
@@ -42,9 +44,9 @@
 namespace rl {
 
 struct Rocket {                // the ten persistent words (RL_W_*)
-    float x, y;
+    int32_t x, y;              // units of P.pos_unit m
     int32_t ang;               // units of kAngleUnit deg
-    int32_t sx, sy;            // x - x_prev, y - y_prev in units of kDeltaUnit m (v dt while FRESH: bootstrap pending)
+    int32_t sx, sy;            // x - x_prev, y - y_prev in units of P.delta_unit m (v dt while FRESH: bootstrap pending)
     float sang;                // carried pre-wrap angle delta, high part (omega dt while FRESH)
     float dry;
     int32_t fuel;              // units of P.fuel_unit_d kg (signed: an injected negative load acts like the
@@ -69,6 +71,7 @@ struct StepResult {
 // carrying it changes no bit of the results (the fused and the repeated single step are tested to be
 // identical).  The meta word is unpacked here and packed back by flight_end.
 struct Flight {
+    float x, y;                // position in metres (fp32 image of the fixed-point words)
     float vx, vy, om;          // velocities: delta / dt (engine.py:193-194, :220-222)
     float ang;                 // angle in degrees
     float phi;                 // potential of this state (reward.py:231-264)
@@ -112,6 +115,7 @@ __device__ __forceinline__ double rl_rcp_d(double m) {
     return fma(r, fma(-m, r, 1.0), r);
 }
 __device__ __forceinline__ int32_t rl_f2i(float f) { return __float2int_rn(f); }          // saturating, NaN -> 0
+
 __device__ __forceinline__ int32_t rl_d2i(double d) { return __double2int_rn(d); }
 __device__ __forceinline__ long long rl_d2ll(double d) { return __double2ll_rn(d); }
 __device__ __forceinline__ double rl_pow2_bits(uint32_t biased) { return __hiloint2double((int)(biased << 20), 0); }
@@ -233,8 +237,8 @@ __device__ __forceinline__ void rocket_from_words(const PP& P, const uint32_t* w
     const float ay0 = fmaf(P.reset_span(5), u01(w[5]), P.reset_lo(5));
     const float ang = fmaf(P.reset_span(6), u01(w[6]), P.reset_lo(6));
     const float om = fmaf(P.reset_span(7), u01(w[7]), P.reset_lo(7));
-    r.x = fmaf(P.reset_span(0), u01(w[0]), P.reset_lo(0));
-    r.y = fmaf(P.reset_span(1), u01(w[1]), P.reset_lo(1));
+    r.x = rl_f2i(fmaf(P.reset_span(0), u01(w[0]), P.reset_lo(0)) * P.pos_inv_unit);
+    r.y = rl_f2i(fmaf(P.reset_span(1), u01(w[1]), P.reset_lo(1)) * P.pos_inv_unit);
     r.sx = rl_f2i(vx * P.dt_units);
     r.sy = rl_f2i(vy * P.dt_units);
     r.ang = rl_f2i(ang * (float)kAngleInvUnit);
@@ -246,8 +250,8 @@ __device__ __forceinline__ void rocket_from_words(const PP& P, const uint32_t* w
     // the observation reads the STORED words back (as lander.py:124-150 reads Rocket.state), so it is
     // exactly the state the first step starts from
     if (obs)
-        clip_obs(P, r.x, r.y, ((float)r.sx * (float)kDeltaUnit) * P.inv_dt, ((float)r.sy * (float)kDeltaUnit) * P.inv_dt,
-                 ax0, ay0, angle_deg(r.ang), r.sang * P.inv_dt, obs);
+        clip_obs(P, (float)r.x * P.pos_unit, (float)r.y * P.pos_unit, ((float)r.sx * P.delta_unit) * P.inv_dt,
+                 ((float)r.sy * P.delta_unit) * P.inv_dt, ax0, ay0, angle_deg(r.ang), r.sang * P.inv_dt, obs);
 }
 
 // One thread draws all three Philox blocks keyed by (seed, global rocket id, epoch).
@@ -292,11 +296,13 @@ __device__ __forceinline__ void flight_begin(const PP& P, const Rocket& r, Fligh
     f.k = ((int)(r.meta << 5)) >> 29;                          // bits [24,27) sign-extended
     f.lo = ((int)(r.meta << 8)) >> 24;                         // bits [16,24) sign-extended
     f.sim_bits = r.meta & RL_META_SIM_MASK;
-    f.vx = ((float)r.sx * (float)kDeltaUnit) * P.inv_dt;       // (the unit scaling is exact)
-    f.vy = ((float)r.sy * (float)kDeltaUnit) * P.inv_dt;
+    f.x = (float)r.x * P.pos_unit;                             // (the unit scalings are exact: powers of two)
+    f.y = (float)r.y * P.pos_unit;
+    f.vx = ((float)r.sx * P.delta_unit) * P.inv_dt;
+    f.vy = ((float)r.sy * P.delta_unit) * P.inv_dt;
     f.om = r.sang * P.inv_dt;
     f.ang = angle_deg(r.ang);
-    f.phi = potential(r.y, f.vx, f.vy, f.ang, f.om);
+    f.phi = potential(f.y, f.vx, f.vy, f.ang, f.om);
 }
 
 __device__ __forceinline__ void flight_end(Rocket& r, const Flight& f) {
@@ -317,7 +323,7 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, Flight& f
     const int k_prev = f.k, lo_prev = f.lo;
 
     // ---- state before the action (Rocket.get_state, base.py:220) --------------------------
-    const float y_b = r.y, ang_b = f.ang;
+    const float y_b = f.y, ang_b = f.ang;
     const float vx_b = f.vx, vy_b = f.vy, om_b = f.om;
 
     // ---- Rocket.apply_action (base.py:132-184) -----------------------------------------------
@@ -367,9 +373,12 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, Flight& f
         const int32_t ndx = dx + rl_f2i(ax * P.dt2_units);
         const int32_t ndy = dy + rl_f2i(ay * P.dt2_units);
         const double ndang_d = fma(dang_d, P.damp_d, adt2_d);
-        const float sxf = (float)ndx * (float)kDeltaUnit, syf = (float)ndy * (float)kDeltaUnit;
-        r.x += sxf;
-        r.y += syf;
+        const float sxf = (float)ndx * P.delta_unit, syf = (float)ndy * P.delta_unit;
+        // x' = x + dx', rounded to the position grid (ties up).  No overflow check here: the grid spans
+        // 1.3 x the bounds at which reward.py:274-276 ends the episode (the simulation mode, which has
+        // no bounds, clamps in its own kernel)
+        r.x += (ndx + (1 << (kDeltaShift - 1))) >> kDeltaShift;
+        r.y += (ndy + (1 << (kDeltaShift - 1))) >> kDeltaShift;
         vx_a = sxf * P.inv_dt;
         vy_a = syf * P.inv_dt;
         speed_chk = fmaxf(fabsf(sxf), fabsf(syf));
@@ -404,7 +413,7 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, Flight& f
     }
     f.steps = steps;
 
-    const float x_a = r.x, y_a = r.y, ang_a = angle_deg(r.ang);
+    const float x_a = (float)r.x * P.pos_unit, y_a = (float)r.y * P.pos_unit, ang_a = angle_deg(r.ang);
     const float aa = fabsf(ang_a), avy = fabsf(vy_a);
 
     // ---- calculate_reward (reward.py:27-281), shaping path ------------------------------------
@@ -470,20 +479,23 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, Flight& f
     o.vy = vy_a;
     o.om = om_a;
     o.phi = phi_a;
+    f.x = x_a;
+    f.y = y_a;
     f.vx = vx_a;
     f.vy = vy_a;
     f.om = om_a;
     f.ang = ang_a;
     f.phi = phi_a;
-    // NaN / Inf, or a position delta about to leave the fixed-point range (+-256 m per step)
-    o.nonfinite = !(fabsf(total) <= 3.0e38f) || !(fabsf(y_a) <= 3.0e38f) || (speed_chk > 250.0f);
+    // NaN / Inf, or a position delta about to leave the fixed-point range (+-2^31 delta units per step:
+    // +-256 m for the reference's world)
+    o.nonfinite = !(fabsf(total) <= 3.0e38f) || (speed_chk > P.delta_unit * 2.09e9f);
     r.ep_ret += total;
 }
 
 // _get_obs of the state rocket_advance left behind (lander.py:243)
 template <class PP>
 __device__ __forceinline__ void step_obs(const PP& P, const Rocket& r, const Flight& f, StepResult& o) {
-    clip_obs(P, r.x, r.y, f.vx, f.vy, o.ax, o.ay, f.ang, f.om, o.obs);
+    clip_obs(P, f.x, f.y, f.vx, f.vy, o.ax, o.ay, f.ang, f.om, o.obs);
 }
 
 template <class PP>

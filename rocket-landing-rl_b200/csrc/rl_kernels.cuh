@@ -1,6 +1,6 @@
 // Kernels of the batched environment step.  State layout in HBM (DESIGN.md "Data layout"):
 //
-//   plane A  16 B x Np  { x f32, y f32, angle i32, meta u32 }          read + written every step
+//   plane A  16 B x Np  { x i32, y i32, angle i32, meta u32 }          read + written every step
 //   plane B  16 B x Np  { sx i32, sy i32, sangle f32, ep_return f32 }  read + written every step
 //   fuel     i32 [Np]                                                  read + written every step
 //   dry      f32 [Np]                                                  read every step, written on reset only
@@ -204,7 +204,7 @@ __device__ __forceinline__ void stats_flush(BlockStats& s, double* __restrict__ 
 }
 
 __device__ __forceinline__ void unpack_rocket(const float4& a, const float4& b, float fuel_bits, float dry, Rocket& r) {
-    r.x = a.x; r.y = a.y; r.ang = __float_as_int(a.z); r.meta = __float_as_uint(a.w);
+    r.x = __float_as_int(a.x); r.y = __float_as_int(a.y); r.ang = __float_as_int(a.z); r.meta = __float_as_uint(a.w);
     r.sx = __float_as_int(b.x); r.sy = __float_as_int(b.y); r.sang = b.z; r.ep_ret = b.w;
     r.fuel = __float_as_int(fuel_bits);
     r.dry = dry;
@@ -215,7 +215,7 @@ __device__ __forceinline__ void load_rocket(const StatePlanes& st, uint32_t i, R
 }
 
 __device__ __forceinline__ void store_rocket(const StatePlanes& st, uint32_t i, const Rocket& r, bool write_dry) {
-    st.A[i] = make_float4(r.x, r.y, __int_as_float(r.ang), __uint_as_float(r.meta));
+    st.A[i] = make_float4(__int_as_float(r.x), __int_as_float(r.y), __int_as_float(r.ang), __uint_as_float(r.meta));
     st.B[i] = make_float4(__int_as_float(r.sx), __int_as_float(r.sy), r.sang, r.ep_ret);
     st.fuel[i] = __int_as_float(r.fuel);
     if (write_dry) st.dry[i] = r.dry;

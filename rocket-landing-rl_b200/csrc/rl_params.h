@@ -34,8 +34,7 @@ namespace rl {
 // integrated words persist for the rest of an episode, so they carry 32 significant bits.
 constexpr double kAngleUnit = 360.0 / 4294967296.0;      // degrees per unit of the int32 angle: [-180, 180) = int32
 constexpr double kAngleInvUnit = 4294967296.0 / 360.0;
-constexpr double kDeltaUnit = 1.0 / 8388608.0;           // metres per unit of the int32 position deltas (2^-23 m)
-constexpr double kDeltaInvUnit = 8388608.0;
+constexpr int kDeltaShift = 8;                           // a position delta counts units of pos_unit / 2^kDeltaShift
 
 struct DevParams {
     float dt, inv_dt, dt2, half_dt2;
@@ -45,9 +44,12 @@ struct DevParams {
     double alpha_dt2_d;        // alpha_k dt^2 in fp64: the angle delta gains cg alpha_dt2_d / m per step
     double fuel_unit_d;        // kg per unit of the fixed-point fuel word (a power of two)
     double alpha_min_mass_d;   // fp64 copy of the inertia gate
-    float dt2_units;           // dt^2 / kDeltaUnit: acceleration -> fixed-point delta increment
-    float half_dt2_units;      // dt^2 / 2 / kDeltaUnit: Verlet bootstrap correction of a FRESH rocket
-    float dt_units;            // dt / kDeltaUnit: velocity -> fixed-point delta (reset)
+    float pos_unit;            // metres per unit of the fixed-point positions x, y (a power of two)
+    float pos_inv_unit;        // 1 / pos_unit (reset: metres -> units)
+    float delta_unit;          // metres per unit of the position deltas = pos_unit / 2^kDeltaShift
+    float dt2_units;           // dt^2 / delta_unit: acceleration -> fixed-point delta increment
+    float half_dt2_units;      // dt^2 / 2 / delta_unit: Verlet bootstrap correction of a FRESH rocket
+    float dt_units;            // dt / delta_unit: velocity -> fixed-point delta (reset)
     float burn_units;          // fuel_consumption_rate dt / fuel_unit: throttle -> fixed-point burn
     float fuel_inv_unit;       // 1 / fuel_unit (reset: kg -> units)
     float gravity;
@@ -88,6 +90,9 @@ struct DefaultParams {
     static constexpr double alpha_dt2_d = 7.0e4 * 1.85 / (0.5 * 1.85 * 1.85) * (180.0 / kPi) * (kDt * kDt);
     static constexpr double fuel_unit_d = 1.0 / 4096.0;               // 410 000 kg < 2^19 -> 2^(19-31)
     static constexpr double alpha_min_mass_d = 1e-6 / (0.5 * 1.85 * 1.85);
+    static constexpr float pos_unit = (float)(1.0 / 32768.0);          // 1.3 x 50 000 m < 2^16 -> 2^(16-31)
+    static constexpr float pos_inv_unit = 32768.0f;
+    static constexpr float delta_unit = (float)(1.0 / 8388608.0);      // 2^-23 m
     static constexpr float dt2_units = (float)(kDt * kDt * 8388608.0);
     static constexpr float half_dt2_units = (float)(0.5 * kDt * kDt * 8388608.0);
     static constexpr float dt_units = (float)(kDt * 8388608.0);
@@ -137,6 +142,7 @@ inline bool matches_default(const DevParams& d) {
     using D = DefaultParams;
     bool ok = d.dt == D::dt && d.dt_d == D::dt_d && d.damp_d == D::damp_d && d.alpha_dt2_d == D::alpha_dt2_d &&
               d.fuel_unit_d == D::fuel_unit_d && d.alpha_min_mass_d == D::alpha_min_mass_d &&
+              d.pos_unit == D::pos_unit && d.pos_inv_unit == D::pos_inv_unit && d.delta_unit == D::delta_unit &&
               d.dt2_units == D::dt2_units && d.half_dt2_units == D::half_dt2_units && d.dt_units == D::dt_units && d.burn_units == D::burn_units && d.fuel_inv_unit == D::fuel_inv_unit && d.inv_dt == D::inv_dt && d.dt2 == D::dt2 && d.half_dt2 == D::half_dt2 &&
               d.gravity == D::gravity && d.thrust_power == D::thrust_power && d.drag_k == D::drag_k &&
               d.alpha_k == D::alpha_k && d.alpha_min_mass == D::alpha_min_mass && d.damp == D::damp &&
@@ -187,6 +193,18 @@ inline double fuel_unit_for(double max_fuel) {
     return ldexp(1.0, k - 31);
 }
 
+// metres per unit of the fixed-point positions: 2^(k - 31) with 2^k the first power of two above 1.3 x
+// the largest coordinate a rocket can hold before the bounds check ends its episode (reward.py:274-276;
+// the margin covers the last step), and never below the reset ranges (config.yaml: 50 000 m -> 2^-15 m)
+inline double pos_unit_for(const RlParams& p) {
+    double m = fmax(fabs(p.max_horizontal_position), fabs(p.max_altitude));
+    for (int k = 0; k < 2; ++k) m = fmax(m, fmax(fabs(p.reset_low[k]), fabs(p.reset_high[k])));
+    m *= 1.3;
+    int k = 0;
+    if (m >= 1.0) k = (int)floor(log2(m)) + 1;
+    return ldexp(1.0, k - 31);
+}
+
 inline int derive_params(const RlParams& p, DevParams& d, char* err, size_t err_len) {
     if (!(p.time_step > 0)) return derive_fail(err, err_len, "time_step must be positive");          // engine.py:35
     if (p.thrust_power < 0 || p.cold_gas_thrust_power < 0 || p.fuel_consumption_rate < 0)
@@ -197,6 +215,8 @@ inline int derive_params(const RlParams& p, DevParams& d, char* err, size_t err_
         return derive_fail(err, err_len, "max_episode_steps out of range (1 .. %d)", (int)RL_META_STEP_MASK);
     if (!(p.reset_high[9] < 9.0e18))
         return derive_fail(err, err_len, "reset_high[9] (fuel mass) out of range");
+    if (!(fmax(fabs(p.max_horizontal_position), fabs(p.max_altitude)) < 1.0e15))
+        return derive_fail(err, err_len, "max_horizontal_position / max_altitude out of range");
     const double pi = 3.14159265358979323846;
     const double dt = p.time_step;
     d.dt = (float)dt;
@@ -221,9 +241,13 @@ inline int derive_params(const RlParams& p, DevParams& d, char* err, size_t err_
     d.fuel_unit_d = fuel_unit_for(p.reset_high[9]);
     d.fuel_inv_unit = (float)(1.0 / d.fuel_unit_d);
     d.burn_units = (float)(p.fuel_consumption_rate * dt / d.fuel_unit_d);
-    d.dt2_units = (float)(dt * dt / kDeltaUnit);
-    d.half_dt2_units = (float)(0.5 * dt * dt / kDeltaUnit);
-    d.dt_units = (float)(dt / kDeltaUnit);
+    const double pos_unit = pos_unit_for(p), delta_unit = ldexp(pos_unit, -kDeltaShift);
+    d.pos_unit = (float)pos_unit;
+    d.pos_inv_unit = (float)(1.0 / pos_unit);
+    d.delta_unit = (float)delta_unit;
+    d.dt2_units = (float)(dt * dt / delta_unit);
+    d.half_dt2_units = (float)(0.5 * dt * dt / delta_unit);
+    d.dt_units = (float)(dt / delta_unit);
     d.mass_gate = f32_down(1e-6);
     d.throttle_gate = f32_down(1e-6);
     d.speed2_gate = f32_down(1e-9);

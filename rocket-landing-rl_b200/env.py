@@ -94,6 +94,7 @@ class RocketLandingVecEnv:
                                      dev_index, self.state_buffer.data_ptr(), C.byref(handle)), "rl_create")
         self._h = handle
         self.fuel_unit = float(self._L.rl_fuel_unit(self._h))     # kg per unit of the fixed-point fuel word
+        self.pos_unit = float(self._L.rl_pos_unit(self._h))       # m per unit of the fixed-point positions
         f32 = dict(dtype=torch.float32, device=self.device)
         self.obs = torch.zeros((n, 8), **f32)
         self.reward = torch.zeros((n,), **f32)
@@ -201,7 +202,7 @@ class RocketLandingVecEnv:
 
     def get_reference_state(self) -> dict:
         """Persistent state as the reference's ``Rocket.state`` words (float64 numpy)."""
-        return reference_view(self.get_state().cpu().numpy(), self.dt, self.fuel_unit)
+        return reference_view(self.get_state().cpu().numpy(), self.dt, self.fuel_unit, self.pos_unit)
 
     def state_dict(self) -> dict:
         return {"state": self.state_buffer.clone(), "epoch": int(self._L.rl_get_epoch(self._h)),

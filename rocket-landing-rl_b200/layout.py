@@ -24,7 +24,8 @@ META_DLO_SHIFT = 16
 META_WRAP_SHIFT = 24
 META_FRESH = 0x80000000
 ANGLE_UNITS_PER_DEG = 4294967296.0 / 360.0       # int32 range == [-180, 180)
-DELTA_UNITS_PER_M = 8388608.0                    # 2^-23 m per unit
+DELTA_UNITS_PER_POS_UNIT = 256                   # the position deltas count 1/256 of the position unit
+DEFAULT_POS_UNIT = 1.0 / 32768.0                 # m; reference config.yaml (+-50 km world): deltas in 2^-23 m
 DEFAULT_FUEL_UNIT = 1.0 / 4096.0                 # kg; reference config.yaml (fuel <= 410 000 kg)
 
 
@@ -33,6 +34,19 @@ def fuel_unit_for(max_fuel: float) -> float:
     the first power of two above the largest fuel load of the reset distribution."""
     k = int(math.floor(math.log2(max_fuel))) + 1 if max_fuel >= 1.0 else 0
     return math.ldexp(1.0, k - 31)
+
+
+def pos_unit_for(params) -> float:
+    """m per unit of the fixed-point positions (``rl_pos_unit_for``) of an ``RlParams``."""
+    m = max(abs(params.max_horizontal_position), abs(params.max_altitude),
+            *(abs(v) for k in range(2) for v in (params.reset_low[k], params.reset_high[k]))) * 1.3
+    k = int(math.floor(math.log2(m))) + 1 if m >= 1.0 else 0
+    return math.ldexp(1.0, k - 31)
+
+
+def _pos_units(metres, pos_unit: float) -> np.ndarray:
+    u = np.rint(np.asarray(metres, np.float64) / pos_unit)
+    return np.clip(u, -2147483648, 2147483647).astype(np.int32)
 
 
 def _bits(a) -> np.ndarray:
@@ -94,22 +108,24 @@ def join_angle_delta(hi: np.ndarray, lo: np.ndarray) -> np.ndarray:
 
 
 def fresh_state_soa(x, y, vx, vy, angle, ang_vel, dry_mass, fuel, steps=0, ep_return=0.0,
-                    fuel_unit: float = DEFAULT_FUEL_UNIT, dt: float = 0.1) -> np.ndarray:
+                    fuel_unit: float = DEFAULT_FUEL_UNIT, dt: float = 0.1,
+                    pos_unit: float = DEFAULT_POS_UNIT) -> np.ndarray:
     """A just-reset rocket (``Rocket.reset``, base.py:186): the kernel applies the Verlet
     bootstrap (base.py:65-130) itself on the first step.  All arguments are arrays [N]
-    (or scalars); returns the public words as int32 [10, N].  ``dt`` and ``fuel_unit`` must be
-    the environment's (``env.dt``, ``env.fuel_unit``): the delta slots of a FRESH rocket hold
-    ``v * dt``."""
+    (or scalars); returns the public words as int32 [10, N].  ``dt``, ``fuel_unit`` and ``pos_unit``
+    must be the environment's (``env.dt``, ``env.fuel_unit``, ``env.pos_unit``): the delta slots of a
+    FRESH rocket hold ``v * dt``."""
     cols = np.broadcast_arrays(*[np.asarray(v, np.float64) for v in
                                  (x, y, angle, vx, vy, ang_vel, dry_mass, fuel)])
     cx, cy, cang, cvx, cvy, com, cdry, cfuel = [c.reshape(-1) for c in cols]
     n = cx.size
     soa = np.zeros((10, n), np.int32)
-    soa[W_X], soa[W_Y] = _bits(cx), _bits(cy)
+    soa[W_X], soa[W_Y] = _pos_units(cx, pos_unit), _pos_units(cy, pos_unit)
     soa[W_ANGLE] = _angle_units(cang)
     dt = float(dt)
-    soa[W_SX] = np.rint(cvx * dt * DELTA_UNITS_PER_M).astype(np.int32)      # v dt while FRESH: the first step
-    soa[W_SY] = np.rint(cvy * dt * DELTA_UNITS_PER_M).astype(np.int32)      # subtracts the bootstrap term a0 dt^2 / 2
+    per_m = DELTA_UNITS_PER_POS_UNIT / pos_unit
+    soa[W_SX] = np.rint(cvx * dt * per_m).astype(np.int32)      # v dt while FRESH: the first step
+    soa[W_SY] = np.rint(cvy * dt * per_m).astype(np.int32)      # subtracts the bootstrap term a0 dt^2 / 2
     om_hi, om_lo = split_angle_delta(com * dt)                 # (omega dt with its 8 extra bits)
     soa[W_SANGLE] = _bits(om_hi)
     soa[W_DRY] = _bits(cdry)
@@ -120,7 +136,8 @@ def fresh_state_soa(x, y, vx, vy, angle, ang_vel, dry_mass, fuel, steps=0, ep_re
 
 
 def state_soa_from_reference(state: np.ndarray, prev: np.ndarray, steps, dt: float,
-                             ep_return=0.0, fuel_unit: float = DEFAULT_FUEL_UNIT) -> np.ndarray:
+                             ep_return=0.0, fuel_unit: float = DEFAULT_FUEL_UNIT,
+                             pos_unit: float = DEFAULT_POS_UNIT) -> np.ndarray:
     """Mid-episode injection from the reference's dicts.
 
     ``state`` [N,10] float64 in the reference's word order (x y vx vy ax ay angle
@@ -132,10 +149,11 @@ def state_soa_from_reference(state: np.ndarray, prev: np.ndarray, steps, dt: flo
     prev = np.asarray(prev, np.float64)
     n = state.shape[0]
     soa = np.zeros((10, n), np.int32)
-    soa[W_X], soa[W_Y] = _bits(state[:, 0]), _bits(state[:, 1])
+    soa[W_X], soa[W_Y] = _pos_units(state[:, 0], pos_unit), _pos_units(state[:, 1], pos_unit)
     soa[W_ANGLE] = _angle_units(state[:, 6])
-    soa[W_SX] = np.rint((state[:, 0] - prev[:, 0]) * DELTA_UNITS_PER_M).astype(np.int32)
-    soa[W_SY] = np.rint((state[:, 1] - prev[:, 1]) * DELTA_UNITS_PER_M).astype(np.int32)
+    per_m = DELTA_UNITS_PER_POS_UNIT / pos_unit
+    soa[W_SX] = np.rint((state[:, 0] - prev[:, 0]) * per_m).astype(np.int32)
+    soa[W_SY] = np.rint((state[:, 1] - prev[:, 1]) * per_m).astype(np.int32)
     pre_wrap = state[:, 7] * dt
     hi, lo = split_angle_delta(pre_wrap)
     soa[W_SANGLE] = _bits(hi)
@@ -147,13 +165,14 @@ def state_soa_from_reference(state: np.ndarray, prev: np.ndarray, steps, dt: flo
     return soa
 
 
-def reference_view(soa: np.ndarray, dt: float, fuel_unit: float = DEFAULT_FUEL_UNIT) -> dict:
+def reference_view(soa: np.ndarray, dt: float, fuel_unit: float = DEFAULT_FUEL_UNIT,
+                   pos_unit: float = DEFAULT_POS_UNIT) -> dict:
     """Public format -> the words of the reference's ``Rocket.state`` (float64 arrays) plus
     ``steps`` / ``fresh`` / ``wraps`` / ``ep_return``.  ``ax`` / ``ay`` are not persistent state
     (they are outputs of a step) and are not included.
 
     Velocities and the angle are formed in float32 exactly as the kernel forms the values it
-    feeds its reward / termination tests (``delta * 2^-23 * (1/dt)``, ``units * 360/2^32``), so
+    feeds its reward / termination tests (``float(units) * unit``, ``delta * unit * (1/dt)``), so
     that the reference's decision functions evaluated on this view agree with the kernel's flags
     bit for bit."""
     soa = as_words(soa)
@@ -162,7 +181,8 @@ def reference_view(soa: np.ndarray, dt: float, fuel_unit: float = DEFAULT_FUEL_U
     wraps = ((meta >> META_WRAP_SHIFT) & 7).astype(np.int64)
     wraps = np.where(wraps >= 4, wraps - 8, wraps)
     inv_dt = np.float32(1.0 / dt)
-    unit = np.float32(1.0 / DELTA_UNITS_PER_M)
+    unit = np.float32(pos_unit / DELTA_UNITS_PER_POS_UNIT)
+    punit = np.float32(pos_unit)
     f = lambda w: soa[w].view(np.float32)                                   # noqa: E731
 
     def vel(w):                                   # (also while FRESH: the slots then hold v dt)
@@ -170,7 +190,8 @@ def reference_view(soa: np.ndarray, dt: float, fuel_unit: float = DEFAULT_FUEL_U
 
     ang = soa[W_ANGLE].astype(np.float32) * np.float32(1.0 / ANGLE_UNITS_PER_DEG)
     om = (f(W_SANGLE) * inv_dt).astype(np.float64)
-    return {"x": f(W_X).astype(np.float64), "y": f(W_Y).astype(np.float64),
+    return {"x": (soa[W_X].astype(np.float32) * punit).astype(np.float64),
+            "y": (soa[W_Y].astype(np.float32) * punit).astype(np.float64),
             "vx": vel(W_SX), "vy": vel(W_SY), "angle": ang.astype(np.float64),
             "ang_vel": om, "dry_mass": f(W_DRY).astype(np.float64),
             "fuel": soa[W_FUEL].astype(np.float64) * fuel_unit,

@@ -45,6 +45,7 @@ class RocketLandingEnv:
                                      C.byref(handle)), "rl_create")
         self._h = handle
         self.fuel_unit = float(self._L.rl_fuel_unit(self._h))
+        self.pos_unit = float(self._L.rl_pos_unit(self._h))
         self._act = np.zeros((1, 2), np.float32)
         self._obs = np.zeros((1, 8), np.float32)
         self._rew = np.zeros((1,), np.float32)
@@ -78,7 +79,7 @@ class RocketLandingEnv:
 
     def _get_info(self) -> Dict[str, Any]:
         _lib.check(self._L.rl_get_state_host(self._h, self._soa.ctypes.data), "rl_get_state_host")
-        v = reference_view(self._soa, self.dt, self.fuel_unit)
+        v = reference_view(self._soa, self.dt, self.fuel_unit, self.pos_unit)
         vx, vy = float(v["vx"][0]), float(v["vy"][0])
         state = {"x": float(v["x"][0]), "y": float(v["y"][0]), "vx": vx, "vy": vy,
                  "ax": self._accel[0], "ay": self._accel[1], "angle": float(v["angle"][0]),

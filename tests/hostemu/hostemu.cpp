@@ -35,13 +35,13 @@ static inline void s32(float* soa, int64_t n, int w, int64_t i, uint32_t u) { st
 static inline float wf(const float* soa, int64_t n, int w, int64_t i) { return soa[w * n + i]; }
 
 static void load_rocket(const float* soa, int64_t n, int64_t i, rl::Rocket& r) {
-    r.x = wf(soa, n, RL_W_X, i); r.y = wf(soa, n, RL_W_Y, i); r.ang = (int32_t)w32(soa, n, RL_W_ANGLE, i);
+    r.x = (int32_t)w32(soa, n, RL_W_X, i); r.y = (int32_t)w32(soa, n, RL_W_Y, i); r.ang = (int32_t)w32(soa, n, RL_W_ANGLE, i);
     r.sx = (int32_t)w32(soa, n, RL_W_SX, i); r.sy = (int32_t)w32(soa, n, RL_W_SY, i); r.sang = wf(soa, n, RL_W_SANGLE, i);
     r.dry = wf(soa, n, RL_W_DRY, i); r.fuel = (int32_t)w32(soa, n, RL_W_FUEL, i);
     r.meta = w32(soa, n, RL_W_META, i); r.ep_ret = wf(soa, n, RL_W_EPRET, i);
 }
 static void store_rocket(float* soa, int64_t n, int64_t i, const rl::Rocket& r) {
-    soa[RL_W_X * n + i] = r.x; soa[RL_W_Y * n + i] = r.y; s32(soa, n, RL_W_ANGLE, i, (uint32_t)r.ang);
+    s32(soa, n, RL_W_X, i, (uint32_t)r.x); s32(soa, n, RL_W_Y, i, (uint32_t)r.y); s32(soa, n, RL_W_ANGLE, i, (uint32_t)r.ang);
     s32(soa, n, RL_W_SX, i, (uint32_t)r.sx); s32(soa, n, RL_W_SY, i, (uint32_t)r.sy); soa[RL_W_SANGLE * n + i] = r.sang;
     soa[RL_W_DRY * n + i] = r.dry; s32(soa, n, RL_W_FUEL, i, (uint32_t)r.fuel);
     s32(soa, n, RL_W_META, i, r.meta); soa[RL_W_EPRET * n + i] = r.ep_ret;
@@ -109,11 +109,14 @@ int emu_sim_step(const RlParams* p, float* soa, int64_t n, const float* actions,
         const float th = std::fmin(std::fmax(actions[2 * i], 0.0f), 1.0f);
         const float cg = std::fmin(std::fmax(actions[2 * i + 1], -1.0f), 1.0f);
         rl::StepResult o;
+        const int32_t x0 = r.x, y0 = r.y;
         rl::rocket_step(P, r, th, cg, o);
+        if (((x0 ^ r.x) < 0) && (x0 > 0x40000000 || x0 < -0x40000000)) r.x = x0 > 0 ? INT32_MAX : INT32_MIN;
+        if (((y0 ^ r.y) < 0) && (y0 > 0x40000000 || y0 < -0x40000000)) r.y = y0 > 0 ? INT32_MAX : INT32_MIN;
         const bool landed = o.terminated;
         if (landed) r.meta |= kLanded | ((uint32_t)o.landing << 27);
         store_rocket(soa, n, i, r);
-        const float rv[16] = {r.x, r.y, o.vx, o.vy, o.ax, o.ay, rl::angle_deg(r.ang), o.om,
+        const float rv[16] = {(float)r.x * P.pos_unit, (float)r.y * P.pos_unit, o.vx, o.vy, o.ax, o.ay, rl::angle_deg(r.ang), o.om,
                               o.alpha, r.dry, (float)((double)r.fuel * P.fuel_unit_d), o.reward, landed ? 0.0f : actions[2 * i],
                               landed ? 0.0f : actions[2 * i + 1], (float)o.landing, 1.0f};
         std::memcpy(rec, rv, sizeof(rv));

@@ -70,10 +70,11 @@ LAND_V = (30.0, 40.0, 100.0)
 LAND_A = (5.0, 8.0, 10.0)
 
 
-def _fresh_soa(states: np.ndarray, steps=0, fuel_unit=layout.DEFAULT_FUEL_UNIT, dt=0.1) -> np.ndarray:
+def _fresh_soa(states: np.ndarray, steps=0, fuel_unit=layout.DEFAULT_FUEL_UNIT, dt=0.1,
+               pos_unit=layout.DEFAULT_POS_UNIT) -> np.ndarray:
     s = np.asarray(states, np.float64)
     return layout.fresh_state_soa(s[:, 0], s[:, 1], s[:, 2], s[:, 3], s[:, 6], s[:, 7], s[:, 8],
-                                  s[:, 9], steps=steps, fuel_unit=fuel_unit, dt=dt)
+                                  s[:, 9], steps=steps, fuel_unit=fuel_unit, dt=dt, pos_unit=pos_unit)
 
 
 # ----------------------------------------------------------------------------------------
@@ -102,10 +103,11 @@ class HostEmuStepper:
         self.params = params or load_params()
         self.dt = self.params.time_step
         self.fuel_unit = layout.fuel_unit_for(self.params.reset_high[9])
+        self.pos_unit = layout.pos_unit_for(self.params)
         self.soa = np.zeros((10, n), np.int32)
 
     def inject_fresh(self, states: np.ndarray, mask=None, steps=0) -> None:
-        new = _fresh_soa(states, steps, self.fuel_unit, self.dt)
+        new = _fresh_soa(states, steps, self.fuel_unit, self.dt, self.pos_unit)
         if mask is None:
             self.soa[:] = new
         else:
@@ -128,7 +130,7 @@ class HostEmuStepper:
         return obs, rew, term.astype(bool), trunc.astype(bool), land
 
     def view(self) -> dict:
-        return layout.reference_view(self.soa, self.dt, self.fuel_unit)
+        return layout.reference_view(self.soa, self.dt, self.fuel_unit, self.pos_unit)
 
     def philox_reset(self, gid0: int, seed: int, epoch: int):
         obs = np.zeros((self.n, 8), np.float32)
@@ -159,7 +161,7 @@ class GpuStepper:
         self.dt = self.env.dt
 
     def inject_fresh(self, states: np.ndarray, mask=None, steps=0) -> None:
-        self.env.set_state(self.torch.from_numpy(_fresh_soa(states, steps, self.env.fuel_unit, self.dt)),
+        self.env.set_state(self.torch.from_numpy(_fresh_soa(states, steps, self.env.fuel_unit, self.dt, self.env.pos_unit)),
                            None if mask is None else self.torch.from_numpy(np.asarray(mask, np.uint8)))
 
     def inject_soa(self, soa: np.ndarray) -> None:

@@ -47,11 +47,17 @@ def test_header_constants_match_python_layout():
     assert val("RL_META_DLO_SHIFT") == layout.META_DLO_SHIFT
     assert val("RL_META_WRAP_SHIFT") == layout.META_WRAP_SHIFT
     assert "RL_ANGLE_UNITS_PER_DEG (4294967296.0 / 360.0)" in text and layout.ANGLE_UNITS_PER_DEG == 4294967296.0 / 360.0
-    assert "RL_DELTA_UNITS_PER_M 8388608.0" in text and layout.DELTA_UNITS_PER_M == 8388608.0
+    assert val("RL_DELTA_UNITS_PER_POS_UNIT") == layout.DELTA_UNITS_PER_POS_UNIT == 256
     # the fixed-point fuel unit: library and Python helper derive the same power of two
     lib = _lib.load()
     p = load_params()
     assert lib.rl_fuel_unit_for(C.byref(p)) == layout.fuel_unit_for(p.reset_high[9]) == layout.DEFAULT_FUEL_UNIT
+    p = load_params()
+    assert lib.rl_pos_unit_for(C.byref(p)) == layout.pos_unit_for(p) == layout.DEFAULT_POS_UNIT == 2.0 ** -15
+    for world in (10.0, 50412.0, 50413.0, 2.0e6):           # 1.3 x 50 412.3 = 65 536
+        p.max_horizontal_position = world
+        assert lib.rl_pos_unit_for(C.byref(p)) == layout.pos_unit_for(p)
+    p = load_params()
     for hi in (0.5, 1.0, 3.0, 524287.0, 524288.0, 1.0e9):
         p.reset_high[9] = hi
         u = lib.rl_fuel_unit_for(C.byref(p))

@@ -166,7 +166,7 @@ def test_thousand_step_episodes_against_c_oracle(action_fn):
                                     action_fn=action_fn)
     rep.assert_ok(max_guard_events=0)
     assert rep.steps_compared == n * 1000 and rep.episodes == n          # every rocket flew to the limit
-    assert rep.max_state_err.max() < 0.8 and rep.max_obs_err < 0.8, rep.summary()
+    assert rep.max_state_err.max() < 0.5 and rep.max_obs_err < 0.5, rep.summary()
     assert rep.reward_guard_events < 0.05 * n * 1000
 
 
@@ -180,7 +180,7 @@ def test_thousand_step_reference_trajectories_replayed(golden_dir, name):
     rep = parity.replay_golden_rollout(parity.HostEmuStepper(8), g)
     rep.assert_ok(max_guard_events=1)
     assert rep.steps_compared >= 8 * 1100 - 2
-    assert rep.max_state_err.max() < 0.8 and rep.max_obs_err < 0.8, rep.summary()
+    assert rep.max_state_err.max() < 0.5 and rep.max_obs_err < 0.5, rep.summary()
 
 
 def test_another_configuration_flown_to_its_time_limit():
@@ -193,8 +193,9 @@ def test_another_configuration_flown_to_its_time_limit():
     assert st.fuel_unit == 2.0 ** -11 and st.L.emu_matches_default(__import__("ctypes").addressof(p)) == 0
     rep = parity.lockstep_vs_oracle(st, c_oracle.BatchOracle(n, parity.constants_from_params(p)), 1500, seed=9,
                                     action_fn=parity.hover_actions)
-    rep.assert_ok(max_guard_events=0)                     # (x reaches 0.9 of the tolerance: 1500 steps of fp32 x rounding)
+    rep.assert_ok(max_guard_events=0)
     assert rep.steps_compared == n * 1500 and rep.episodes == n
+    assert rep.max_state_err.max() < 0.5 and rep.max_obs_err < 0.5, rep.summary()
 
 
 def test_plain_fp32_accumulators_would_drift():
@@ -215,7 +216,7 @@ def test_plain_fp32_accumulators_would_drift():
         orc.step(a)
         soa = st.soa
         # degrade: deltas, angle, fuel, angle-delta extension back to 24 significant bits
-        for w in (L.W_SX, L.W_SY, L.W_ANGLE, L.W_FUEL):
+        for w in (L.W_X, L.W_Y, L.W_SX, L.W_SY, L.W_ANGLE, L.W_FUEL):
             soa[w] = soa[w].astype(np.float32).astype(np.int64).clip(-2**31, 2**31 - 1).astype(np.int32)
         soa[L.W_META] &= ~np.int32(0xFF << L.META_DLO_SHIFT)
         err = np.abs(st.view()["vx"] - orc.rockets["vx"]) / (parity.RTOL * np.maximum(np.abs(orc.rockets["vx"]), 25.0))
