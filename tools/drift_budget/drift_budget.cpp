@@ -49,8 +49,8 @@ void abl_step(int bits,double*st,int64_t n,const float*act,double*out){
     if(bits&1024) ndy=dy+rint((double)((float)ay*dt2)/XU)*XU; else if(bits&(8|256)) ndy=dy+ay*(dtd*dtd); else ndy=fmaf((float)ay,dt2,(float)dy);
     if(bits&2) ndang=dang*0.995+alpha*(dtd*dtd); else ndang=fmaf((float)dang,damp,(float)alpha*dt2);
     if(bits&2048){ float hi=(float)ndang; double r=ndang-(double)hi; int e; frexp((double)hi,&e); double u=ldexp(1.0,e-24-8); double lo=rint(r/u); if(lo>127)lo=127; if(lo<-128)lo=-128; ndang=(double)hi+lo*u; }
-    double nx=(bits&1024)?(double)((float)x+(float)ndx):(bits&4)?x+ndx:(double)((float)x+(float)ndx);
-    double ny=(bits&1024)?(double)((float)y+(float)ndy):(bits&(8|512))?y+ndy:(double)((float)y+(float)ndy);
+    double nx=(bits&4096)?(x+floor(ndx*32768.0+0.5)/32768.0):(bits&1024)?(double)((float)x+(float)ndx):(bits&4)?x+ndx:(double)((float)x+(float)ndx);
+    double ny=(bits&4096)?(y+floor(ndy*32768.0+0.5)/32768.0):(bits&1024)?(double)((float)y+(float)ndy):(bits&(8|512))?y+ndy:(double)((float)y+(float)ndy);
     int k; double nang; if(bits&128){ const double U=360.0/4294967296.0; nang=norm_angle(ang+ndang,k); nang=rint(nang/U)*U; if(nang>=180.0){nang-=360.0;++k;} } else nang=(bits&2)?norm_angle(ang+ndang,k):(double)(float)norm_angle((double)((float)ang+(float)ndang),k);
     double nfuel; if(bits&128){ const double FU=1.0/8192.0; nfuel=fmax(0.0,fuel-rint(fmax(0.0,(double)th*170.0)/FU)*FU);} else nfuel=(bits&1)?fmax(0.0,fuel-fmax(0.0,(double)th*170.0)):(double)fmaxf(0.f,(float)fuel-fmaxf(0.f,th*burn));
     s[0]=nx;s[1]=ny;s[2]=nang;s[3]=ndx;s[4]=ndy;s[5]=ndang;s[7]=nfuel;s[8]=k;s[9]=0;

@@ -8,9 +8,10 @@ drift_budget.cpp restates the PHYSICS of one step (no reward) with a precision s
    16 all force arithmetic    32 total mass and 1/m                64 sin / cos
   128 the SHIPPED scheme: fuel / angle fixed point, 1/m and alpha dt^2 in fp64 (with bit 2: angle delta in fp64)
   256 dy only   512 y only   1024 dx, dy as 2^-23 m fixed point   2048 angle delta = fp32 + 8 bits
+ 4096 x, y as 2^-15 m fixed point (with 1024)
 and the script flies 512 rockets for 1000 steps under the hover controller of tests/parity.py against
 the fp64 C oracle, printing the worst error of each state word in units of the tolerance
-1e-5 * max(|ref|, scale).  bits = 0 is the round-1 kernel's arithmetic; 3202 (= 2048 + 1024 + 128 + 2)
+1e-5 * max(|ref|, scale).  bits = 0 is the round-1 kernel's arithmetic; 7298 (= 4096 + 2048 + 1024 + 128 + 2)
 is what csrc/rl_device.cuh does now.  TEST / ANALYSIS TOOL: not part of the product, uses the oracle."""
 import ctypes as C
 import os
@@ -58,9 +59,10 @@ if __name__=="__main__":
              4: "+ x, dx carried exactly", 8: "+ y, dy carried exactly", 16: "+ all forces in fp64", 32: "+ 1/m in fp64",
              64: "+ sin/cos in fp64", 3: "fuel + angle chain exact", 15: "every carried word exact, forces fp32",
              18: "angle chain exact + forces fp64", 31: "every carried word exact + forces fp64",
-             130: "shipped: fuel/angle fixed point, fp64 torque chain (fp32 dx, dy)",
+             130: "fuel / angle fixed point + fp64 torque chain (x, y, dx, dy still fp32)",
              386: "... + dy exact", 1154: "... + dx, dy 2^-23 m fixed point",
-             3202: "SHIPPED scheme (rl_device.cuh): ... + angle delta fp32 + 8 bits"}
-    for bits in [int(b) for b in sys.argv[1:]] or [0, 1, 2, 4, 8, 16, 32, 64, 3, 15, 18, 31, 130, 386, 1154, 3202]:
+             3202: "... + angle delta fp32 + 8 bits (x, y still fp32)",
+             7298: "SHIPPED scheme (rl_device.cuh): ... + x, y 2^-15 m fixed point"}
+    for bits in [int(b) for b in sys.argv[1:]] or [0, 1, 2, 4, 8, 16, 32, 64, 3, 15, 18, 31, 130, 386, 1154, 3202, 7298]:
         mx, _ = run(bits)
         print(f"bits={bits:5d}  " + " ".join(f"{n}={e:6.3f}" for n, e in zip(names, mx)) + "   " + LABEL.get(bits, ""), flush=True)
