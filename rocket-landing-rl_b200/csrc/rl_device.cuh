@@ -315,7 +315,11 @@ __device__ __forceinline__ void flight_end(Rocket& r, const Flight& f) {
 //
 // rocket_advance does everything except the observation and the meta word: `f` describes the state
 // before the step on entry and the state after it on return (ready for the next fused substep).
-template <class PP>
+// kClampPos (simulation mode only): that mode has no bounds check (controls.py:89 ignores truncation),
+// so a rocket can reach the edge of the fixed-point position grid; it then stays there instead of
+// wrapping around.  The gym step does not need the check: reward.py:274-276 ends the episode at
+// 1 / 1.3 of the grid.
+template <class PP, bool kClampPos = false>
 __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, Flight& f, float th_raw, float cg_raw,
                                                StepResult& o) {
     const bool fresh = f.fresh;
@@ -377,8 +381,13 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, Flight& f
         // x' = x + dx', rounded to the position grid (ties up).  No overflow check here: the grid spans
         // 1.3 x the bounds at which reward.py:274-276 ends the episode (the simulation mode, which has
         // no bounds, clamps in its own kernel)
+        const int32_t x0 = r.x, y0 = r.y;
         r.x += (ndx + (1 << (kDeltaShift - 1))) >> kDeltaShift;
         r.y += (ndy + (1 << (kDeltaShift - 1))) >> kDeltaShift;
+        if constexpr (kClampPos) {                             // sign flip far from zero = wrap-around
+            if (((x0 ^ r.x) < 0) && (x0 > 0x40000000 || x0 < -0x40000000)) r.x = x0 > 0 ? INT32_MAX : INT32_MIN;
+            if (((y0 ^ r.y) < 0) && (y0 > 0x40000000 || y0 < -0x40000000)) r.y = y0 > 0 ? INT32_MAX : INT32_MIN;
+        }
         vx_a = sxf * P.inv_dt;
         vy_a = syf * P.inv_dt;
         speed_chk = fmaxf(fabsf(sxf), fabsf(syf));
@@ -498,12 +507,12 @@ __device__ __forceinline__ void step_obs(const PP& P, const Rocket& r, const Fli
     clip_obs(P, f.x, f.y, f.vx, f.vy, o.ax, o.ay, f.ang, f.om, o.obs);
 }
 
-template <class PP>
+template <class PP, bool kClampPos = false>
 __device__ __forceinline__ void rocket_step(const PP& P, Rocket& r, float th_raw, float cg_raw,
                                             StepResult& o) {
     Flight f;
     flight_begin(P, r, f);
-    rocket_advance(P, r, f, th_raw, cg_raw, o);
+    rocket_advance<PP, kClampPos>(P, r, f, th_raw, cg_raw, o);
     flight_end(r, f);
     step_obs(P, r, f, o);
 }

@@ -40,12 +40,8 @@ __global__ void __launch_bounds__(kCtaThreads) sim_step_kernel(const __grid_cons
         const float2 act = actions[i];
         const float th = clipf(act.x, 0.0f, 1.0f), cg = clipf(act.y, -1.0f, 1.0f);     // controls.py:72-73
         StepResult o;
-        const int32_t x0 = r.x, y0 = r.y;
-        rocket_step(P, r, th, cg, o);                     // the reward sees the CLIPPED action here
-        // this mode has no bounds check (controls.py:89 ignores truncation): a rocket that reaches the
-        // edge of the fixed-point position grid (1.3 x the gym env's bounds) stays there instead of wrapping
-        if (((x0 ^ r.x) < 0) && (x0 > 0x40000000 || x0 < -0x40000000)) r.x = x0 > 0 ? INT32_MAX : INT32_MIN;
-        if (((y0 ^ r.y) < 0) && (y0 > 0x40000000 || y0 < -0x40000000)) r.y = y0 > 0 ? INT32_MAX : INT32_MIN;
+        rocket_step<PP, true>(P, r, th, cg, o);           // the reward sees the CLIPPED action here; positions clamp
+                                                          // at the edge of the fixed-point grid (no bounds check in this mode)
         const float vx = o.vx, vy = o.vy, om = o.om;      // (delta / dt of the state just written)
         const bool landed = o.terminated;                 // the truncation flag is ignored (controls.py:89)
         if (landed) r.meta |= kMetaLanded | ((uint32_t)o.landing << kMetaCodeShift);

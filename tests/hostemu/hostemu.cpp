@@ -109,10 +109,7 @@ int emu_sim_step(const RlParams* p, float* soa, int64_t n, const float* actions,
         const float th = std::fmin(std::fmax(actions[2 * i], 0.0f), 1.0f);
         const float cg = std::fmin(std::fmax(actions[2 * i + 1], -1.0f), 1.0f);
         rl::StepResult o;
-        const int32_t x0 = r.x, y0 = r.y;
-        rl::rocket_step(P, r, th, cg, o);
-        if (((x0 ^ r.x) < 0) && (x0 > 0x40000000 || x0 < -0x40000000)) r.x = x0 > 0 ? INT32_MAX : INT32_MIN;
-        if (((y0 ^ r.y) < 0) && (y0 > 0x40000000 || y0 < -0x40000000)) r.y = y0 > 0 ? INT32_MAX : INT32_MIN;
+        rl::rocket_step<rl::DevParams, true>(P, r, th, cg, o);
         const bool landed = o.terminated;
         if (landed) r.meta |= kLanded | ((uint32_t)o.landing << 27);
         store_rocket(soa, n, i, r);
