@@ -5,7 +5,9 @@ the C oracle) and applies the stated tolerances.
 Two legs run on every step.
 
 FREE-RUNNING (the stepper's trajectory against the reference's from the same injected
-reset state; errors accumulate over the episode, ~120 steps):
+reset state; errors accumulate over the whole episode -- ~120 steps under random actions, the
+full 1000 (``lander.py:237-241``) under the hover / tilted-cruise controllers and in the
+reference's own agent-flown trajectories of ``tests/golden/ref_long_*.npz``):
 
 * state / observation words: ``|got - ref| <= RTOL * max(|ref|, SCALE[word])``, ``RTOL = 1e-5``
   (the bar of BASELINE.json ``north_star``: "rel 1e-5 per step", scale-relative as in
