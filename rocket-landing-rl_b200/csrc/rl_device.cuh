@@ -145,6 +145,10 @@ inline long long rl_d2ll(double d) {
 inline double rl_pow2_bits(uint32_t biased) { const uint64_t b = (uint64_t)biased << 52; double d; std::memcpy(&d, &b, 8); return d; }
 #endif
 
+// int32 add / subtract with two's-complement wrap-around (signed overflow is undefined in C++)
+__device__ __forceinline__ int32_t rl_wrap_add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+__device__ __forceinline__ int32_t rl_wrap_sub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+
 // ---- the 32-bit-mantissa angle delta: sang (fp32) + lo * ulp(sang) / 256, lo in [-128, 127] ----
 // unit of the low part of a value whose high part has the biased fp32 exponent E: 2^(E - 127 - 31)
 __device__ __forceinline__ double dtheta_join(float hi, int lo) {
@@ -366,24 +370,23 @@ __device__ __forceinline__ void rocket_advance(const PP& P, Rocket& r, Flight& f
             // Verlet bootstrap (base.py:65-130): x - x_prev = v dt - a0 dt^2 / 2 (the slots hold v dt)
             // and, alpha0 being 0, angle - angle_prev = omega dt with the previous angle normalised
             // (base.py:117), which only matters within one step of +-180
-            dx -= rl_f2i(a0x * P.half_dt2_units);
-            dy -= rl_f2i(a0y * P.half_dt2_units);
+            dx = rl_wrap_sub(dx, rl_f2i(a0x * P.half_dt2_units));
+            dy = rl_wrap_sub(dy, rl_f2i(a0y * P.half_dt2_units));
             if (!(fabsf(ang_b) + fabsf(r.sang) < 179.0f)) {
                 const double prev = (double)r.ang * kAngleUnit - dang_d;
                 dang_d += 360.0 * floor((prev + 180.0) * (1.0 / 360.0));
             }
         }
         // engine.py:181-222
-        const int32_t ndx = dx + rl_f2i(ax * P.dt2_units);
-        const int32_t ndy = dy + rl_f2i(ay * P.dt2_units);
+        const int32_t ndx = rl_wrap_add(dx, rl_f2i(ax * P.dt2_units));        // (two's-complement wrap is well defined
+        const int32_t ndy = rl_wrap_add(dy, rl_f2i(ay * P.dt2_units));        // here; speed_chk below reports it)
         const double ndang_d = fma(dang_d, P.damp_d, adt2_d);
         const float sxf = (float)ndx * P.delta_unit, syf = (float)ndy * P.delta_unit;
-        // x' = x + dx', rounded to the position grid (ties up).  No overflow check here: the grid spans
-        // 1.3 x the bounds at which reward.py:274-276 ends the episode (the simulation mode, which has
-        // no bounds, clamps in its own kernel)
+        // x' = x + dx', rounded to the position grid (ties up).  No overflow check in the gym step: the grid
+        // spans 1.3 x the bounds at which reward.py:274-276 ends the episode (kClampPos: the simulation mode)
         const int32_t x0 = r.x, y0 = r.y;
-        r.x += (ndx + (1 << (kDeltaShift - 1))) >> kDeltaShift;
-        r.y += (ndy + (1 << (kDeltaShift - 1))) >> kDeltaShift;
+        r.x = rl_wrap_add(x0, rl_wrap_add(ndx, 1 << (kDeltaShift - 1)) >> kDeltaShift);
+        r.y = rl_wrap_add(y0, rl_wrap_add(ndy, 1 << (kDeltaShift - 1)) >> kDeltaShift);
         if constexpr (kClampPos) {                             // sign flip far from zero = wrap-around
             if (((x0 ^ r.x) < 0) && (x0 > 0x40000000 || x0 < -0x40000000)) r.x = x0 > 0 ? INT32_MAX : INT32_MIN;
             if (((y0 ^ r.y) < 0) && (y0 > 0x40000000 || y0 < -0x40000000)) r.y = y0 > 0 ? INT32_MAX : INT32_MIN;

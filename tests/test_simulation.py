@@ -113,19 +113,33 @@ def test_host_build_of_the_sim_mode_matches_the_reference_stream(golden):
     print("sim mode (host build) worst err / tol:", dict(zip(FIELDS[:11], worst[:11].round(3))))
 
 
-def test_sim_mode_rocket_stops_at_the_edge_of_the_position_grid():
-    """The simulation mode has no bounds check (controls.py:89 ignores truncation), so a rocket under
-    full throttle eventually leaves the fixed-point position grid (+-65 536 m for the reference's
-    world): it must stay at the edge, not wrap around to the other side."""
+def _edge_states():
     n = 4
-    st = parity.HostEmuStepper(n)
-    st.L.emu_sim_step.argtypes = [C.c_void_p] * 2 + [C.c_int64] + [C.c_void_p] * 2
     init = np.zeros((n, 10))
     init[:, 0] = [0.0, 65000.0, -65000.0, 100.0]                 # x
     init[:, 1] = [64000.0, 1000.0, 1000.0, 2000.0]               # y
     init[:, 2] = [0.0, 240.0, -240.0, 0.0]                       # vx
     init[:, 3] = [240.0, 0.0, 0.0, -10.0]                        # vy
     init[:, 8], init[:, 9] = 36000.0, 400000.0
+    return init
+
+
+def _check_edge(xs, ys):
+    xs, ys = np.array(xs), np.array(ys)
+    assert (np.diff(ys[:, 0]) >= 0).all() and ys[-1, 0] == pytest.approx(65536.0, abs=1e-2)     # climbs, then sits at the top
+    assert (np.diff(xs[:, 1]) >= 0).all() and xs[-1, 1] == pytest.approx(65536.0, abs=1e-2)
+    assert (np.diff(xs[:, 2]) <= 0).all() and xs[-1, 2] == pytest.approx(-65536.0, abs=1e-2)
+    assert abs(xs[-1, 3] - 100.0) < 1.0 and ys[:, 3].max() < 60000.0                          # an ordinary rocket is untouched
+
+
+def test_sim_mode_rocket_stops_at_the_edge_of_the_position_grid():
+    """The simulation mode has no bounds check (controls.py:89 ignores truncation), so a rocket under
+    full throttle eventually leaves the fixed-point position grid (+-65 536 m for the reference's
+    world): it must stay at the edge, not wrap around to the other side."""
+    init = _edge_states()
+    n = init.shape[0]
+    st = parity.HostEmuStepper(n)
+    st.L.emu_sim_step.argtypes = [C.c_void_p] * 2 + [C.c_int64] + [C.c_void_p] * 2
     st.inject_fresh(init)
     a = np.tile(np.array([[1.0, 0.0]], np.float32), (n, 1))
     rec = np.zeros((n, 16), np.float32)
@@ -134,11 +148,24 @@ def test_sim_mode_rocket_stops_at_the_edge_of_the_position_grid():
         assert st.L.emu_sim_step(C.addressof(st.params), st.soa.ctypes.data, n, a.ctypes.data, rec.ctypes.data) == 0
         xs.append(rec[:, 0].copy())
         ys.append(rec[:, 1].copy())
-    xs, ys = np.array(xs), np.array(ys)
-    assert (np.diff(ys[:, 0]) >= 0).all() and ys[-1, 0] == pytest.approx(65536.0, abs=1e-2)     # climbs, then sits at the top
-    assert (np.diff(xs[:, 1]) >= 0).all() and xs[-1, 1] == pytest.approx(65536.0, abs=1e-2)
-    assert (np.diff(xs[:, 2]) <= 0).all() and xs[-1, 2] == pytest.approx(-65536.0, abs=1e-2)
-    assert abs(xs[-1, 3] - 100.0) < 1.0 and ys[:, 3].max() < 60000.0                          # an ordinary rocket is untouched
+    _check_edge(xs, ys)
+
+
+@pytest.mark.gpu
+def test_cuda_sim_mode_rocket_stops_at_the_edge_of_the_position_grid():
+    from rocket_landing_rl_b200 import RocketSimulation
+    s = _edge_states()
+    n = s.shape[0]
+    sim = RocketSimulation(n)
+    sim.set_state(layout.fresh_state_soa(s[:, 0], s[:, 1], s[:, 2], s[:, 3], s[:, 6], s[:, 7], s[:, 8], s[:, 9]))
+    a = np.tile(np.array([[1.0, 0.0]], np.float32), (n, 1))
+    xs, ys = [], []
+    for t in range(400):
+        rec = RocketSimulation.decode(sim.step(a))
+        xs.append(rec[:, 0].copy())
+        ys.append(rec[:, 1].copy())
+    _check_edge(xs, ys)
+    sim.close()
 
 
 @pytest.mark.gpu
