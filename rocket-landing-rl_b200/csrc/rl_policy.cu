@@ -186,6 +186,365 @@ __device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
     return y;
 }
 
+#ifndef RL_MLP_PIPE
+#define RL_MLP_PIPE 1                       // 1: warp-specialised kernel below; 0: the round-1 kernel (kept for A/B runs)
+#endif
+
+#if RL_MLP_PIPE
+// ---------------------------------------------------------------------------------------------------
+// Warp-specialised version.  What bounds this kernel is the MUFU pipe (512 tanh per rocket); the
+// tensor core needs half that time.  The round-1 kernel moved all 16 warps in lockstep through
+// epilogue 1 -> layer 2 -> epilogue 2 of a row block: whenever they met at a barrier, waited for a
+// TMEM load or for the last MMAs to drain, the MUFU pipe had nothing to do (58 % busy).  Here the
+// two epilogues belong to two teams of 8 warps that run one row block apart and only ever meet
+// through mbarriers, so that each scheduler always holds warps of both kinds:
+//   team X (warps 0..7)   epilogue 1: D1 -> tanh(. + b1) -> bf16 -> A2s, four K slices of 64 units
+//   team Y (warps 8..15)  epilogue 2: D2 -> tanh(. + b2) -> head, as two N halves (A: units 0..127, B: 128..255)
+//   warp 16               stages the observations (A1, two buffers) and issues every tcgen05.mma
+// Tensor memory (512 columns) cannot hold two whole layer-2 accumulators next to layer 1, so
+//   * layer 1 runs in four N = 64 slices through a two-slot ring, columns [0, 128): the slice two
+//     ahead is issued into a slot as soon as team X has drained it;
+//   * layer 2 runs as two N = 128 halves into THREE accumulators of 128 columns used in rotation
+//     (half A of block i -> accumulator 2 i mod 3, half B -> 2 i + 1 mod 3): half A follows team X
+//     slice by slice into the accumulator team Y drained one block ago; half B goes into the one
+//     that held half A of the previous block, from the moment team Y has drained that (about
+//     mid-way through epilogue 1), first catching up, then slice by slice.
+// No MMA waits for the END of an epilogue any more, and team X may start the next block at once:
+// A2s slice 0 has been read by then (barrier e0), slices 1..2 / 3 are released by the commits of
+// half A / B.
+constexpr int kSmA1b = kSmA1 + kM * 16 * 2;               // second observation buffer
+// Both biases come out of the tensor core as well: D = Ones (128 x 16: columns 0, 1 = 1) Bb^T + ..., with
+// Bb (256 x 16) = [high part of b | remainder | 0 ...].  Only the first 8 k's of a bias tile are stored: its
+// second K chunk (LBO = 4096 further on) meets the zero columns of Ones, so it may alias anything FINITE --
+// the next bias tile, and for the last one the first chunk of Ones.
+constexpr int kSmBb1 = kSmA1b + kM * 16 * 2;              // 256 x 8 bf16
+constexpr int kSmBb2 = kSmBb1 + kHidden * 8 * 2;
+constexpr int kSmOnes = kSmBb2 + kHidden * 8 * 2;         // 128 x 16 bf16, LBO 2048
+static_assert(kSmBb2 - kSmBb1 == kLboW && kSmOnes - kSmBb2 == kLboW, "aliased second K chunks");
+constexpr int kSmW3p = kSmOnes + kM * 16 * 2;
+constexpr int kSmB3p = kSmW3p + 2 * kHidden * 4;
+constexpr int kSmRedp = kSmB3p + 16;                      // 2 x [128 rows][2] f32: partial sums of one warp of a pair
+constexpr int kSmBarp = kSmRedp + 2 * kM * 2 * 4;
+constexpr int kNumBars = 11;                              // x_ready[4] | l1bar[2] | barA | e0 | barB | y_doneA | y_doneB
+constexpr int kSmemBytesP = kSmBarp + 8 * kNumBars + 8 + 16;
+static_assert(kSmemBytesP <= 227 * 1024, "shared memory budget");
+constexpr int kTeamWarps = 8;
+constexpr int kThreadsP = 32 * (2 * kTeamWarps + 1);      // 544
+
+__host__ __device__ constexpr uint32_t idesc_n(int n_cols) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
+}
+
+// The low word of a shared-memory descriptor holds (address >> 4) | (LBO >> 4) << 16, the high word SBO >> 4 and
+// the version: the issuing warp keeps one low word per operand array and adds (byte offset >> 4) per instruction.
+constexpr uint32_t kDescHi = (uint32_t)(kSbo >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ void mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .b64 a, b;\n\t.reg .pred p;\n\tmov.b64 a, {%1, %3};\n\tmov.b64 b, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %4, p;\n\t}\n"
+        :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void pair_barrier(int q) {             // the two team-Y warps that share TMEM lanes 32 q .. 32 q + 31
+    asm volatile("bar.sync %0, 64;" :: "r"(q + 1) : "memory");
+}
+
+template <int kOut>
+__global__ void __launch_bounds__(kThreadsP, 1) mlp_forward_tc5_kernel(const unsigned char* __restrict__ blob,
+                                                                const float* __restrict__ obs, float* __restrict__ out,
+                                                                int64_t n, const SampleArgs sa) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bars = sbase + kSmBarp;
+    const uint32_t x_ready = bars, l1bar = bars + 32, barA = bars + 48, e0 = bars + 56, barB = bars + 64, y_doneA = bars + 72,
+                   y_doneB = bars + 80;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBarp + 8 * kNumBars + 8);
+
+    // ---- one-time setup: weights in the canonical layout, barriers, tensor memory ------------------
+    for (int c = tid; c < kHidden * 32; c += kThreadsP) {                 // W2: chunk (row n, 8 k's kc); consecutive threads -> consecutive rows
+        const int n_row = c & 255, kc = c >> 8;
+        *reinterpret_cast<uint4*>(smem + kSmW2 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
+            *reinterpret_cast<const uint4*>(blob + kOffW2 + n_row * (kHidden * 2) + kc * 16);
+    }
+    for (int c = tid; c < kHidden * 2; c += kThreadsP) {                  // W1 stacked twice: 2 chunks per row
+        const int n_row = c & 255, kc = c >> 8;
+        *reinterpret_cast<uint4*>(smem + kSmW1 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
+            *reinterpret_cast<const uint4*>(blob + kOffW1 + n_row * 32 + kc * 16);
+    }
+    for (int c = tid; c < kM * 2; c += kThreadsP) {
+        const int r = c & 127, kc = c >> 7;
+        *reinterpret_cast<uint4*>(smem + kSmOnes + kc * kLboA + (r >> 3) * kSbo + (r & 7) * 16) =
+            make_uint4(kc == 0 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
+    }
+    for (int c = tid; c < kHidden * 2; c += kThreadsP) {                  // b1 | b2
+        const int n_row = c & 255, layer = c >> 8;
+        float hi, lo;
+        split_bf16(*reinterpret_cast<const float*>(blob + (layer ? kOffB2 : kOffB1) + n_row * 4), hi, lo);
+        *reinterpret_cast<uint4*>(smem + (layer ? kSmBb2 : kSmBb1) + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
+            make_uint4(pack_bf16(hi, lo), 0u, 0u, 0u);
+    }
+    for (int c = tid; c < (kSmRedp - kSmW3p) / 16; c += kThreadsP)        // W3 | b3
+        *reinterpret_cast<uint4*>(smem + kSmW3p + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffW3 + c * 16);
+    if (tid == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) mbar_init(x_ready + 8 * c, kTeamWarps);
+        mbar_init(l1bar, 1);
+        mbar_init(l1bar + 8, 1);
+        mbar_init(barA, 1);
+        mbar_init(e0, 1);
+        mbar_init(barB, 1);
+        mbar_init(y_doneA, kTeamWarps);
+        mbar_init(y_doneB, kTeamWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {                                              // one warp allocates all 512 columns (1 CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    const int64_t n_blocks = (n + kM - 1) / kM;
+    const int64_t stride = gridDim.x;
+    const int q = warp & 3;                                       // TMEM lane quarter of this warp
+    const int row = 32 * q + lane;                                // this thread's row of the block = its TMEM lane
+    const int yh = (warp >> 2) & 1;                               // team Y: which 64 of a half's 128 units
+
+    // Observations: the first four warps of team Y hold one row each, two blocks ahead, and stage it as
+    // A1 = [bf16 high parts | bf16 low parts] (two buffers, block i -> buffer i & 1).
+    const bool stager = warp >= kTeamWarps && warp < kTeamWarps + 4;
+    float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
+    auto load_obs = [&](int64_t blk) {
+        oa = ob = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int64_t r = blk * kM + row;
+        if (stager && blk < n_blocks && r < n) {
+            oa = *reinterpret_cast<const float4*>(obs + r * kObs);
+            ob = *reinterpret_cast<const float4*>(obs + r * kObs + 4);
+        }
+    };
+    auto stage_obs = [&](int buf) {
+        if (stager) {
+            const float x[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
+            float hi[8], lo[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) split_bf16(x[k], hi[k], lo[k]);
+            unsigned char* dst = smem + (buf ? kSmA1b : kSmA1) + (row >> 3) * kSbo + (row & 7) * 16;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
+            *reinterpret_cast<uint4*>(dst + kLboA) = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
+            fence_async_proxy();
+        }
+    };
+    load_obs(blockIdx.x);
+    stage_obs(0);
+    load_obs((int64_t)blockIdx.x + stride);
+    stage_obs(1);
+    load_obs((int64_t)blockIdx.x + 2 * stride);
+
+    fence_async_proxy();                                          // the weights were written through the generic proxy
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
+
+    if (warp < kTeamWarps) {
+        // =============================== team X: epilogue 1 ===========================================
+        const int xh = warp >> 2;                                 // which 32 of a slice's 64 units
+        int it = 0;
+        for (int64_t blk = blockIdx.x; blk < n_blocks; blk += stride, ++it) {
+            const uint32_t ppar = (uint32_t)(it & 1) ^ 1u;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t cur[32];
+                mbar_wait(l1bar + 8 * (c & 1), (uint32_t)(c >> 1));   // two completions per slot and block: parity = c / 2
+                fence_after_sync();
+                tmem_ld32_issue(t_lane + (uint32_t)(64 * (c & 1) + 32 * xh), cur);
+                tmem_ld_wait(cur);
+                // A2s slice c is free when the previous block's MMAs of both halves have read it
+                if (it > 0 && c == 0) mbar_wait(e0, ppar);
+                if (it > 0 && c == 1) mbar_wait(barA, ppar);
+                if (it > 0 && c == 3) mbar_wait(barB, ppar);
+                const int col0 = 64 * c + 32 * xh;
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {                  // 8 units = one 16-byte chunk of the K-major operand
+                    uint32_t w[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        w[j] = tanh_bf16x2(pack_bf16(__uint_as_float(cur[8 * k4 + 2 * j]), __uint_as_float(cur[8 * k4 + 2 * j + 1])));
+                    const int kc = (col0 >> 3) + k4;
+                    *reinterpret_cast<uint4*>(smem + kSmA2 + kc * kLboA + (row >> 3) * kSbo + (row & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                fence_async_proxy();                              // A2s writes -> visible to the tensor core
+                fence_before_sync();                              // this thread's reads of ring slot c & 1 are complete
+                __syncwarp();
+                if (lane == 0) mbar_arrive(x_ready + 8 * c);
+            }
+        }
+    } else if (warp < 2 * kTeamWarps) {
+        // =============================== team Y: epilogue 2 and the head ==============================
+        const float* w3s = reinterpret_cast<const float*>(smem + kSmW3p);
+        const float* b3s = reinterpret_cast<const float*>(smem + kSmB3p);
+        float* red = reinterpret_cast<float*>(smem + kSmRedp);
+        int it = 0;
+        for (int64_t blk = blockIdx.x; blk < n_blocks; blk += stride, ++it) {
+            const uint32_t par = (uint32_t)(it & 1);
+            float s[kOut];
+#pragma unroll
+            for (int o = 0; o < kOut; ++o) s[o] = 0.f;
+#pragma unroll
+            for (int nh = 0; nh < 2; ++nh) {
+                // (the wait for this half was done before the arrival that released the previous one, see below)
+                if (it == 0 && nh == 0) mbar_wait(barA, 0u);
+                fence_after_sync();
+                const uint32_t col = 128u + 128u * (uint32_t)((2 * it + nh) % 3) + (uint32_t)(64 * yh);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t cur[32];
+                    tmem_ld32_issue(t_lane + col + 32u * (uint32_t)c, cur);
+                    tmem_ld_wait(cur);
+                    const int unit0 = 128 * nh + 64 * yh + 32 * c;
+#pragma unroll
+                    for (int k = 0; k < 32; k += 4) {
+                        const float h0 = tanh_fast(__uint_as_float(cur[k])), h1 = tanh_fast(__uint_as_float(cur[k + 1]));
+                        const float h2 = tanh_fast(__uint_as_float(cur[k + 2])), h3 = tanh_fast(__uint_as_float(cur[k + 3]));
+#pragma unroll
+                        for (int o = 0; o < kOut; ++o) {
+                            const float4 w = *reinterpret_cast<const float4*>(w3s + o * kHidden + unit0 + k);
+                            s[o] = fmaf(h0, w.x, fmaf(h1, w.y, fmaf(h2, w.z, fmaf(h3, w.w, s[o]))));
+                        }
+                    }
+                }
+                fence_before_sync();                              // this thread's reads of the accumulator are complete
+                // Wait for the NEXT half before releasing this one: the commit that completes the next
+                // half's barrier a second time is issued only after this release, so a parity wait can
+                // never see its barrier two phases ahead.
+                if (nh == 0) {
+                    mbar_wait(barB, par);
+                    // Team X has finished this block (barA), so layer 1 has read its A1 buffer: the observations of
+                    // the block two ahead go there, announced by the arrival below (warp 16 waits for it before it
+                    // issues that block's layer 1).
+                    stage_obs(it & 1);
+                    load_obs(blk + 3 * stride);
+                } else if (blk + stride < n_blocks) {
+                    mbar_wait(barA, par ^ 1u);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(nh ? y_doneB : y_doneA);
+            }
+            float* rbuf = red + (it & 1) * (kM * 2);               // the warp with units 0..63 of each half hands its sums to its partner
+            if (yh == 0) {
+#pragma unroll
+                for (int o = 0; o < kOut; ++o) rbuf[row * 2 + o] = s[o];
+            }
+            pair_barrier(q);
+            if (yh == 1) {
+                const int64_t r = blk * kM + row;
+                if (r < n) {
+                    float v[kOut];
+#pragma unroll
+                    for (int o = 0; o < kOut; ++o) v[o] = b3s[o] + rbuf[row * 2 + o] + s[o];
+                    if (kOut == 2 && sa.actions != nullptr) {
+                        // counter (global row, draw); the KEY is the seed xor a domain tag, so that this stream is
+                        // independent of the environment's reset stream (key = seed, counter = (global id, epoch))
+                        // even when both are given the same seed
+                        const uint64_t gr = (uint64_t)r + sa.row_offset;
+                        const uint4 bits = rl::philox4x32_10(make_uint4((uint32_t)gr, (uint32_t)(gr >> 32), (uint32_t)sa.draw,
+                                                                        (uint32_t)(sa.draw >> 32)),
+                                                             make_uint2((uint32_t)sa.seed ^ 0x706F6C69u, (uint32_t)(sa.seed >> 32) ^ 0x63792E61u));
+                        const float u1 = (float)((bits.x >> 8) + 1u) * 5.9604644775390625e-8f;      // (0, 1]
+                        const float u2 = (float)(bits.y >> 8) * 5.9604644775390625e-8f;             // [0, 1)
+                        const float rad = sqrtf(-2.0f * logf(u1));
+                        float sn, cs;
+                        sincospif(2.0f * u2, &sn, &cs);
+                        const float z0 = rad * cs, z1 = rad * sn;
+                        const float ls0 = sa.log_std[0], ls1 = sa.log_std[1];
+                        const float a0 = fmaf(expf(ls0), z0, v[0]), a1 = fmaf(expf(ls1), z1, v[kOut - 1]);
+                        *reinterpret_cast<float2*>(sa.actions + 2 * r) = make_float2(a0, a1);
+                        *reinterpret_cast<float2*>(sa.clipped + 2 * r) =
+                            make_float2(fminf(fmaxf(a0, sa.lo0), sa.hi0), fminf(fmaxf(a1, sa.lo1), sa.hi1));
+                        sa.log_prob[r] = (-0.5f * z0 * z0 - ls0 - 0.91893853320467274f) + (-0.5f * z1 * z1 - ls1 - 0.91893853320467274f);
+                        if (sa.mean) *reinterpret_cast<float2*>(sa.mean + 2 * r) = make_float2(v[0], v[kOut - 1]);
+                    } else {
+#pragma unroll
+                        for (int o = 0; o < kOut; ++o) out[r * kOut + o] = v[o];
+                    }
+                }
+            }
+            // (rbuf is rewritten two blocks later: both warps of the pair pass another pair_barrier in between)
+        }
+    } else {
+        // =============================== warp 16: every MMA =============================================
+        // The period of the whole pipeline cannot be shorter than this warp's own instruction stream
+        // (42 MMAs, 10 commits, 10 waits per block), so it does nothing else and keeps its descriptors as
+        // 32-bit low words that only need an add.
+        const uint32_t a2_lo = desc_lo(sbase + kSmA2, kLboA), w2_lo = desc_lo(sbase + kSmW2, kLboW);
+        const uint32_t a1_lo0 = desc_lo(sbase + kSmA1, kLboA), a1_lo1 = desc_lo(sbase + kSmA1b, kLboA);
+        const uint32_t ones_lo = desc_lo(sbase + kSmOnes, kLboA), w1_lo = desc_lo(sbase + kSmW1, kLboW);
+        const uint32_t bb1_lo = desc_lo(sbase + kSmBb1, kLboW), bb2_lo = desc_lo(sbase + kSmBb2, kLboW);
+        // lane 0: layer 1 (bias, then A1 W1^T), units [64 u, 64 u + 64) -> ring slot u & 1
+        auto issue_layer1 = [&](uint32_t a1_lo, int u) {
+            const uint32_t d = tmem + 64u * (uint32_t)(u & 1), off = (uint32_t)(u * (64 / 8) * kSbo) >> 4;
+            mma_lo(d, ones_lo, bb1_lo + off, idesc_n(64), 0u);
+            mma_lo(d, a1_lo, w1_lo + off, idesc_n(64), 1u);
+            mma_commit(l1bar + 8 * (u & 1));
+        };
+        // lane 0: layer 2, K slice c (64 units) of N half nh -> accumulator column `acc` (slice 0 starts from b2)
+        auto issue_layer2 = [&](uint32_t acc, int nh, int c) {
+            const uint32_t n_off = (uint32_t)(nh * (128 / 8) * kSbo) >> 4;
+            if (c == 0) mma_lo(tmem + acc, ones_lo, bb2_lo + n_off, idesc_n(128), 0u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ks = 4 * c + j;
+                mma_lo(tmem + acc, a2_lo + ((uint32_t)(ks * 2 * kLboA) >> 4), w2_lo + ((uint32_t)(ks * 2 * kLboW) >> 4) + n_off, idesc_n(128), 1u);
+            }
+        };
+        if (lane == 0) {
+            fence_after_sync();
+            issue_layer1(a1_lo0, 0);
+            issue_layer1(a1_lo0, 1);
+        }
+        int it = 0;
+        for (int64_t blk = blockIdx.x; blk < n_blocks; blk += stride, ++it) {
+            const bool has_next = blk + stride < n_blocks;
+            const uint32_t par = (uint32_t)(it & 1), ppar = par ^ 1u;
+            const uint32_t accA = 128u + 128u * (uint32_t)((2 * it) % 3), accB = 128u + 128u * (uint32_t)((2 * it + 1) % 3);
+            const uint32_t a1_cur = (it & 1) ? a1_lo1 : a1_lo0, a1_nxt = (it & 1) ? a1_lo0 : a1_lo1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                mbar_wait(x_ready + 8 * c, par);                  // team X: A2s slice c written, ring slot c & 1 drained
+                // team Y: half A of the previous block drained -> accB is free; observations of the next block staged
+                if (c == 2 && it > 0) mbar_wait(y_doneA, ppar);
+                if (lane == 0) {
+                    fence_after_sync();
+                    if (c < 2) issue_layer1(a1_cur, c + 2);       // team X waits for this one first
+                    else if (has_next) issue_layer1(a1_nxt, c - 2);
+                    issue_layer2(accA, 0, c);                     // (accA was released by y_doneB two blocks ago: waited for below)
+                    if (c == 3) mma_commit(barA);
+                    if (c == 2) {
+                        issue_layer2(accB, 1, 0);
+                        mma_commit(e0);
+                        issue_layer2(accB, 1, 1);
+                        issue_layer2(accB, 1, 2);
+                    }
+                    if (c == 3) {
+                        issue_layer2(accB, 1, 3);
+                        mma_commit(barB);
+                    }
+                }
+                __syncwarp();
+            }
+            if (it > 0) mbar_wait(y_doneB, ppar);                  // half B of the previous block drained -> free for half A of the next
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
+}
+constexpr int kLaunchThreads = kThreadsP;
+constexpr int kLaunchSmem = kSmemBytesP;
+
+#else   // RL_MLP_PIPE == 0: the round-1 kernel
 #ifndef RL_MLP_TC5_SPLIT
 #define RL_MLP_TC5_SPLIT 4                  // warps per TMEM lane quarter = column slices per row
 #endif
@@ -312,11 +671,8 @@ __global__ void __launch_bounds__(kTc5Threads, 1) mlp_forward_tc5_kernel(const u
                 for (int k4 = 0; k4 < 4; ++k4) {                  // 8 units = one 16-byte chunk of the K-major operand
                     uint32_t w[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 bias = *reinterpret_cast<const float2*>(b1s + col0 + 8 * k4 + 2 * j);
-                        w[j] = tanh_bf16x2(pack_bf16(__uint_as_float(cur[8 * k4 + 2 * j]) + bias.x,
-                                                     __uint_as_float(cur[8 * k4 + 2 * j + 1]) + bias.y));
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        w[j] = tanh_bf16x2(pack_bf16(__uint_as_float(cur[8 * k4 + 2 * j]), __uint_as_float(cur[8 * k4 + 2 * j + 1])));
                     const int kc = (col0 >> 3) + k4;
                     *reinterpret_cast<uint4*>(smem + kSmA2 + kc * kLboA + (row >> 3) * kSbo + (row & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
@@ -415,6 +771,10 @@ __global__ void __launch_bounds__(kTc5Threads, 1) mlp_forward_tc5_kernel(const u
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
+constexpr int kLaunchThreads = kTc5Threads;
+constexpr int kLaunchSmem = kSmemBytes;
+#endif  // RL_MLP_PIPE
+
 }  // namespace tc5
 
 }  // namespace
@@ -434,13 +794,13 @@ int launch_mlp(const void* blob, const float* obs, float* out, int64_t n, int ou
     const int grid = (int)(blocks < sms ? blocks : sms);          // persistent: the weights are staged once per CTA
     cudaError_t e;
     if (out_dim == 2) {
-        e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
+        e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kLaunchSmem);
         if (e == cudaSuccess)
-            tc5::mlp_forward_tc5_kernel<2><<<grid, tc5::kTc5Threads, tc5::kSmemBytes, stream>>>((const unsigned char*)blob, obs, out, n, sa);
+            tc5::mlp_forward_tc5_kernel<2><<<grid, tc5::kLaunchThreads, tc5::kLaunchSmem, stream>>>((const unsigned char*)blob, obs, out, n, sa);
     } else {
-        e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
+        e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kLaunchSmem);
         if (e == cudaSuccess)
-            tc5::mlp_forward_tc5_kernel<1><<<grid, tc5::kTc5Threads, tc5::kSmemBytes, stream>>>((const unsigned char*)blob, obs, out, n, sa);
+            tc5::mlp_forward_tc5_kernel<1><<<grid, tc5::kLaunchThreads, tc5::kLaunchSmem, stream>>>((const unsigned char*)blob, obs, out, n, sa);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return po_fail(RL_E_CUDA, "rl_mlp_forward launch failed: %s", cudaGetErrorString(e));
