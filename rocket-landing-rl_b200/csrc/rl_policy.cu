@@ -7,39 +7,52 @@
 // collection loop spends 3.3 of its 3.6 ms per step there.  Here one launch evaluates one whole net
 // and nothing but the observation (32 B) and the head output (4-8 B) of a rocket touches HBM.
 //
-// tcgen05 / TMEM: one CTA steps 128-rocket row blocks; both layers are single-thread-issued
-// tcgen05.mma (M = 128, N = 256, K = 16 per instruction, bf16 x bf16 -> fp32 in tensor memory).
+// tcgen05 / TMEM: one persistent CTA per SM steps 128-rocket row blocks; both layers are
+// single-thread-issued tcgen05.mma (M = 128, K = 16 per instruction, bf16 x bf16 -> fp32 in tensor
+// memory).  What bounds the kernel once the GEMMs are on tcgen05 is the MUFU pipe: 2 x 256 tanh per
+// rocket = 4096 MUFU cycles per row block and scheduler, twice what the tensor core needs.  The
+// kernel is therefore built around keeping the MUFU pipe fed (see "schedule" below).
 //
 //   shared memory (operands in the canonical K-major no-swizzle layout: 8 x 16-byte "core matrices",
 //   element (row r, k) at (k / 8) LBO + (r / 8) 128 + (r % 8) 16 + (k % 8) 2 bytes):
 //     W2s  256 x 256 bf16, LBO 4096   (loaded once per CTA)        W1s  256 x 16, LBO 4096
-//     A2s  128 x 256 bf16, LBO 2048   (layer-1 activations)        A1s  128 x 16, LBO 2048 (obs hi | lo)
-//   tensor memory (512 columns): D1 = columns 0..255 (layer 1), D2 = columns 256..511 (layer 2)
+//     A2s  128 x 256 bf16, LBO 2048   (layer-1 activations)        A1s  2 x (128 x 16), LBO 2048 (obs hi | lo)
+//     Bb1, Bb2, Ones                   bias tiles: b1 and b2 come out of the tensor core too
+//   tensor memory (512 columns): [0, 128) layer-1 ring (2 slots of 64), [128, 512) three layer-2
+//   accumulators of 128 columns used in rotation
 //
 //   layer 1 (8 -> 256)   K = 16 = [bf16 high part | bf16 low part] of the fp32 observation against W1
-//                        stacked twice: the input keeps ~16 mantissa bits
-//   epilogue 1           all 16 warps: D1 -> +b1, tanh, bf16 -> A2s, 32 units at a time; as soon as the
-//                        whole CTA has written a slice of K the layer-2 MMAs that consume it are issued
-//   layer 2 (256 -> 256) 16 x tcgen05.mma into D2; when the last one is issued, layer 1 of the NEXT row
-//                        block follows it (its observations were loaded one block ahead)
-//   epilogue 2           D2 -> +b2, tanh, head dot product -> out (or: sample the action, see below)
+//                        stacked twice: the input keeps ~16 mantissa bits; four N = 64 slices
+//   epilogue 1  (team X) ring slot -> tanh -> bf16 -> A2s, one K slice of 64 units at a time
+//   layer 2 (256 -> 256) two N = 128 halves (A: units 0..127, B: 128..255), each 16 x tcgen05.mma
+//                        issued slice by slice behind team X
+//   epilogue 2  (team Y) accumulator -> tanh -> head dot product -> out (or: sample the action, see below)
 //
-//   Warp w reads TMEM lanes 32 (w % 4) .. + 31 (its rows) and column slice w / 4, so the 2 x 256 tanh
-//   per rocket -- the MUFU pipe is what bounds this kernel once the GEMM is on tcgen05 -- are spread
-//   over 512 threads.  Generic-proxy writes of A1s / A2s are published to the tensor core with
-//   fence.proxy.async + a CTA barrier; MMA completion comes back through tcgen05.commit -> mbarrier.
+// Schedule.  The first tcgen05 version moved all 16 warps in lockstep through epilogue 1 -> layer 2
+// -> epilogue 2 of a row block: whenever they met at a CTA barrier, waited for a TMEM load or for
+// the last MMAs to drain, the MUFU pipe had nothing to do (58 % busy, 0.22 ms per net at 1 Mi
+// rockets).  Now the two epilogues belong to two teams of 8 warps that run about one row block apart
+// and only ever meet through mbarriers, so that every scheduler holds warps of both kinds, and a
+// 17th warp does nothing but issue the MMAs:
+//   * tensor memory cannot hold two whole layer-2 accumulators next to layer 1, so half A of block i
+//     goes to accumulator 2 i mod 3 (drained by team Y one block ago) and half B to 2 i + 1 mod 3
+//     (which held half A of block i - 1: free about mid-way through epilogue 1 of block i) -- no MMA
+//     waits for the END of an epilogue;
+//   * layer 1 of the slice two ahead is issued into a ring slot as soon as team X has drained it;
+//   * team X may start the next block at once: A2s slice 0 has been read by then (barrier e0),
+//     slices 1..2 / 3 are released by the commits of half A / B;
+//   * both bias adds are MMAs against a tile of ones (no LDS + FADD in either epilogue);
+//   * the period of the pipeline cannot be shorter than the issuing warp's own instruction stream
+//     (42 MMAs, 10 commits, 10 waits per block), so the observations are staged by team Y and the
+//     descriptors are 32-bit words that only need an add.
+// Measured (profiles/mlp_forward_r2b_summary.txt): 0.163 ms (value net) / 0.178 ms (policy net) at
+// 1 Mi rockets, MUFU pipe 80 % busy, tensor pipe 47 %.
 //
-// Weights are bf16 (what torch.autocast(bfloat16) would use), accumulation and biases fp32; measured
-// against the fp32 module: rms error 8e-4, max 4e-3 on outputs of mean magnitude 0.24 (autocast:
-// 1.2e-3 / 7e-3; tools/mlp_error_probe.py), and the test states the tolerance.
-// Measured (profiles/README.md): 0.22 ms per net at 1 Mi rockets: the MUFU (tanh) pipe is 57 % busy,
-// the tensor pipe 30 %; the two epilogues and the MMAs of ONE row block still run mostly one after
-// the other.  Overlapping epilogue 1 of block i + 1 with layer 2 of block i needs a second A2s
-// buffer (64 KiB more than one SM's shared memory holds beside W2): a cta_group::2 pair with W2
-// split over the two SMs would make room -- the next step for this kernel.  The first version of this kernel
-// used warp-level mma.sync with the activations chained through registers (layer-1 accumulator
-// fragments = layer-2 A fragments): 0.37 ms, 70 % of the legacy tensor path's peak -- a quarter of
-// tcgen05's; it is in the history of this file.
+// Weights are bf16 (what torch.autocast(bfloat16) would use), accumulation fp32, biases bf16 high +
+// low parts (16 mantissa bits); measured against the fp32 module: rms error 8e-4, max 4e-3 on
+// outputs of mean magnitude 0.24 (autocast: 1.2e-3 / 7e-3; tools/mlp_error_probe.py), and the test
+// states the tolerance.  Earlier versions are in the history of this file: warp-level mma.sync with
+// the activations chained through registers (0.37 ms), lockstep tcgen05 (0.22 ms).
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -111,33 +124,52 @@ namespace tc5 {
 
 constexpr int kM = 128;                       // rows per block = TMEM lanes
 constexpr int kLboW = 4096, kLboA = 2048, kSbo = 128;
+#ifndef RL_MLP_Y_WARPS
+#define RL_MLP_Y_WARPS 8
+#endif
+constexpr int kXWarps = 8, kYWarps = RL_MLP_Y_WARPS;      // team sizes: multiples of 4 (a warp reads TMEM lanes 32 (w % 4) .. + 31)
+constexpr int kYSlices = kYWarps / 4;                     // team Y warps per lane quarter = column slices of an N half
+constexpr int kYUnits = 128 / kYSlices;                   // units of an N half per team-Y thread
+static_assert(kYUnits % 32 == 0, "team Y reads 32 columns at a time");
+constexpr int kThreads = 32 * (kXWarps + kYWarps + 1);
+
 constexpr int kSmW2 = 0;                                  // 131072
 constexpr int kSmW1 = kSmW2 + kHidden * kHidden * 2;      // 8192
 constexpr int kSmA2 = kSmW1 + kHidden * 16 * 2;           // 65536
-constexpr int kSmA1 = kSmA2 + kM * kHidden * 2;           // 4096
-constexpr int kSmB1 = kSmA1 + kM * 16 * 2;
-constexpr int kSmB2 = kSmB1 + kHidden * 4;
-constexpr int kSmW3 = kSmB2 + kHidden * 4;
+constexpr int kSmA1 = kSmA2 + kM * kHidden * 2;           // 4096: observations of even blocks
+constexpr int kSmA1b = kSmA1 + kM * 16 * 2;               // ... of odd blocks
+// Both biases come out of the tensor core as well: D = Ones (128 x 16: columns 0, 1 = 1) Bb^T + ..., with
+// Bb (256 x 16) = [high part of b | remainder | 0 ...].  Only the first 8 k's of a bias tile are stored: its
+// second K chunk (LBO = 4096 further on) meets the zero columns of Ones, so it may alias anything FINITE --
+// the next bias tile, and for the last one the first chunk of Ones.
+constexpr int kSmBb1 = kSmA1b + kM * 16 * 2;              // 256 x 8 bf16
+constexpr int kSmBb2 = kSmBb1 + kHidden * 8 * 2;
+constexpr int kSmOnes = kSmBb2 + kHidden * 8 * 2;         // 128 x 16 bf16, LBO 2048
+static_assert(kSmBb2 - kSmBb1 == kLboW && kSmOnes - kSmBb2 == kLboW, "aliased second K chunks");
+constexpr int kSmW3 = kSmOnes + kM * 16 * 2;
 constexpr int kSmB3 = kSmW3 + 2 * kHidden * 4;
-constexpr int kSmRed = kSmB3 + 16;                        // [column slices][128 rows][2] f32
-constexpr int kSmBar = kSmRed + 4 * kM * 2 * 4;           // 2 mbarriers + TMEM base address
-constexpr int kSmemBytes = kSmBar + 32;
+constexpr int kRedBufs = kYSlices > 2 ? 1 : 2;            // one buffer (and a second barrier after it has been read) when two do not fit
+constexpr int kSmRed = kSmB3 + 16;                        // kRedBufs x [kYSlices - 1][128 rows][2] f32: partial sums handed to the last slice's warp
+constexpr int kSmBar = kSmRed + kRedBufs * (kYSlices - 1) * kM * 2 * 4;
+constexpr int kNumBars = 11;                              // x_ready[4] | l1bar[2] | barA | e0 | barB | y_doneA | y_doneB
+constexpr int kSmemBytes = kSmBar + 8 * kNumBars + 8 + 16; // ... + the TMEM base address
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
-// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A / B bf16, both K-major, N = 256, M = 128
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kHidden >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
-
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), no swizzle, version 1 (Blackwell)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-           (1ull << 46);
+// instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A / B bf16, both K-major, M = 128, N = n_cols
+__host__ __device__ constexpr uint32_t idesc_n(int n_cols) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
 }
 
-__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), no swizzle, version 1 (Blackwell): the low word
+// holds (address >> 4) | (LBO >> 4) << 16, the high word SBO >> 4 and the version.  The issuing warp keeps one
+// low word per operand array and adds (byte offset >> 4) per instruction.
+constexpr uint32_t kDescHi = (uint32_t)(kSbo >> 4) | (1u << 14);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
+__device__ __forceinline__ void mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        "{\n\t.reg .b64 a, b;\n\t.reg .pred p;\n\tmov.b64 a, {%1, %3};\n\tmov.b64 b, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %4, p;\n\t}\n"
+        :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
@@ -179,126 +211,67 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                    "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                  :: "memory");
 }
-// tanh of two bf16 values in one MUFU operation
+// tanh of two bf16 values (two MUFU operations: there is no packed form in hardware)
 __device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
     uint32_t y;
     asm("tanh.approx.bf16x2 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
 
-#ifndef RL_MLP_PIPE
-#define RL_MLP_PIPE 1                       // 1: warp-specialised kernel below; 0: the round-1 kernel (kept for A/B runs)
-#endif
-
-#if RL_MLP_PIPE
-// ---------------------------------------------------------------------------------------------------
-// Warp-specialised version.  What bounds this kernel is the MUFU pipe (512 tanh per rocket); the
-// tensor core needs half that time.  The round-1 kernel moved all 16 warps in lockstep through
-// epilogue 1 -> layer 2 -> epilogue 2 of a row block: whenever they met at a barrier, waited for a
-// TMEM load or for the last MMAs to drain, the MUFU pipe had nothing to do (58 % busy).  Here the
-// two epilogues belong to two teams of 8 warps that run one row block apart and only ever meet
-// through mbarriers, so that each scheduler always holds warps of both kinds:
-//   team X (warps 0..7)   epilogue 1: D1 -> tanh(. + b1) -> bf16 -> A2s, four K slices of 64 units
-//   team Y (warps 8..15)  epilogue 2: D2 -> tanh(. + b2) -> head, as two N halves (A: units 0..127, B: 128..255)
-//   warp 16               stages the observations (A1, two buffers) and issues every tcgen05.mma
-// Tensor memory (512 columns) cannot hold two whole layer-2 accumulators next to layer 1, so
-//   * layer 1 runs in four N = 64 slices through a two-slot ring, columns [0, 128): the slice two
-//     ahead is issued into a slot as soon as team X has drained it;
-//   * layer 2 runs as two N = 128 halves into THREE accumulators of 128 columns used in rotation
-//     (half A of block i -> accumulator 2 i mod 3, half B -> 2 i + 1 mod 3): half A follows team X
-//     slice by slice into the accumulator team Y drained one block ago; half B goes into the one
-//     that held half A of the previous block, from the moment team Y has drained that (about
-//     mid-way through epilogue 1), first catching up, then slice by slice.
-// No MMA waits for the END of an epilogue any more, and team X may start the next block at once:
-// A2s slice 0 has been read by then (barrier e0), slices 1..2 / 3 are released by the commits of
-// half A / B.
-constexpr int kSmA1b = kSmA1 + kM * 16 * 2;               // second observation buffer
-// Both biases come out of the tensor core as well: D = Ones (128 x 16: columns 0, 1 = 1) Bb^T + ..., with
-// Bb (256 x 16) = [high part of b | remainder | 0 ...].  Only the first 8 k's of a bias tile are stored: its
-// second K chunk (LBO = 4096 further on) meets the zero columns of Ones, so it may alias anything FINITE --
-// the next bias tile, and for the last one the first chunk of Ones.
-constexpr int kSmBb1 = kSmA1b + kM * 16 * 2;              // 256 x 8 bf16
-constexpr int kSmBb2 = kSmBb1 + kHidden * 8 * 2;
-constexpr int kSmOnes = kSmBb2 + kHidden * 8 * 2;         // 128 x 16 bf16, LBO 2048
-static_assert(kSmBb2 - kSmBb1 == kLboW && kSmOnes - kSmBb2 == kLboW, "aliased second K chunks");
-constexpr int kSmW3p = kSmOnes + kM * 16 * 2;
-constexpr int kSmB3p = kSmW3p + 2 * kHidden * 4;
-constexpr int kSmRedp = kSmB3p + 16;                      // 2 x [128 rows][2] f32: partial sums of one warp of a pair
-constexpr int kSmBarp = kSmRedp + 2 * kM * 2 * 4;
-constexpr int kNumBars = 11;                              // x_ready[4] | l1bar[2] | barA | e0 | barB | y_doneA | y_doneB
-constexpr int kSmemBytesP = kSmBarp + 8 * kNumBars + 8 + 16;
-static_assert(kSmemBytesP <= 227 * 1024, "shared memory budget");
-constexpr int kTeamWarps = 8;
-constexpr int kThreadsP = 32 * (2 * kTeamWarps + 1);      // 544
-
-__host__ __device__ constexpr uint32_t idesc_n(int n_cols) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_cols >> 3) << 17) | ((uint32_t)(kM >> 4) << 24);
-}
-
-// The low word of a shared-memory descriptor holds (address >> 4) | (LBO >> 4) << 16, the high word SBO >> 4 and
-// the version: the issuing warp keeps one low word per operand array and adds (byte offset >> 4) per instruction.
-constexpr uint32_t kDescHi = (uint32_t)(kSbo >> 4) | (1u << 14);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16); }
-__device__ __forceinline__ void mma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .b64 a, b;\n\t.reg .pred p;\n\tmov.b64 a, {%1, %3};\n\tmov.b64 b, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], a, b, %4, p;\n\t}\n"
-        :: "r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(kDescHi), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
-__device__ __forceinline__ void pair_barrier(int q) {             // the two team-Y warps that share TMEM lanes 32 q .. 32 q + 31
-    asm volatile("bar.sync %0, 64;" :: "r"(q + 1) : "memory");
+__device__ __forceinline__ void quarter_barrier(int q) {          // the team-Y warps that share TMEM lanes 32 q .. 32 q + 31
+    asm volatile("bar.sync %0, %1;" :: "r"(q + 1), "n"(32 * kYSlices) : "memory");
 }
 
 template <int kOut>
-__global__ void __launch_bounds__(kThreadsP, 1) mlp_forward_tc5_kernel(const unsigned char* __restrict__ blob,
+__global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsigned char* __restrict__ blob,
                                                                 const float* __restrict__ obs, float* __restrict__ out,
                                                                 int64_t n, const SampleArgs sa) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bars = sbase + kSmBarp;
+    const uint32_t bars = sbase + kSmBar;
     const uint32_t x_ready = bars, l1bar = bars + 32, barA = bars + 48, e0 = bars + 56, barB = bars + 64, y_doneA = bars + 72,
                    y_doneB = bars + 80;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBarp + 8 * kNumBars + 8);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 8 * kNumBars + 8);
 
     // ---- one-time setup: weights in the canonical layout, barriers, tensor memory ------------------
-    for (int c = tid; c < kHidden * 32; c += kThreadsP) {                 // W2: chunk (row n, 8 k's kc); consecutive threads -> consecutive rows
+    for (int c = tid; c < kHidden * 32; c += kThreads) {                 // W2: chunk (row n, 8 k's kc); consecutive threads -> consecutive rows
         const int n_row = c & 255, kc = c >> 8;
         *reinterpret_cast<uint4*>(smem + kSmW2 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
             *reinterpret_cast<const uint4*>(blob + kOffW2 + n_row * (kHidden * 2) + kc * 16);
     }
-    for (int c = tid; c < kHidden * 2; c += kThreadsP) {                  // W1 stacked twice: 2 chunks per row
+    for (int c = tid; c < kHidden * 2; c += kThreads) {                  // W1 stacked twice: 2 chunks per row
         const int n_row = c & 255, kc = c >> 8;
         *reinterpret_cast<uint4*>(smem + kSmW1 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
             *reinterpret_cast<const uint4*>(blob + kOffW1 + n_row * 32 + kc * 16);
     }
-    for (int c = tid; c < kM * 2; c += kThreadsP) {
+    for (int c = tid; c < kM * 2; c += kThreads) {
         const int r = c & 127, kc = c >> 7;
         *reinterpret_cast<uint4*>(smem + kSmOnes + kc * kLboA + (r >> 3) * kSbo + (r & 7) * 16) =
             make_uint4(kc == 0 ? 0x3F803F80u : 0u, 0u, 0u, 0u);
     }
-    for (int c = tid; c < kHidden * 2; c += kThreadsP) {                  // b1 | b2
+    for (int c = tid; c < kHidden * 2; c += kThreads) {                  // b1 | b2
         const int n_row = c & 255, layer = c >> 8;
         float hi, lo;
         split_bf16(*reinterpret_cast<const float*>(blob + (layer ? kOffB2 : kOffB1) + n_row * 4), hi, lo);
         *reinterpret_cast<uint4*>(smem + (layer ? kSmBb2 : kSmBb1) + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
             make_uint4(pack_bf16(hi, lo), 0u, 0u, 0u);
     }
-    for (int c = tid; c < (kSmRedp - kSmW3p) / 16; c += kThreadsP)        // W3 | b3
-        *reinterpret_cast<uint4*>(smem + kSmW3p + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffW3 + c * 16);
+    for (int c = tid; c < (kSmRed - kSmW3) / 16; c += kThreads)        // W3 | b3
+        *reinterpret_cast<uint4*>(smem + kSmW3 + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffW3 + c * 16);
     if (tid == 0) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) mbar_init(x_ready + 8 * c, kTeamWarps);
+        for (int c = 0; c < 4; ++c) mbar_init(x_ready + 8 * c, kXWarps);
         mbar_init(l1bar, 1);
         mbar_init(l1bar + 8, 1);
         mbar_init(barA, 1);
         mbar_init(e0, 1);
         mbar_init(barB, 1);
-        mbar_init(y_doneA, kTeamWarps);
-        mbar_init(y_doneB, kTeamWarps);
+        mbar_init(y_doneA, kYWarps);
+        mbar_init(y_doneB, kYWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {                                              // one warp allocates all 512 columns (1 CTA per SM)
@@ -309,11 +282,11 @@ __global__ void __launch_bounds__(kThreadsP, 1) mlp_forward_tc5_kernel(const uns
     const int64_t stride = gridDim.x;
     const int q = warp & 3;                                       // TMEM lane quarter of this warp
     const int row = 32 * q + lane;                                // this thread's row of the block = its TMEM lane
-    const int yh = (warp >> 2) & 1;                               // team Y: which 64 of a half's 128 units
+    const int yh = (warp - kXWarps) >> 2;                         // team Y: which kYUnits of a half's 128 units
 
     // Observations: the first four warps of team Y hold one row each, two blocks ahead, and stage it as
     // A1 = [bf16 high parts | bf16 low parts] (two buffers, block i -> buffer i & 1).
-    const bool stager = warp >= kTeamWarps && warp < kTeamWarps + 4;
+    const bool stager = warp >= kXWarps && warp < kXWarps + 4;
     float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
     auto load_obs = [&](int64_t blk) {
         oa = ob = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -348,7 +321,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) mlp_forward_tc5_kernel(const uns
     const uint32_t tmem = *tmem_slot;
     const uint32_t t_lane = tmem + ((uint32_t)(32 * q) << 16);
 
-    if (warp < kTeamWarps) {
+    if (warp < kXWarps) {
         // =============================== team X: epilogue 1 ===========================================
         const int xh = warp >> 2;                                 // which 32 of a slice's 64 units
         int it = 0;
@@ -381,11 +354,11 @@ __global__ void __launch_bounds__(kThreadsP, 1) mlp_forward_tc5_kernel(const uns
                 if (lane == 0) mbar_arrive(x_ready + 8 * c);
             }
         }
-    } else if (warp < 2 * kTeamWarps) {
+    } else if (warp < kXWarps + kYWarps) {
         // =============================== team Y: epilogue 2 and the head ==============================
-        const float* w3s = reinterpret_cast<const float*>(smem + kSmW3p);
-        const float* b3s = reinterpret_cast<const float*>(smem + kSmB3p);
-        float* red = reinterpret_cast<float*>(smem + kSmRedp);
+        const float* w3s = reinterpret_cast<const float*>(smem + kSmW3);
+        const float* b3s = reinterpret_cast<const float*>(smem + kSmB3);
+        float* red = reinterpret_cast<float*>(smem + kSmRed);
         int it = 0;
         for (int64_t blk = blockIdx.x; blk < n_blocks; blk += stride, ++it) {
             const uint32_t par = (uint32_t)(it & 1);
@@ -397,13 +370,13 @@ __global__ void __launch_bounds__(kThreadsP, 1) mlp_forward_tc5_kernel(const uns
                 // (the wait for this half was done before the arrival that released the previous one, see below)
                 if (it == 0 && nh == 0) mbar_wait(barA, 0u);
                 fence_after_sync();
-                const uint32_t col = 128u + 128u * (uint32_t)((2 * it + nh) % 3) + (uint32_t)(64 * yh);
+                const uint32_t col = 128u + 128u * (uint32_t)((2 * it + nh) % 3) + (uint32_t)(kYUnits * yh);
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
+                for (int c = 0; c < kYUnits / 32; ++c) {
                     uint32_t cur[32];
                     tmem_ld32_issue(t_lane + col + 32u * (uint32_t)c, cur);
                     tmem_ld_wait(cur);
-                    const int unit0 = 128 * nh + 64 * yh + 32 * c;
+                    const int unit0 = 128 * nh + kYUnits * yh + 32 * c;
 #pragma unroll
                     for (int k = 0; k < 32; k += 4) {
                         const float h0 = tanh_fast(__uint_as_float(cur[k])), h1 = tanh_fast(__uint_as_float(cur[k + 1]));
@@ -432,18 +405,25 @@ __global__ void __launch_bounds__(kThreadsP, 1) mlp_forward_tc5_kernel(const uns
                 __syncwarp();
                 if (lane == 0) mbar_arrive(nh ? y_doneB : y_doneA);
             }
-            float* rbuf = red + (it & 1) * (kM * 2);               // the warp with units 0..63 of each half hands its sums to its partner
-            if (yh == 0) {
+            float* rbuf = red + (kRedBufs == 2 ? (it & 1) : 0) * ((kYSlices - 1) * kM * 2);   // the other slices' warps hand their sums to the last one
+            if (yh < kYSlices - 1) {
 #pragma unroll
-                for (int o = 0; o < kOut; ++o) rbuf[row * 2 + o] = s[o];
+                for (int o = 0; o < kOut; ++o) rbuf[(yh * kM + row) * 2 + o] = s[o];
             }
-            pair_barrier(q);
-            if (yh == 1) {
+            quarter_barrier(q);
+            float v[kOut];
+            if (yh == kYSlices - 1) {
+#pragma unroll
+                for (int o = 0; o < kOut; ++o) {
+                    v[o] = b3s[o] + s[o];
+#pragma unroll
+                    for (int sl = 0; sl < kYSlices - 1; ++sl) v[o] += rbuf[(sl * kM + row) * 2 + o];
+                }
+            }
+            if (kRedBufs == 1) quarter_barrier(q);                // the single buffer has been read: the next block may overwrite it
+            if (yh == kYSlices - 1) {
                 const int64_t r = blk * kM + row;
                 if (r < n) {
-                    float v[kOut];
-#pragma unroll
-                    for (int o = 0; o < kOut; ++o) v[o] = b3s[o] + rbuf[row * 2 + o] + s[o];
                     if (kOut == 2 && sa.actions != nullptr) {
                         // counter (global row, draw); the KEY is the seed xor a domain tag, so that this stream is
                         // independent of the environment's reset stream (key = seed, counter = (global id, epoch))
@@ -471,10 +451,10 @@ __global__ void __launch_bounds__(kThreadsP, 1) mlp_forward_tc5_kernel(const uns
                     }
                 }
             }
-            // (rbuf is rewritten two blocks later: both warps of the pair pass another pair_barrier in between)
+            // (rbuf is rewritten two blocks later: all warps of the quarter pass another quarter_barrier in between)
         }
     } else {
-        // =============================== warp 16: every MMA =============================================
+        // =============================== the last warp: every MMA =============================================
         // The period of the whole pipeline cannot be shorter than this warp's own instruction stream
         // (42 MMAs, 10 commits, 10 waits per block), so it does nothing else and keeps its descriptors as
         // 32-bit low words that only need an add.
@@ -541,239 +521,7 @@ __global__ void __launch_bounds__(kThreadsP, 1) mlp_forward_tc5_kernel(const uns
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
-constexpr int kLaunchThreads = kThreadsP;
-constexpr int kLaunchSmem = kSmemBytesP;
 
-#else   // RL_MLP_PIPE == 0: the round-1 kernel
-#ifndef RL_MLP_TC5_SPLIT
-#define RL_MLP_TC5_SPLIT 4                  // warps per TMEM lane quarter = column slices per row
-#endif
-constexpr int kSplit = RL_MLP_TC5_SPLIT;
-constexpr int kTc5Threads = 128 * kSplit;
-constexpr int kColsPerThread = kHidden / kSplit;
-constexpr int kChunks = kColsPerThread / 32;
-static_assert(kSmBar - kSmRed >= kSplit * kM * 2 * 4, "head partial sums");
-
-template <int kOut>
-__global__ void __launch_bounds__(kTc5Threads, 1) mlp_forward_tc5_kernel(const unsigned char* __restrict__ blob,
-                                                                  const float* __restrict__ obs, float* __restrict__ out,
-                                                                  int64_t n, const SampleArgs sa) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar1 = sbase + kSmBar, bar2 = sbase + kSmBar + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 16);
-
-    // ---- one-time setup: weights in the canonical layout, barriers, tensor memory ------------------
-    for (int c = tid; c < kHidden * 32; c += kTc5Threads) {               // W2: chunk (row n, 8 k's kc); consecutive threads -> consecutive rows
-        const int n_row = c & 255, kc = c >> 8;
-        *reinterpret_cast<uint4*>(smem + kSmW2 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
-            *reinterpret_cast<const uint4*>(blob + kOffW2 + n_row * (kHidden * 2) + kc * 16);
-    }
-    for (int c = tid; c < kHidden * 2; c += kTc5Threads) {                // W1 stacked twice: 2 chunks per row
-        const int n_row = c & 255, kc = c >> 8;
-        *reinterpret_cast<uint4*>(smem + kSmW1 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
-            *reinterpret_cast<const uint4*>(blob + kOffW1 + n_row * 32 + kc * 16);
-    }
-    for (int c = tid; c < kHidden * 4 / 16; c += kTc5Threads)
-        *reinterpret_cast<uint4*>(smem + kSmB1 + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffB1 + c * 16);
-    for (int c = tid; c < (kSmRed - kSmB2) / 16; c += kTc5Threads)        // b2 | W3 | b3
-        *reinterpret_cast<uint4*>(smem + kSmB2 + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffB2 + c * 16);
-    if (tid == 0) {
-        mbar_init(bar1, 1);
-        mbar_init(bar2, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == 0) {                                              // one warp allocates all 512 columns (1 CTA per SM)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" :: "r"(smem_u32(tmem_slot)) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    fence_async_proxy();                                          // the weights were written through the generic proxy
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    const uint32_t tmem = *tmem_slot;
-
-    const float* b1s = reinterpret_cast<const float*>(smem + kSmB1);
-    const float* b2s = reinterpret_cast<const float*>(smem + kSmB2);
-    const float* w3s = reinterpret_cast<const float*>(smem + kSmW3);
-    const float* b3s = reinterpret_cast<const float*>(smem + kSmB3);
-    float* red = reinterpret_cast<float*>(smem + kSmRed);
-
-    const int row = 32 * (warp & 3) + lane;                       // this thread's row of the block = its TMEM lane
-    const int half = warp >> 2;                                   // ... and its slice of the 256 columns
-    const uint32_t t_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-    uint32_t parity = 0;
-
-    const int64_t n_blocks = (n + kM - 1) / kM;
-    // Layer 1 of the NEXT row block is issued as soon as epilogue 1 of this one has drained D1, so its
-    // latency -- and that of the global load of its observations, held in registers one block ahead --
-    // never sits on the critical path.
-    float4 oa = make_float4(0.f, 0.f, 0.f, 0.f), ob = oa;
-    auto load_obs = [&](int64_t blk) {                            // threads 0..127: one observation row each
-        oa = ob = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int64_t r = blk * kM + tid;
-        if (tid < kM && blk < n_blocks && r < n) {
-            oa = *reinterpret_cast<const float4*>(obs + r * kObs);
-            ob = *reinterpret_cast<const float4*>(obs + r * kObs + 4);
-        }
-    };
-    auto stage_obs = [&]() {                                      // -> A1s: k 0..7 = bf16 high parts, k 8..15 = low parts
-        if (tid < kM) {
-            const float x[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
-            float hi[8], lo[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) split_bf16(x[k], hi[k], lo[k]);
-            unsigned char* dst = smem + kSmA1 + (tid >> 3) * kSbo + (tid & 7) * 16;
-            *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(hi[0], hi[1]), pack_bf16(hi[2], hi[3]), pack_bf16(hi[4], hi[5]), pack_bf16(hi[6], hi[7]));
-            *reinterpret_cast<uint4*>(dst + kLboA) = make_uint4(pack_bf16(lo[0], lo[1]), pack_bf16(lo[2], lo[3]), pack_bf16(lo[4], lo[5]), pack_bf16(lo[6], lo[7]));
-        }
-    };
-    auto issue_layer1 = [&]() {                                   // thread 0: D1 = A1 (128 x 16) W1^T (16 x 256)
-        mma_f16_ss(tmem, smem_desc(sbase + kSmA1, kLboA, kSbo), smem_desc(sbase + kSmW1, kLboW, kSbo), kIdesc, 0u);
-        mma_commit(bar1);
-    };
-    if ((int64_t)blockIdx.x < n_blocks) {                         // prologue: layer 1 of the first block
-        load_obs(blockIdx.x);
-        stage_obs();
-        load_obs((int64_t)blockIdx.x + gridDim.x);
-        fence_async_proxy();
-        fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            fence_after_sync();
-            issue_layer1();
-        }
-    }
-    for (int64_t blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const int64_t row0 = blk * kM;
-        const bool has_next = blk + gridDim.x < n_blocks;
-        mbar_wait(bar1, parity);                                  // layer 1 of this block is in D1; A1s is free again
-        fence_after_sync();
-        if (has_next) {
-            stage_obs();                                          // next block's observations (published by the barriers below)
-            load_obs(blk + 2 * (int64_t)gridDim.x);
-        }
-        // ---- epilogue 1: D1 -> tanh(. + b1) -> bf16 -> A2s (this thread: its row, 128 of the 256 units),
-        // ---- 32 units at a time; as soon as the whole CTA has written a slice of K, the layer-2 MMAs that
-        // ---- consume it are issued, so that the tensor core works while the MUFU-bound epilogue goes on
-        {
-            uint32_t ra[32], rb[32];
-            tmem_ld32_issue(t_lane + (uint32_t)(kColsPerThread * half), ra);
-#pragma unroll
-            for (int c = 0; c < kChunks; ++c) {
-                uint32_t (&cur)[32] = (c & 1) ? rb : ra;
-                uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
-                tmem_ld_wait(cur);
-                if (c + 1 < kChunks) tmem_ld32_issue(t_lane + (uint32_t)(kColsPerThread * half + 32 * (c + 1)), nxt);
-                const int col0 = kColsPerThread * half + 32 * c;
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {                  // 8 units = one 16-byte chunk of the K-major operand
-                    uint32_t w[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        w[j] = tanh_bf16x2(pack_bf16(__uint_as_float(cur[8 * k4 + 2 * j]), __uint_as_float(cur[8 * k4 + 2 * j + 1])));
-                    const int kc = (col0 >> 3) + k4;
-                    *reinterpret_cast<uint4*>(smem + kSmA2 + kc * kLboA + (row >> 3) * kSbo + (row & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                fence_async_proxy();
-                fence_before_sync();
-                __syncthreads();
-                if (tid == 0) {                                   // every column slice has written its K range [32 c, 32 c + 32)
-                    fence_after_sync();
-#pragma unroll
-                    for (int j = 0; j < 2 * kSplit; ++j) {
-                        const int ks = (kColsPerThread / 16) * (j >> 1) + 2 * c + (j & 1);
-                        mma_f16_ss(tmem + 256u, smem_desc(sbase + kSmA2 + ks * 2 * kLboA, kLboA, kSbo),
-                                   smem_desc(sbase + kSmW2 + ks * 2 * kLboW, kLboW, kSbo), kIdesc, (c | j) ? 1u : 0u);
-                    }
-                    if (c == kChunks - 1) {
-                        mma_commit(bar2);
-                        if (has_next) issue_layer1();             // every thread's reads of D1 are complete (barrier above)
-                    }
-                }
-            }
-        }
-        mbar_wait(bar2, parity);
-        fence_after_sync();
-        parity ^= 1u;
-        // ---- epilogue 2: D2 -> tanh(. + b2) -> head dot over this thread's 128 units ---------------------
-        float s[kOut];
-#pragma unroll
-        for (int o = 0; o < kOut; ++o) s[o] = 0.f;
-        {
-            uint32_t ra[32], rb[32];
-            tmem_ld32_issue(t_lane + 256u + (uint32_t)(kColsPerThread * half), ra);
-#pragma unroll
-            for (int c = 0; c < kChunks; ++c) {
-                uint32_t (&cur)[32] = (c & 1) ? rb : ra;
-                uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
-                tmem_ld_wait(cur);
-                if (c + 1 < kChunks) tmem_ld32_issue(t_lane + 256u + (uint32_t)(kColsPerThread * half + 32 * (c + 1)), nxt);
-                const int col0 = kColsPerThread * half + 32 * c;
-#pragma unroll
-                for (int k = 0; k < 32; k += 4) {
-                    const float4 bias = *reinterpret_cast<const float4*>(b2s + col0 + k);
-                    const float h0 = tanh_fast(__uint_as_float(cur[k]) + bias.x), h1 = tanh_fast(__uint_as_float(cur[k + 1]) + bias.y);
-                    const float h2 = tanh_fast(__uint_as_float(cur[k + 2]) + bias.z), h3 = tanh_fast(__uint_as_float(cur[k + 3]) + bias.w);
-#pragma unroll
-                    for (int o = 0; o < kOut; ++o) {
-                        const float4 w = *reinterpret_cast<const float4*>(w3s + o * kHidden + col0 + k);
-                        s[o] = fmaf(h0, w.x, fmaf(h1, w.y, fmaf(h2, w.z, fmaf(h3, w.w, s[o]))));
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int o = 0; o < kOut; ++o) red[(half * kM + row) * 2 + o] = s[o];
-        fence_before_sync();                                      // this thread's TMEM reads are done before the next block's MMAs
-        __syncthreads();
-        if (tid < kM) {
-            const int64_t r = row0 + tid;
-            if (r < n) {
-                float v[kOut];
-#pragma unroll
-                for (int o = 0; o < kOut; ++o) {
-                    v[o] = b3s[o];
-#pragma unroll
-                    for (int sl = 0; sl < kSplit; ++sl) v[o] += red[(sl * kM + tid) * 2 + o];
-                }
-                if (kOut == 2 && sa.actions != nullptr) {
-                    // counter (global row, draw); the KEY is the seed xor a domain tag, so that this stream is
-                    // independent of the environment's reset stream (key = seed, counter = (global id, epoch))
-                    // even when both are given the same seed
-                    const uint64_t gr = (uint64_t)r + sa.row_offset;
-                    const uint4 bits = rl::philox4x32_10(make_uint4((uint32_t)gr, (uint32_t)(gr >> 32), (uint32_t)sa.draw,
-                                                                    (uint32_t)(sa.draw >> 32)),
-                                                         make_uint2((uint32_t)sa.seed ^ 0x706F6C69u, (uint32_t)(sa.seed >> 32) ^ 0x63792E61u));
-                    const float u1 = (float)((bits.x >> 8) + 1u) * 5.9604644775390625e-8f;      // (0, 1]
-                    const float u2 = (float)(bits.y >> 8) * 5.9604644775390625e-8f;             // [0, 1)
-                    const float rad = sqrtf(-2.0f * logf(u1));
-                    float sn, cs;
-                    sincospif(2.0f * u2, &sn, &cs);
-                    const float z0 = rad * cs, z1 = rad * sn;
-                    const float ls0 = sa.log_std[0], ls1 = sa.log_std[1];
-                    const float a0 = fmaf(expf(ls0), z0, v[0]), a1 = fmaf(expf(ls1), z1, v[kOut - 1]);
-                    *reinterpret_cast<float2*>(sa.actions + 2 * r) = make_float2(a0, a1);
-                    *reinterpret_cast<float2*>(sa.clipped + 2 * r) =
-                        make_float2(fminf(fmaxf(a0, sa.lo0), sa.hi0), fminf(fmaxf(a1, sa.lo1), sa.hi1));
-                    sa.log_prob[r] = (-0.5f * z0 * z0 - ls0 - 0.91893853320467274f) + (-0.5f * z1 * z1 - ls1 - 0.91893853320467274f);
-                    if (sa.mean) *reinterpret_cast<float2*>(sa.mean + 2 * r) = make_float2(v[0], v[kOut - 1]);
-                } else {
-#pragma unroll
-                    for (int o = 0; o < kOut; ++o) out[r * kOut + o] = v[o];
-                }
-            }
-        }
-        // (red is rewritten only after two more CTA barriers; A1s only after MMA 1 of this block completed)
-    }
-    __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
-}
-
-constexpr int kLaunchThreads = kTc5Threads;
-constexpr int kLaunchSmem = kSmemBytes;
-#endif  // RL_MLP_PIPE
 
 }  // namespace tc5
 
@@ -794,13 +542,13 @@ int launch_mlp(const void* blob, const float* obs, float* out, int64_t n, int ou
     const int grid = (int)(blocks < sms ? blocks : sms);          // persistent: the weights are staged once per CTA
     cudaError_t e;
     if (out_dim == 2) {
-        e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kLaunchSmem);
+        e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
         if (e == cudaSuccess)
-            tc5::mlp_forward_tc5_kernel<2><<<grid, tc5::kLaunchThreads, tc5::kLaunchSmem, stream>>>((const unsigned char*)blob, obs, out, n, sa);
+            tc5::mlp_forward_tc5_kernel<2><<<grid, tc5::kThreads, tc5::kSmemBytes, stream>>>((const unsigned char*)blob, obs, out, n, sa);
     } else {
-        e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kLaunchSmem);
+        e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
         if (e == cudaSuccess)
-            tc5::mlp_forward_tc5_kernel<1><<<grid, tc5::kLaunchThreads, tc5::kLaunchSmem, stream>>>((const unsigned char*)blob, obs, out, n, sa);
+            tc5::mlp_forward_tc5_kernel<1><<<grid, tc5::kThreads, tc5::kSmemBytes, stream>>>((const unsigned char*)blob, obs, out, n, sa);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return po_fail(RL_E_CUDA, "rl_mlp_forward launch failed: %s", cudaGetErrorString(e));
