@@ -211,6 +211,12 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                    "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
                  :: "memory");
 }
+// acc.x += a0 b0, acc.y += a1 b1 in one instruction (FFMA2)
+__device__ __forceinline__ void ffma2(float2& acc, float a0, float a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}\n"
+        : "+f"(acc.x), "+f"(acc.y) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 // tanh of two bf16 values (two MUFU operations: there is no packed form in hardware)
 __device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
     uint32_t y;
@@ -362,9 +368,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
         int it = 0;
         for (int64_t blk = blockIdx.x; blk < n_blocks; blk += stride, ++it) {
             const uint32_t par = (uint32_t)(it & 1);
-            float s[kOut];
+            float2 s2[kOut];
 #pragma unroll
-            for (int o = 0; o < kOut; ++o) s[o] = 0.f;
+            for (int o = 0; o < kOut; ++o) s2[o] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int nh = 0; nh < 2; ++nh) {
                 // (the wait for this half was done before the arrival that released the previous one, see below)
@@ -382,9 +388,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
                         const float h0 = tanh_fast(__uint_as_float(cur[k])), h1 = tanh_fast(__uint_as_float(cur[k + 1]));
                         const float h2 = tanh_fast(__uint_as_float(cur[k + 2])), h3 = tanh_fast(__uint_as_float(cur[k + 3]));
 #pragma unroll
-                        for (int o = 0; o < kOut; ++o) {
+                        for (int o = 0; o < kOut; ++o) {                  // even / odd units accumulate in the two halves of a packed FMA
                             const float4 w = *reinterpret_cast<const float4*>(w3s + o * kHidden + unit0 + k);
-                            s[o] = fmaf(h0, w.x, fmaf(h1, w.y, fmaf(h2, w.z, fmaf(h3, w.w, s[o]))));
+                            ffma2(s2[o], h0, h1, w.x, w.y);
+                            ffma2(s2[o], h2, h3, w.z, w.w);
                         }
                     }
                 }
@@ -405,6 +412,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
                 __syncwarp();
                 if (lane == 0) mbar_arrive(nh ? y_doneB : y_doneA);
             }
+            float s[kOut];
+#pragma unroll
+            for (int o = 0; o < kOut; ++o) s[o] = s2[o].x + s2[o].y;
             float* rbuf = red + (kRedBufs == 2 ? (it & 1) : 0) * ((kYSlices - 1) * kM * 2);   // the other slices' warps hand their sums to the last one
             if (yh < kYSlices - 1) {
 #pragma unroll
