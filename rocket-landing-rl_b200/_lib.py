@@ -21,7 +21,7 @@ EXPORTS = ("rl_abi_version", "rl_last_error", "rl_params_default", "rl_state_byt
            "rl_set_state", "rl_get_state", "rl_stats", "rl_step_host", "rl_reset_host", "rl_get_state_host",
            "rl_launch_count", "rl_vecnorm_last_error", "rl_vecnorm_create", "rl_vecnorm_destroy",
            "rl_vecnorm_reset", "rl_vecnorm_step", "rl_vecnorm_normalize_obs", "rl_vecnorm_get_stats",
-           "rl_vecnorm_set_stats", "rl_vecnorm_launch_count", "rl_rollout_last_error", "rl_gae", "rl_sim_step",
+           "rl_vecnorm_set_stats", "rl_vecnorm_launch_count", "rl_rollout_last_error", "rl_gae", "rl_episode_flags", "rl_sim_step",
            "rl_sim_step_host", "rl_policy_last_error", "rl_mlp_blob_bytes", "rl_mlp_forward", "rl_policy_sample")
 
 _lib = None
@@ -94,6 +94,7 @@ def load():
     L.rl_sim_step.argtypes = [vp, vp, vp, vp, vp, vp]
     L.rl_sim_step_host.argtypes = [vp, vp, vp]
     L.rl_gae.argtypes = [vp] * 7 + [i32, i64, f64, f64, vp]
+    L.rl_episode_flags.argtypes = [vp] * 5 + [i64, vp]
     L.rl_policy_last_error.restype = C.c_char_p
     L.rl_mlp_blob_bytes.restype = i64
     L.rl_mlp_forward.argtypes = [vp, vp, vp, i64, i32, vp]

@@ -8,6 +8,7 @@
 // issued together, ahead of the chain that consumes them, and CTAs own consecutive rockets and are
 // dispatched in address order (profiles/README.md "grid order").
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 
 #include <cuda_runtime.h>
@@ -74,6 +75,40 @@ __global__ void __launch_bounds__(256) gae_kernel(const float* __restrict__ rewa
     }
 }
 
+// What SB3's collect_rollouts derives on the host from `dones` and `infos` after every step, in one pass
+// over the two flag arrays: the next step's episode_start, the "ended by the time limit alone" mask whose
+// rewards get the gamma V(terminal observation) bootstrap, and whether there is any such rocket at all.
+__global__ void __launch_bounds__(256) episode_flags_kernel(const uint8_t* __restrict__ terminated,
+                                                            const uint8_t* __restrict__ truncated,
+                                                            uint8_t* __restrict__ episode_start_next,
+                                                            uint8_t* __restrict__ time_limit, int* __restrict__ any_time_limit,
+                                                            int64_t n, int vectorised) {
+    const int64_t t = blockIdx.x * 256ll + threadIdx.x;
+    uint32_t any = 0;
+    if (vectorised) {                                      // 16 rockets per thread (all pointers 16-byte aligned)
+        if (16 * t + 16 <= n) {
+            const uint4 a = reinterpret_cast<const uint4*>(terminated)[t], b = reinterpret_cast<const uint4*>(truncated)[t];
+            const uint4 tl = make_uint4(b.x & ~a.x, b.y & ~a.y, b.z & ~a.z, b.w & ~a.w);   // flags are 0 / 1 bytes
+            if (episode_start_next) reinterpret_cast<uint4*>(episode_start_next)[t] = make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w);
+            reinterpret_cast<uint4*>(time_limit)[t] = tl;
+            any = tl.x | tl.y | tl.z | tl.w;
+        } else {
+            for (int64_t i = 16 * t; i < n; ++i) {
+                const uint8_t a = terminated[i], b = truncated[i], tl = (uint8_t)(b & (a ^ 1u));
+                if (episode_start_next) episode_start_next[i] = a | b;
+                time_limit[i] = tl;
+                any |= tl;
+            }
+        }
+    } else if (t < n) {
+        const uint8_t a = terminated[t], b = truncated[t], tl = (uint8_t)(b & (a ^ 1u));
+        if (episode_start_next) episode_start_next[t] = a | b;
+        time_limit[t] = tl;
+        any = tl;
+    }
+    if (__any_sync(0xffffffffu, any != 0) && (threadIdx.x & 31) == 0) atomicOr(any_time_limit, 1);
+}
+
 }  // namespace
 
 extern "C" {
@@ -95,6 +130,25 @@ int rl_gae(const float* rewards, const float* values, const uint8_t* episode_sta
                                                        advantages, returns, T, n_envs, (float)gamma, (float)gae_lambda);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return ro_fail(RL_E_CUDA, "rl_gae launch failed: %s", cudaGetErrorString(e));
+    return RL_OK;
+}
+
+// terminated, truncated: uint8 [N] (0 / 1) of the step just taken.  Writes episode_start_next[i] = terminated |
+// truncated (nullable), time_limit[i] = truncated & !terminated, and ORs 1 into *any_time_limit (int32, DEVICE)
+// if any rocket ended by the time limit alone.  DEVICE pointers, enqueue only.
+int rl_episode_flags(const uint8_t* terminated, const uint8_t* truncated, uint8_t* episode_start_next, uint8_t* time_limit,
+                     int32_t* any_time_limit, int64_t n_envs, void* stream) {
+    if (!terminated || !truncated || !time_limit || !any_time_limit) return ro_fail(RL_E_INVALID, "rl_episode_flags: null argument");
+    if (n_envs < 1) return ro_fail(RL_E_INVALID, "rl_episode_flags: n_envs must be positive");
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(terminated) | reinterpret_cast<uintptr_t>(truncated) |
+                           reinterpret_cast<uintptr_t>(episode_start_next) | reinterpret_cast<uintptr_t>(time_limit);
+    const int vectorised = (bits & 15) == 0;
+    const int64_t threads = vectorised ? (n_envs + 15) / 16 : n_envs;
+    if ((threads + 255) / 256 > 2147483647LL) return ro_fail(RL_E_INVALID, "rl_episode_flags: too many rockets per call");
+    episode_flags_kernel<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(terminated, truncated, episode_start_next,
+                                                                                       time_limit, any_time_limit, n_envs, vectorised);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return ro_fail(RL_E_CUDA, "rl_episode_flags launch failed: %s", cudaGetErrorString(e));
     return RL_OK;
 }
 

@@ -252,6 +252,12 @@ def collect_rollout(env, policy, buffer: DeviceRolloutBuffer, last_obs: torch.Te
     obs = buffer.observations[0]
     starts = last_episode_starts
     pending = None                         # (step, time-limit mask) whose bootstrap is still to be decided
+    L = _lib.load()
+    n_envs = buffer.num_envs
+    flag = _pinned_flags(T, last_obs.device)
+    scratch = _scratch(T, n_envs, last_obs.device)
+    if bootstrap_timeouts:
+        scratch["any"].zero_()
     for t in range(T):
         if fused:     # sample, clip and log-prob in the policy kernel's epilogue, straight into the buffer
             _, clipped, _, _ = policy.act(obs, buffer.actions[t], buffer.log_probs[t])
@@ -271,48 +277,64 @@ def collect_rollout(env, policy, buffer: DeviceRolloutBuffer, last_obs: torch.Te
             if nxt is not None:
                 nxt.copy_(obs)
                 obs = nxt
+        starts_out = buffer.episode_starts[t + 1] if t + 1 < T else scratch["last_starts"]
         if bootstrap_timeouts:
             # SB3 adds gamma V(terminal observation) to the reward of a step that ended by the time limit
             # (infos[i]["TimeLimit.truncated"]).  Asking the device "did any rocket time out?" every
             # step would stall the host behind the GPU, so the question is asked asynchronously and
             # answered one step late: a rocket that timed out at step t was reset at step t and cannot
             # finish another episode at step t + 1, so its row of the terminal-observation buffer is
-            # still intact then.
-            timeout = torch.logical_and(truncated, torch.logical_not(terminated))
-            flag = _pinned_flags(T, last_obs.device)
-            flag["host"][t].copy_(timeout.any(), non_blocking=True)
+            # still intact then.  One kernel (rl_episode_flags) derives the next episode_start, the
+            # time-limit mask and the "any" flag from the step's two flag arrays.
+            timeout = scratch["timeout"][t & 1]
+            rc = L.rl_episode_flags(terminated.data_ptr(), truncated.data_ptr(), starts_out.data_ptr(), timeout.data_ptr(),
+                                    scratch["any"][t].data_ptr(), n_envs, torch.cuda.current_stream(last_obs.device).cuda_stream)
+            if rc != 0:
+                raise _lib.RocketLibraryError(f"rl_episode_flags failed ({rc}): {L.rl_rollout_last_error().decode()}")
+            flag["host"][t].copy_(scratch["any"][t], non_blocking=True)
             flag["events"][t].record()
             if pending is not None:
-                _bootstrap(policy, buffer, info, pending, flag, gamma, terminated | truncated)
+                _bootstrap(policy, buffer, info, pending, flag, gamma, starts_out)
             pending = (t, timeout)
-        if t + 1 < T:
-            starts = torch.logical_or(terminated, truncated, out=buffer.episode_starts[t + 1])
+            starts = starts_out
         else:
-            starts = terminated | truncated
+            starts = torch.logical_or(terminated, truncated, out=starts_out)
     if pending is not None:
         _bootstrap(policy, buffer, info, pending, _pinned_flags(T, last_obs.device), gamma, None)
     last_values = policy.predict_values(obs)
     buffer.compute_returns_and_advantage(last_values, starts, gamma, gae_lambda)
-    return obs, starts
+    return obs, starts.clone()             # (the last step's dones live in per-shape scratch: hand out a copy)
 
 
 _FLAGS: dict = {}
+_SCRATCH: dict = {}
 
 
 def _pinned_flags(n_steps: int, device) -> dict:
     """Per-device pinned host flags + events for the asynchronous "any time-limit truncation?" test."""
     key = (str(device), n_steps)
     if key not in _FLAGS:
-        _FLAGS[key] = {"host": torch.zeros(n_steps, dtype=torch.bool).pin_memory(),
+        _FLAGS[key] = {"host": torch.zeros(n_steps, dtype=torch.int32).pin_memory(),
                        "events": [torch.cuda.Event() for _ in range(n_steps)]}
     return _FLAGS[key]
+
+
+def _scratch(n_steps: int, n_envs: int, device) -> dict:
+    """Per-(device, shape) device scratch of ``collect_rollout``: two alternating time-limit masks (a mask is
+    read one step after it was written), the per-step "any time-limit truncation" words, the last step's dones."""
+    key = (str(device), n_steps, n_envs)
+    if key not in _SCRATCH:
+        _SCRATCH[key] = {"timeout": torch.zeros((2, n_envs), dtype=torch.bool, device=device),
+                         "any": torch.zeros(n_steps, dtype=torch.int32, device=device),
+                         "last_starts": torch.zeros(n_envs, dtype=torch.bool, device=device)}
+    return _SCRATCH[key]
 
 
 def _bootstrap(policy, buffer: DeviceRolloutBuffer, info, pending, flag, gamma: float, done_now) -> None:
     """Resolve the time-limit bootstrap of an earlier step (see ``collect_rollout``)."""
     t, mask = pending
     flag["events"][t].synchronize()        # recorded a whole env step ago: already complete in steady state
-    if not bool(flag["host"][t]):
+    if not int(flag["host"][t]):
         return
     if done_now is not None:               # rows overwritten since (cannot happen with episodes longer than one step)
         mask = torch.logical_and(mask, torch.logical_not(done_now))

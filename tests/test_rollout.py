@@ -48,6 +48,39 @@ def test_gae_kernel_matches_the_oracle():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n,offset", [(1, 0), (15, 0), (16, 0), (4099, 0), (1 << 20, 0), (4099, 3)])
+def test_episode_flags_kernel(n, offset):
+    """rl_episode_flags against the three torch expressions it replaces in collect_rollout (SB3 derives the
+    same from dones / infos on the host); ragged sizes and a misaligned view take the scalar path."""
+    import torch
+    from rocket_landing_rl_b200 import _lib
+    L = _lib.load()
+    g = torch.Generator(device="cuda").manual_seed(n + offset)
+    base = torch.rand((2, n + offset), device="cuda", generator=g)
+    terminated = (base[0] < 0.3)[offset:]
+    truncated = (base[1] < (0.3 if n > 16 else 0.9))[offset:]
+    if offset:
+        assert terminated.data_ptr() % 16 != 0
+    else:
+        terminated, truncated = terminated.contiguous(), truncated.contiguous()
+    starts = torch.zeros(n + 32, dtype=torch.bool, device="cuda")
+    limit = torch.zeros(n + 32, dtype=torch.bool, device="cuda")
+    any_flag = torch.zeros(2, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    assert L.rl_episode_flags(terminated.data_ptr(), truncated.data_ptr(), starts.data_ptr(), limit.data_ptr(),
+                              any_flag.data_ptr(), n, stream) == 0
+    want_limit = truncated & ~terminated
+    assert torch.equal(starts[:n], terminated | truncated) and not starts[n:].any()      # nothing written past n
+    assert torch.equal(limit[:n], want_limit) and not limit[n:].any()
+    assert any_flag.tolist() == [int(want_limit.any()), 0]
+    # a null episode_start output is allowed; no time-limit rocket leaves the word alone
+    none = torch.zeros_like(truncated)
+    assert L.rl_episode_flags(terminated.data_ptr(), none.data_ptr(), None, limit.data_ptr(), any_flag[1:].data_ptr(), n, stream) == 0
+    assert not limit.any() and any_flag.tolist()[1] == 0
+    assert L.rl_episode_flags(None, none.data_ptr(), None, limit.data_ptr(), any_flag.data_ptr(), n, stream) != 0
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("fused", [False, True])
 def test_device_resident_rollout_collection(fused):
     """configs[4] in miniature: envs -> VecNormalize -> policy -> buffer -> GAE, all on the GPU,
