@@ -311,8 +311,8 @@ int rl_episode_flags(const uint8_t *terminated, const uint8_t *truncated, uint8_
 /* ---------------------------------------------------------------------------------------------
  * Fused inference of one of the reference's actor-critic MLPs (scripts/train.py:117: net_arch =
  * dict(pi=[256, 256], vf=[256, 256]), tanh; assets/model/v3): out = W3 tanh(W2 tanh(W1 obs + b1) +
- * b2) + b3 for n rockets in one launch, activations kept in registers (tensor cores, bf16 weights,
- * fp32 accumulation).  `blob` is the packed net in DEVICE memory (16-byte aligned), RL_MLP_BLOB_BYTES:
+ * b2) + b3 for n rockets in one launch, activations kept on chip (tcgen05 tensor cores, bf16 weights,
+ * fp32 accumulation in tensor memory).  `blob` is the packed net in DEVICE memory (16-byte aligned), RL_MLP_BLOB_BYTES:
  *   bf16 [256][16]  W1[j][0..7] twice (the kernel feeds the observation as bf16 high | low parts)
  *   f32  [256]      b1
  *   bf16 [256][256] W2 (row = output unit, as nn.Linear.weight)

@@ -117,7 +117,7 @@ def test_device_resident_rollout_collection(fused):
 
 @pytest.mark.gpu
 def test_fused_mlp_kernel_matches_the_pytorch_module():
-    """rl_mlp_forward (tensor cores, bf16 weights, fp32 accumulation, activations in registers)
+    """rl_mlp_forward (tcgen05 tensor cores, bf16 weights, fp32 accumulation, activations on chip)
     against the fp32 PyTorch module it packs.  Tolerance: bf16 weights carry 2^-9 relative error
     each and the hidden activations are rounded to bf16 once; over 256-term dot products of O(1)
     activations with O(1/16) weights that is ~1e-3 absolute on outputs of O(0.3); 1e-2 is asserted."""
