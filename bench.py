@@ -268,6 +268,34 @@ def measure_extras(torch, dev) -> dict:
                           "pipeline": "rl_step -> rl_vecnorm_step -> fused tcgen05 policy + value nets (rl_policy.cu) -> "
                                       "[T,N] device buffers -> rl_gae"}
     raw.close()
+    del buf, policy, venv, raw, state
+    torch.cuda.empty_cache()
+
+    # The denominator of roofline.frac is a BURST copy figure (MEASURED_PEAKS.json: best of 10 copies on an idle
+    # board).  The headline kernel is timed after seconds of back-to-back launches, with the board on its power
+    # cap; the same copy (torch b.copy_(a), 1 Gi bf16 elements, read + write bytes) is timed here both ways.
+    a = torch.empty(1 << 30, dtype=torch.bfloat16, device=dev)
+    b = torch.empty_like(a)
+    nbytes = 2.0 * a.numel() * a.element_size()
+    torch.cuda.synchronize(dev)
+    time.sleep(0.5)                                          # let the board leave the cap
+    burst = []
+    for _ in range(10):
+        e0.record()
+        b.copy_(a)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        burst.append(e0.elapsed_time(e1))
+    for _ in range(1500):                                    # ~1 s of back-to-back copies
+        b.copy_(a)
+    e0.record()
+    for _ in range(200):
+        b.copy_(a)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    out["copy_kernel"] = {"burst_gbs": nbytes / (min(burst) * 1e-3) / 1e9, "sustained_gbs": nbytes / (e0.elapsed_time(e1) / 200 * 1e-3) / 1e9,
+                          "how": "torch b.copy_(a) over 1 Gi bf16 elements, read + write bytes: best of 10 on an idle board; "
+                                 "200 copies after 1 500 back-to-back ones"}
     return out
 
 
@@ -477,6 +505,8 @@ def main() -> None:
         }
         if world == 1 and not args.no_extras:
             line["extra"] = measure_extras(torch, dev)
+            # (informational, next to the contract's frac: the same kernel time against the copy rate this board sustains)
+            roofline["frac_of_sustained_copy"] = roofline["achieved"] / line["extra"]["copy_kernel"]["sustained_gbs"]
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
