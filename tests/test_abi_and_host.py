@@ -96,6 +96,10 @@ def test_create_fails_loudly_without_gpu_or_with_bad_args():
         with pytest.raises(_lib.RocketLibraryError):
             pkg.RocketLandingSB3VecEnv(16)
     assert lib.rl_step(None, None, None, None, None, None, None, None, None, None, None, 1, 1, None) == -1
+    # the rollout neighbours validate their arguments before they touch the device
+    assert lib.rl_episode_flags(None, None, None, None, None, 16, None) == -1 and b"null" in lib.rl_rollout_last_error()
+    assert lib.rl_gae(None, None, None, None, None, None, None, 1, 16, 0.99, 0.95, None) == -1
+    assert lib.rl_mlp_forward(None, None, None, 16, 1, None) == -1 and b"null" in lib.rl_policy_last_error()
 
 
 def test_product_never_imports_the_oracle():
