@@ -455,8 +455,10 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
             out_store(&a.reward[i], reward);
             out_store(&a.terminated[i], (uint8_t)(terminated ? 1 : 0));
             out_store(&a.truncated[i], (uint8_t)(truncated ? 1 : 0));
-            if (a.optional & 1u) out_store(reinterpret_cast<uint8_t*>(&a.landing[i]), (uint8_t)landing);
-            if (a.optional & 2u) out_store(&a.raw_accel[i], make_float2(o.ax, o.ay));
+            if (a.optional) {                                  // rarely asked for: one uniform test on the common path
+                if (a.optional & 1u) out_store(reinterpret_cast<uint8_t*>(&a.landing[i]), (uint8_t)landing);
+                if (a.optional & 2u) out_store(&a.raw_accel[i], make_float2(o.ax, o.ay));
+            }
         }
     }
     cp_async_wait<0>();
