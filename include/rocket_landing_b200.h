@@ -315,7 +315,8 @@ int rl_episode_flags(const uint8_t *terminated, const uint8_t *truncated, uint8_
  * fp32 accumulation in tensor memory).  `blob` is the packed net in DEVICE memory (16-byte aligned), RL_MLP_BLOB_BYTES:
  *   bf16 [256][16]  W1[j][0..7] twice (the kernel feeds the observation as bf16 high | low parts)
  *   f32  [256]      b1
- *   bf16 [256][256] W2 (row = output unit, as nn.Linear.weight)
+ *   bf16 [32][256][8] W2 in the tensor core's K-major tile order: element (n, k) of nn.Linear.weight
+ *                   (n = output unit) at [k / 8][n][k % 8] -- the image of the kernel's shared-memory operand
  *   f32  [256]      b2
  *   f32  [2][256]   W3 (second row ignored when out_dim = 1)
  *   f32  [4]        b3 (first out_dim used)

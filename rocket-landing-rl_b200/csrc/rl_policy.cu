@@ -15,7 +15,7 @@
 //
 //   shared memory (operands in the canonical K-major no-swizzle layout: 8 x 16-byte "core matrices",
 //   element (row r, k) at (k / 8) LBO + (r / 8) 128 + (r % 8) 16 + (k % 8) 2 bytes):
-//     W2s  256 x 256 bf16, LBO 4096   (loaded once per CTA)        W1s  256 x 16, LBO 4096
+//     W2s  256 x 256 bf16, LBO 4096   (one TMA bulk copy per CTA)  W1s  256 x 16, LBO 4096
 //     A2s  128 x 256 bf16, LBO 2048   (layer-1 activations)        A1s  2 x (128 x 16), LBO 2048 (obs hi | lo)
 //     Bb1, Bb2, Ones                   bias tiles: b1 and b2 come out of the tensor core too
 //   tensor memory (512 columns): [0, 128) layer-1 ring (2 slots of 64), [128, 512) three layer-2
@@ -45,8 +45,10 @@
 //   * the period of the pipeline cannot be shorter than the issuing warp's own instruction stream
 //     (42 MMAs, 10 commits, 10 waits per block), so the observations are staged by team Y and the
 //     descriptors are 32-bit words that only need an add.
-// Measured (profiles/mlp_forward_r2b_summary.txt): 0.163 ms (value net) / 0.178 ms (policy net) at
-// 1 Mi rockets, MUFU pipe 80 % busy, tensor pipe 47 %.
+//   * W2 (128 KiB) is stored in the blob as the image of its shared-memory operand and staged by one
+//     bulk copy of the TMA engine that only the issuing warp ever waits for.
+// Measured (profiles/mlp_forward_r2b_summary.txt): 0.160 ms (value net) / 0.172 ms (policy net) at
+// 1 Mi rockets, MUFU pipe 83 % busy, tensor pipe 49 %.
 //
 // Weights are bf16 (what torch.autocast(bfloat16) would use), accumulation fp32, biases bf16 high +
 // low parts (16 mantissa bits); measured against the fp32 module: rms error 8e-4, max 4e-3 on
@@ -80,7 +82,7 @@ constexpr int kObs = 8;
 // packed weights in global memory (RL_MLP_BLOB_BYTES, built by the host side: rollout.py pack_mlp)
 constexpr int kOffW1 = 0;                               // bf16 [256][16]: W1[n][0..7] twice
 constexpr int kOffB1 = kOffW1 + kHidden * 16 * 2;       // f32 [256]
-constexpr int kOffW2 = kOffB1 + kHidden * 4;            // bf16 [256][256]  (row = output unit, as nn.Linear.weight)
+constexpr int kOffW2 = kOffB1 + kHidden * 4;            // bf16 [32][256][8]: W2[n][k] at [k / 8][n][k % 8] = the image of W2s
 constexpr int kOffB2 = kOffW2 + kHidden * kHidden * 2;  // f32 [256]
 constexpr int kOffW3 = kOffB2 + kHidden * 4;            // f32 [2][256]     (second row unused by a 1-wide head)
 constexpr int kOffB3 = kOffW3 + 2 * kHidden * 4;        // f32 [2]
@@ -151,7 +153,7 @@ constexpr int kSmB3 = kSmW3 + 2 * kHidden * 4;
 constexpr int kRedBufs = kYSlices > 2 ? 1 : 2;            // one buffer (and a second barrier after it has been read) when two do not fit
 constexpr int kSmRed = kSmB3 + 16;                        // kRedBufs x [kYSlices - 1][128 rows][2] f32: partial sums handed to the last slice's warp
 constexpr int kSmBar = kSmRed + kRedBufs * (kYSlices - 1) * kM * 2 * 4;
-constexpr int kNumBars = 11;                              // x_ready[4] | l1bar[2] | barA | e0 | barB | y_doneA | y_doneB
+constexpr int kNumBars = 12;                              // x_ready[4] | l1bar[2] | barA | e0 | barB | y_doneA | y_doneB | wbar
 constexpr int kSmemBytes = kSmBar + 8 * kNumBars + 8 + 16; // ... + the TMEM base address
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -239,16 +241,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + kSmBar;
-    const uint32_t x_ready = bars, l1bar = bars + 32, barA = bars + 48, e0 = bars + 56, barB = bars + 64, y_doneA = bars + 72,
+    const uint32_t x_ready = bars, l1bar = bars + 32, barA = bars + 48, e0 = bars + 56, barB = bars + 64, y_doneA = bars + 72, wbar = bars + 88,
                    y_doneB = bars + 80;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kSmBar + 8 * kNumBars + 8);
 
     // ---- one-time setup: weights in the canonical layout, barriers, tensor memory ------------------
-    for (int c = tid; c < kHidden * 32; c += kThreads) {                 // W2: chunk (row n, 8 k's kc); consecutive threads -> consecutive rows
-        const int n_row = c & 255, kc = c >> 8;
-        *reinterpret_cast<uint4*>(smem + kSmW2 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
-            *reinterpret_cast<const uint4*>(blob + kOffW2 + n_row * (kHidden * 2) + kc * 16);
-    }
     for (int c = tid; c < kHidden * 2; c += kThreads) {                  // W1 stacked twice: 2 chunks per row
         const int n_row = c & 255, kc = c >> 8;
         *reinterpret_cast<uint4*>(smem + kSmW1 + kc * kLboW + (n_row >> 3) * kSbo + (n_row & 7) * 16) =
@@ -269,6 +266,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
     for (int c = tid; c < (kSmRed - kSmW3) / 16; c += kThreads)        // W3 | b3
         *reinterpret_cast<uint4*>(smem + kSmW3 + c * 16) = *reinterpret_cast<const uint4*>(blob + kOffW3 + c * 16);
     if (tid == 0) {
+        // W2 (128 KiB) is stored in the blob as the image of W2s: one bulk copy by the TMA engine, complete
+        // (mbarrier wbar) long before the first layer-2 MMA needs it -- nothing else waits for it
+        mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(wbar), "r"(kHidden * kHidden * 2) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(sbase + kSmW2), "l"(blob + kOffW2), "r"(kHidden * kHidden * 2), "r"(wbar) : "memory");
 #pragma unroll
         for (int c = 0; c < 4; ++c) mbar_init(x_ready + 8 * c, kXWarps);
         mbar_init(l1bar, 1);
@@ -494,6 +498,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
             issue_layer1(a1_lo0, 0);
             issue_layer1(a1_lo0, 1);
         }
+        mbar_wait(wbar, 0u);                                      // W2 has landed (the bulk copy was the kernel's first instruction)
         int it = 0;
         for (int64_t blk = blockIdx.x; blk < n_blocks; blk += stride, ++it) {
             const bool has_next = blk + stride < n_blocks;

@@ -99,7 +99,7 @@ MLP_BLOB_BYTES = 143376          # include/rocket_landing_b200.h: RL_MLP_BLOB_BY
 
 def pack_mlp(body: nn.Sequential, head: nn.Linear, device) -> torch.Tensor:
     """One tanh MLP 8 -> 256 -> 256 -> head (1 or 2 outputs) in the layout ``rl_mlp_forward`` reads
-    (``include/rocket_landing_b200.h``): bf16 W1 stacked twice, f32 b1, bf16 W2, f32 b2, f32 W3 [2][256],
+    (``include/rocket_landing_b200.h``): bf16 W1 stacked twice, f32 b1, bf16 W2 (tiled), f32 b2, f32 W3 [2][256],
     f32 b3 [4]."""
     l1, l2 = body[0], body[2]
     if (l1.weight.shape, l2.weight.shape, head.weight.shape[1]) != ((256, 8), (256, 256), 256) or head.weight.shape[0] not in (1, 2):
@@ -116,7 +116,9 @@ def pack_mlp(body: nn.Sequential, head: nn.Linear, device) -> torch.Tensor:
 
     put(torch.cat([l1.weight, l1.weight], dim=1).to(torch.bfloat16))           # [256][16]
     put(l1.bias.float())
-    put(l2.weight.to(torch.bfloat16))                                          # [256][256]
+    # W2 in the tensor core's K-major tile order (the image of the kernel's shared-memory operand, so that one
+    # bulk copy stages it): element (n, k) of nn.Linear.weight at [k // 8][n][k % 8]
+    put(l2.weight.detach().to(torch.bfloat16).view(256, 32, 8).permute(1, 0, 2))   # [32][256][8]
     put(l2.bias.float())
     w3 = torch.zeros((2, 256), dtype=torch.float32, device=head.weight.device)
     w3[:head.weight.shape[0]] = head.weight.detach().float()

@@ -301,7 +301,8 @@ def test_pack_mlp_layout_matches_the_header():
         w1 = take(256 * 16 * 2, torch.bfloat16).view(256, 16)
         assert torch.equal(w1[:, :8], body[0].weight.detach().to(torch.bfloat16)) and torch.equal(w1[:, 8:], w1[:, :8])
         assert torch.equal(take(256 * 4, torch.float32), body[0].bias.detach())
-        assert torch.equal(take(256 * 256 * 2, torch.bfloat16).view(256, 256), body[2].weight.detach().to(torch.bfloat16))
+        w2 = take(256 * 256 * 2, torch.bfloat16).view(32, 256, 8)                 # [k / 8][n][k % 8]
+        assert torch.equal(w2.permute(1, 0, 2).reshape(256, 256), body[2].weight.detach().to(torch.bfloat16))
         assert torch.equal(take(256 * 4, torch.float32), body[2].bias.detach())
         w3 = take(2 * 256 * 4, torch.float32).view(2, 256)
         k = head.weight.shape[0]
