@@ -226,6 +226,81 @@ __device__ __forceinline__ uint32_t tanh_bf16x2(uint32_t x) {
     return y;
 }
 
+// ---- tanh on the FMA pipe (part of both epilogues) ---------------------------------------------
+// The MUFU pipe (16 tanh per clock and SM) is the kernel's roofline while two thirds of the issue slots and
+// nearly all of the FMA pipe idle, so one pair in four of the layer-1 epilogue (RL_MLP_X_POLY) -- and of the
+// layer-2 epilogue of the value net (RL_MLP_Y_POLY_VALUE; the policy net's team Y has no issue slots to spare:
+// it carries a second head row) -- takes this route instead: tanh(x) ~ x R(x^2), fitted on |x| <= 3.8, with R of
+// degree 7 in packed FFMA2 (two units per instruction, coefficients as immediates), clamped beyond; maximum
+// absolute error 1.3e-3 over all x (tools/tanh_poly_fit.py).  The MUFU route of epilogue 1 rounds its INPUT
+// to bf16 first and is no more accurate: the output error against the fp32 module goes DOWN (rms 8.3e-4 ->
+// 7.8e-4).  Measured (profiles/tools/pipe_rates.cu): FFMA2 / FMUL2 issue every 2 cycles per scheduler, MUFU
+// every 8, so a pair costs ~22 cycles of the FMA pipe here against 16 of the MUFU pipe there, and team X, which
+// sets the pace, gets slower with every pair it converts: more than one pair in four loses again
+// (profiles/README.md has the sweep).
+#ifndef RL_MLP_X_POLY
+#define RL_MLP_X_POLY 1
+#endif
+#ifndef RL_MLP_Y_POLY_VALUE
+#define RL_MLP_Y_POLY_VALUE 1
+#endif
+#ifndef RL_MLP_Y_POLY_POLICY
+#define RL_MLP_Y_POLY_POLICY 0
+#endif
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// Inputs are clamped where the fitted polynomial has its maximum, x R(x^2) = 1.00016 at |x| = 3.727 (beyond the
+// fitted range it turns over), so a saturated unit reads 1.0002 and the bound of 1.3e-3 holds for every input.
+constexpr float kTanhClamp = 3.727f;
+// x R(u) for the pair x with u = x^2 <= c^2 (the (c, c) pairs become FFMA2 immediates)
+__device__ __forceinline__ uint64_t tanh_poly_core(uint64_t x, uint64_t u) {
+    const float c[8] = {-9.573820403e-08f, 5.802626095e-06f, -1.463067778e-04f, 2.001198300e-03f,
+                        -1.635971380e-02f, 8.460201472e-02f, -3.004610678e-01f, 9.930788304e-01f};
+    uint64_t r = fma2(u, pk2(c[0], c[0]), pk2(c[1], c[1]));
+#pragma unroll
+    for (int i = 2; i < 8; ++i) r = fma2(r, u, pk2(c[i], c[i]));
+    return mul2(x, r);
+}
+// epilogue 1: bf16x2 of tanh(x0) (bits 0..15), tanh(x1).  u is clamped, and beyond c the linear continuation
+// is clamped at +-1 after the rounding to bf16 (two packed instructions for the pair).
+__device__ __forceinline__ uint32_t tanh_poly_bf16x2(float x0, float x1) {
+    const uint64_t x = pk2(x0, x1);
+    float u0, u1, t0, t1;
+    upk2(mul2(x, x), u0, u1);
+    upk2(tanh_poly_core(x, pk2(fminf(u0, kTanhClamp * kTanhClamp), fminf(u1, kTanhClamp * kTanhClamp))), t0, t1);
+    uint32_t b = pack_bf16(t0, t1);
+    asm("min.bf16x2 %0, %0, %1;" : "+r"(b) : "r"(0x3F803F80u));
+    asm("max.bf16x2 %0, %0, %1;" : "+r"(b) : "r"(0xBF80BF80u));
+    return b;
+}
+// epilogue 2: fp32 results; the inputs are clamped to +-c instead (c R(c^2) = 1.00016: no clamp of the result)
+__device__ __forceinline__ void tanh_poly_f32x2(float x0, float x1, float& t0, float& t1) {
+    const uint64_t x = pk2(fminf(fmaxf(x0, -kTanhClamp), kTanhClamp), fminf(fmaxf(x1, -kTanhClamp), kTanhClamp));
+    upk2(tanh_poly_core(x, mul2(x, x)), t0, t1);
+}
+
+// One thread of a converged warp (elect.sync): ptxas then knows that what the branch guards runs on a single
+// thread and issues the tcgen05 instructions from uniform registers directly -- behind `lane == 0` every one of
+// them sits in a loop that elects and broadcasts (ELECT / R2UR.BROADCAST / BRA.U.ANY, ~11 instructions per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t is_leader;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(is_leader));
+    return is_leader != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
@@ -353,8 +428,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
                 for (int k4 = 0; k4 < 4; ++k4) {                  // 8 units = one 16-byte chunk of the K-major operand
                     uint32_t w[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        w[j] = tanh_bf16x2(pack_bf16(__uint_as_float(cur[8 * k4 + 2 * j]), __uint_as_float(cur[8 * k4 + 2 * j + 1])));
+                    for (int j = 0; j < 4; ++j) {
+                        const float x0 = __uint_as_float(cur[8 * k4 + 2 * j]), x1 = __uint_as_float(cur[8 * k4 + 2 * j + 1]);
+                        w[j] = (j < RL_MLP_X_POLY) ? tanh_poly_bf16x2(x0, x1) : tanh_bf16x2(pack_bf16(x0, x1));
+                    }
                     const int kc = (col0 >> 3) + k4;
                     *reinterpret_cast<uint4*>(smem + kSmA2 + kc * kLboA + (row >> 3) * kSbo + (row & 7) * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                 }
@@ -366,6 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
         }
     } else if (warp < kXWarps + kYWarps) {
         // =============================== team Y: epilogue 2 and the head ==============================
+        constexpr int kYPoly = kOut == 1 ? RL_MLP_Y_POLY_VALUE : RL_MLP_Y_POLY_POLICY;   // pairs in four on the FMA pipe
         const float* w3s = reinterpret_cast<const float*>(smem + kSmW3);
         const float* b3s = reinterpret_cast<const float*>(smem + kSmB3);
         float* red = reinterpret_cast<float*>(smem + kSmRed);
@@ -389,8 +467,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
                     const int unit0 = 128 * nh + kYUnits * yh + 32 * c;
 #pragma unroll
                     for (int k = 0; k < 32; k += 4) {
-                        const float h0 = tanh_fast(__uint_as_float(cur[k])), h1 = tanh_fast(__uint_as_float(cur[k + 1]));
-                        const float h2 = tanh_fast(__uint_as_float(cur[k + 2])), h3 = tanh_fast(__uint_as_float(cur[k + 3]));
+                        float h0, h1, h2, h3;                             // pairs (k, k + 1), (k + 2, k + 3): pair index k / 2, k / 2 + 1
+                        if (((k >> 1) & 3) < kYPoly) tanh_poly_f32x2(__uint_as_float(cur[k]), __uint_as_float(cur[k + 1]), h0, h1);
+                        else h0 = tanh_fast(__uint_as_float(cur[k])), h1 = tanh_fast(__uint_as_float(cur[k + 1]));
+                        if ((((k >> 1) + 1) & 3) < kYPoly) tanh_poly_f32x2(__uint_as_float(cur[k + 2]), __uint_as_float(cur[k + 3]), h2, h3);
+                        else h2 = tanh_fast(__uint_as_float(cur[k + 2])), h3 = tanh_fast(__uint_as_float(cur[k + 3]));
 #pragma unroll
                         for (int o = 0; o < kOut; ++o) {                  // even / odd units accumulate in the two halves of a packed FMA
                             const float4 w = *reinterpret_cast<const float4*>(w3s + o * kHidden + unit0 + k);
@@ -493,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
                 mma_lo(tmem + acc, a2_lo + ((uint32_t)(ks * 2 * kLboA) >> 4), w2_lo + ((uint32_t)(ks * 2 * kLboW) >> 4) + n_off, idesc_n(128), 1u);
             }
         };
-        if (lane == 0) {
+        if (elect_one()) {
             fence_after_sync();
             issue_layer1(a1_lo0, 0);
             issue_layer1(a1_lo0, 1);
@@ -510,7 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
                 mbar_wait(x_ready + 8 * c, par);                  // team X: A2s slice c written, ring slot c & 1 drained
                 // team Y: half A of the previous block drained -> accB is free; observations of the next block staged
                 if (c == 2 && it > 0) mbar_wait(y_doneA, ppar);
-                if (lane == 0) {
+                if (elect_one()) {
                     fence_after_sync();
                     if (c < 2) issue_layer1(a1_cur, c + 2);       // team X waits for this one first
                     else if (has_next) issue_layer1(a1_nxt, c - 2);

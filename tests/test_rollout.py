@@ -148,6 +148,62 @@ def test_fused_mlp_kernel_matches_the_pytorch_module():
     assert a.shape == (1000, 2) and v.shape == (1000,) and lp.shape == (1000,)
 
 
+def test_fma_pipe_tanh_polynomial_of_the_mlp_kernel():
+    """The fused MLP kernel evaluates part of its tanh on the FMA pipe (csrc/rl_policy.cu: tanh_poly_core).
+    The coefficients are read from the source, so that they cannot drift from tools/tanh_poly_fit.py's
+    claim: both clamped forms (epilogue 1 clamps u = x^2 and the result, epilogue 2 clamps x) stay within
+    1.4e-3 of tanh for EVERY fp32 input, are odd and never leave [-1, 1] by more than that."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(__file__), "..", "rocket-landing-rl_b200", "csrc", "rl_policy.cu")).read()
+    body = re.search(r"tanh_poly_core\(uint64_t x, uint64_t u\) \{\s*const float c\[8\] = \{([^}]*)\}", src).group(1)
+    coef = np.array([np.float32(v.strip().rstrip("f")) for v in body.split(",")], np.float32)
+    clamp = np.float32(re.search(r"kTanhClamp = ([0-9.]+)f", src).group(1))
+    assert coef.shape == (8,)
+
+    def core(x, u):                                              # Horner in fp32, as the packed FFMA2 chain
+        r = (u * coef[0] + coef[1]).astype(np.float32)
+        for k in range(2, 8):
+            r = (r * u + coef[k]).astype(np.float32)
+        return (x * r).astype(np.float32)
+
+    x = np.concatenate([np.linspace(-20, 20, 2_000_001), [0.0, 1e-30, -1e-30, 1e4, -1e4, clamp, -clamp]]).astype(np.float32)
+    ref = np.tanh(x.astype(np.float64))
+    e1 = np.clip(core(x, np.minimum(x * x, clamp * clamp)), -1.0, 1.0)          # epilogue 1 (before the bf16 rounding)
+    xc = np.clip(x, -clamp, clamp)
+    e2 = core(xc, xc * xc)                                                        # epilogue 2
+    for got in (e1, e2):
+        assert np.abs(got - ref).max() < 1.4e-3
+        assert np.abs(got).max() <= 1.0 + 1.4e-3
+    assert np.array_equal(core(x, np.minimum(x * x, clamp * clamp)), -core(-x, np.minimum(x * x, clamp * clamp)))
+
+
+@pytest.mark.gpu
+def test_fused_mlp_kernel_with_saturating_units():
+    """The same comparison with layer-1 weights scaled by 4: more than half of the hidden units then sit in
+    the clamped part of the FMA-pipe tanh (|x| > 3.727) or far out on the MUFU one -- the regime a trained
+    policy's large normalised observations reach (measured: 6e-3, PyTorch's bf16 autocast 8e-3)."""
+    import torch
+    from rocket_landing_rl_b200 import ActorCriticMLP, FusedActorCritic
+    torch.manual_seed(11)
+    net = ActorCriticMLP().cuda()
+    with torch.no_grad():
+        for mod in (net.policy_net, net.value_net_body):
+            first = [m for m in mod.modules() if isinstance(m, torch.nn.Linear)][0]
+            first.weight.mul_(4.0)
+            first.bias.uniform_(-1.0, 1.0)
+    fused = FusedActorCritic(net)
+    obs = (torch.randn((65536 + 3, 8), device="cuda") * 3.0).clamp_(-10, 10)
+    with torch.no_grad():
+        first = [m for m in net.policy_net.modules() if isinstance(m, torch.nn.Linear)][0]
+        pre = torch.nn.functional.linear(obs, first.weight, first.bias)
+        assert float((pre.abs() > 3.727).float().mean()) > 0.4               # the regime is reached
+        want_mean = net.action_net(net.policy_net(obs))
+        want_val = net.predict_values(obs)
+    assert float((fused.action_mean(obs) - want_mean).abs().max()) < 1e-2
+    assert float((fused.predict_values(obs) - want_val).abs().max()) < 1e-2
+
+
 @pytest.mark.gpu
 def test_fused_action_sampling():
     """rl_policy_sample: the policy net with SB3's DiagGaussian sampling in its epilogue.  The noise
