@@ -47,8 +47,11 @@
 //     descriptors are 32-bit words that only need an add.
 //   * W2 (128 KiB) is stored in the blob as the image of its shared-memory operand and staged by one
 //     bulk copy of the TMA engine that only the issuing warp ever waits for.
-// Measured (profiles/mlp_forward_r2b_summary.txt): 0.160 ms (value net) / 0.172 ms (policy net) at
-// 1 Mi rockets, MUFU pipe 83 % busy, tensor pipe 49 %.
+//   * one pair of units in four of epilogue 1 (and of the value net's epilogue 2) evaluates its tanh on the
+//     FMA pipe instead ("tanh on the FMA pipe" below), and the MMAs are issued behind elect.sync, which
+//     lets ptxas issue them from uniform registers without a broadcast loop per instruction.
+// Measured (profiles/mlp_forward_r2c_summary.txt): 0.140 ms (value net) / 0.157-0.163 ms (policy net) at
+// 1 Mi rockets, MUFU pipe 71 % busy, tensor pipe 55 % (all tanh on the MUFU pipe: 0.160 / 0.172 ms, 83 %).
 //
 // Weights are bf16 (what torch.autocast(bfloat16) would use), accumulation fp32, biases bf16 high +
 // low parts (16 mantissa bits); measured against the fp32 module: rms error 8e-4, max 4e-3 on
