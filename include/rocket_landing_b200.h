@@ -332,7 +332,12 @@ int rl_episode_flags(const uint8_t *terminated, const uint8_t *truncated, uint8_
  * seed, counter = (global id, epoch)) even for equal seeds: pass a different `draw` on every call and
  * the shard's global id offset (rl_create's env_id_offset) as `row_offset`, so that ranks sharing a
  * seed draw different noise.  log_std is a DEVICE pointer to 2 floats; low2 / high2 are HOST
- * pointers to 2 floats. */
+ * pointers to 2 floats.
+ *
+ * rl_policy_value_sample: rl_policy_sample(blob_pi, ...) and values[n] = rl_mlp_forward(blob_vf, obs, ..., 1)
+ * in ONE launch (what a rollout step asks of the actor-critic, scripts/train.py:117-134: separate pi and vf
+ * nets on the same observation): some CTAs run the policy net, the others the value net.  Results are
+ * bit-identical to the two separate calls. */
 #define RL_MLP_HIDDEN 256
 #define RL_MLP_BLOB_BYTES 143376
 const char *rl_policy_last_error(void);
@@ -341,6 +346,10 @@ int rl_mlp_forward(const void *blob, const float *obs, float *out, int64_t n, in
 int rl_policy_sample(const void *blob, const float *obs, const float *log_std, uint64_t seed, uint64_t draw,
                      int64_t row_offset, const float *low2, const float *high2, float *actions, float *clipped,
                      float *log_prob, float *mean, int64_t n, void *stream);
+int rl_policy_value_sample(const void *blob_pi, const void *blob_vf, const float *obs, const float *log_std,
+                           uint64_t seed, uint64_t draw, int64_t row_offset, const float *low2, const float *high2,
+                           float *actions, float *clipped, float *log_prob, float *mean, float *values, int64_t n,
+                           void *stream);
 
 #ifdef __cplusplus
 }

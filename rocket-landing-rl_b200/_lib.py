@@ -22,7 +22,8 @@ EXPORTS = ("rl_abi_version", "rl_last_error", "rl_params_default", "rl_state_byt
            "rl_launch_count", "rl_vecnorm_last_error", "rl_vecnorm_create", "rl_vecnorm_destroy",
            "rl_vecnorm_reset", "rl_vecnorm_step", "rl_vecnorm_normalize_obs", "rl_vecnorm_get_stats",
            "rl_vecnorm_set_stats", "rl_vecnorm_launch_count", "rl_rollout_last_error", "rl_gae", "rl_episode_flags", "rl_sim_step",
-           "rl_sim_step_host", "rl_policy_last_error", "rl_mlp_blob_bytes", "rl_mlp_forward", "rl_policy_sample")
+           "rl_sim_step_host", "rl_policy_last_error", "rl_mlp_blob_bytes", "rl_mlp_forward", "rl_policy_sample",
+           "rl_policy_value_sample")
 
 _lib = None
 
@@ -99,6 +100,8 @@ def load():
     L.rl_mlp_blob_bytes.restype = i64
     L.rl_mlp_forward.argtypes = [vp, vp, vp, i64, i32, vp]
     L.rl_policy_sample.argtypes = [vp, vp, vp, u64, u64, i64, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp, vp, vp, i64, vp]
+    L.rl_policy_value_sample.argtypes = [vp, vp, vp, vp, u64, u64, i64, C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp, vp,
+                                         vp, vp, i64, vp]
     _lib = L
     return L
 

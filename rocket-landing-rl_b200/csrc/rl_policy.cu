@@ -311,10 +311,11 @@ __device__ __forceinline__ void quarter_barrier(int q) {          // the team-Y 
     asm volatile("bar.sync %0, %1;" :: "r"(q + 1), "n"(32 * kYSlices) : "memory");
 }
 
+// One net over the row blocks cta, cta + n_ctas, ... (the whole CTA: 17 warps).  A launch runs it on every CTA
+// (mlp_forward_tc5_kernel) or the policy net on some CTAs and the value net on the others (mlp_pair_kernel).
 template <int kOut>
-__global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsigned char* __restrict__ blob,
-                                                                const float* __restrict__ obs, float* __restrict__ out,
-                                                                int64_t n, const SampleArgs sa) {
+__device__ __forceinline__ void mlp_body(const unsigned char* __restrict__ blob, const float* __restrict__ obs,
+                                         float* __restrict__ out, int64_t n, const SampleArgs& sa, int64_t cta, int64_t n_ctas) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem);
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     const int64_t n_blocks = (n + kM - 1) / kM;
-    const int64_t stride = gridDim.x;
+    const int64_t stride = n_ctas;
     const int q = warp & 3;                                       // TMEM lane quarter of this warp
     const int row = 32 * q + lane;                                // this thread's row of the block = its TMEM lane
     const int yh = (warp - kXWarps) >> 2;                         // team Y: which kYUnits of a half's 128 units
@@ -396,11 +397,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
             fence_async_proxy();
         }
     };
-    load_obs(blockIdx.x);
+    load_obs(cta);
     stage_obs(0);
-    load_obs((int64_t)blockIdx.x + stride);
+    load_obs(cta + stride);
     stage_obs(1);
-    load_obs((int64_t)blockIdx.x + 2 * stride);
+    load_obs(cta + 2 * stride);
 
     fence_async_proxy();                                          // the weights were written through the generic proxy
     fence_before_sync();
@@ -413,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
         // =============================== team X: epilogue 1 ===========================================
         const int xh = warp >> 2;                                 // which 32 of a slice's 64 units
         int it = 0;
-        for (int64_t blk = blockIdx.x; blk < n_blocks; blk += stride, ++it) {
+        for (int64_t blk = cta; blk < n_blocks; blk += stride, ++it) {
             const uint32_t ppar = (uint32_t)(it & 1) ^ 1u;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -451,7 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
         const float* b3s = reinterpret_cast<const float*>(smem + kSmB3);
         float* red = reinterpret_cast<float*>(smem + kSmRed);
         int it = 0;
-        for (int64_t blk = blockIdx.x; blk < n_blocks; blk += stride, ++it) {
+        for (int64_t blk = cta; blk < n_blocks; blk += stride, ++it) {
             const uint32_t par = (uint32_t)(it & 1);
             float2 s2[kOut];
 #pragma unroll
@@ -584,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
         }
         mbar_wait(wbar, 0u);                                      // W2 has landed (the bulk copy was the kernel's first instruction)
         int it = 0;
-        for (int64_t blk = blockIdx.x; blk < n_blocks; blk += stride, ++it) {
+        for (int64_t blk = cta; blk < n_blocks; blk += stride, ++it) {
             const bool has_next = blk + stride < n_blocks;
             const uint32_t par = (uint32_t)(it & 1), ppar = par ^ 1u;
             const uint32_t accA = 128u + 128u * (uint32_t)((2 * it) % 3), accB = 128u + 128u * (uint32_t)((2 * it + 1) % 3);
@@ -621,6 +622,28 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsi
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" :: "r"(tmem) : "memory");
 }
 
+template <int kOut>
+__global__ void __launch_bounds__(kThreads, 1) mlp_forward_tc5_kernel(const unsigned char* __restrict__ blob,
+                                                                const float* __restrict__ obs, float* __restrict__ out,
+                                                                int64_t n, const SampleArgs sa) {
+    mlp_body<kOut>(blob, obs, out, n, sa, (int64_t)blockIdx.x, (int64_t)gridDim.x);
+}
+
+// Both nets of the actor-critic in ONE launch: CTAs [0, n_pi) run the policy net (with or without the sampling
+// epilogue), the others the value net -- one prologue (W2 staging, barriers, tensor-memory allocation) and one
+// launch instead of two back to back; every CTA computes exactly what it would in a launch of its own net.
+__global__ void __launch_bounds__(kThreads, 1) mlp_pair_kernel(const unsigned char* __restrict__ blob_pi,
+                                                               const unsigned char* __restrict__ blob_vf,
+                                                               const float* __restrict__ obs, float* __restrict__ out_pi,
+                                                               float* __restrict__ values, int64_t n, const SampleArgs sa, int n_pi) {
+    if ((int)blockIdx.x < n_pi) {
+        mlp_body<2>(blob_pi, obs, out_pi, n, sa, (int64_t)blockIdx.x, (int64_t)n_pi);
+    } else {
+        const SampleArgs none = {};
+        mlp_body<1>(blob_vf, obs, values, n, none, (int64_t)blockIdx.x - n_pi, (int64_t)gridDim.x - n_pi);
+    }
+}
+
 
 }  // namespace tc5
 
@@ -651,6 +674,36 @@ int launch_mlp(const void* blob, const float* obs, float* out, int64_t n, int ou
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return po_fail(RL_E_CUDA, "rl_mlp_forward launch failed: %s", cudaGetErrorString(e));
+    return RL_OK;
+}
+}  // namespace
+
+namespace {
+// policy net (sampling epilogue iff sa.actions) + value net in one launch
+int launch_pair(const void* blob_pi, const void* blob_vf, const float* obs, float* out_pi, float* values, int64_t n,
+                const SampleArgs& sa, cudaStream_t stream) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t blocks = (n + tc5::kM - 1) / tc5::kM;
+    // CTAs in proportion to the two nets' time per row block (the policy net carries a second head row and the
+    // sampling: 0.53 of the sum, profiles/README.md), at most one CTA per row block on either side
+    const int64_t total = 2 * blocks < sms ? 2 * blocks : sms;
+    static const int share = [] {                                 // experiment knob: the policy net's share in 1/64
+        const char* t = getenv("RL_B200_PI_SHARE");
+        const long v = t ? strtol(t, nullptr, 10) : 0;
+        return (v >= 1 && v <= 63) ? (int)v : 34;
+    }();
+    int64_t n_pi = (total * share + 32) / 64;
+    n_pi = n_pi < 1 ? 1 : (n_pi > blocks ? blocks : n_pi);
+    int64_t n_vf = total - n_pi;
+    n_vf = n_vf < 1 ? 1 : (n_vf > blocks ? blocks : n_vf);
+    cudaError_t e = cudaFuncSetAttribute(tc5::mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
+    if (e == cudaSuccess)
+        tc5::mlp_pair_kernel<<<(int)(n_pi + n_vf), tc5::kThreads, tc5::kSmemBytes, stream>>>(
+            (const unsigned char*)blob_pi, (const unsigned char*)blob_vf, obs, out_pi, values, n, sa, (int)n_pi);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return po_fail(RL_E_CUDA, "rl_policy_value_sample launch failed: %s", cudaGetErrorString(e));
     return RL_OK;
 }
 }  // namespace
@@ -688,6 +741,26 @@ int rl_policy_sample(const void* blob, const float* obs, const float* log_std, u
     sa.seed = seed; sa.draw = draw; sa.row_offset = (unsigned long long)row_offset;
     sa.lo0 = low2[0]; sa.lo1 = low2[1]; sa.hi0 = high2[0]; sa.hi1 = high2[1];      // HOST pointers: two floats each
     return launch_mlp(blob, obs, actions, n, 2, sa, (cudaStream_t)stream);
+}
+
+// rl_policy_sample and the value net (values[n] = rl_mlp_forward(blob_vf, obs, ..., out_dim 1)) in ONE launch: what
+// a rollout step asks of the actor-critic.  Results are bit-identical to the two separate calls.
+int rl_policy_value_sample(const void* blob_pi, const void* blob_vf, const float* obs, const float* log_std, uint64_t seed,
+                           uint64_t draw, int64_t row_offset, const float* low2, const float* high2, float* actions,
+                           float* clipped, float* log_prob, float* mean, float* values, int64_t n, void* stream) {
+    if (!blob_pi || !blob_vf || !obs || !log_std || !low2 || !high2 || !actions || !clipped || !log_prob || !values)
+        return po_fail(RL_E_INVALID, "rl_policy_value_sample: null argument");
+    if (n < 1) return po_fail(RL_E_INVALID, "rl_policy_value_sample: n must be positive");
+    if (row_offset < 0) return po_fail(RL_E_INVALID, "rl_policy_value_sample: row_offset must be >= 0");
+    if ((reinterpret_cast<uintptr_t>(blob_pi) & 15) || (reinterpret_cast<uintptr_t>(blob_vf) & 15) ||
+        (reinterpret_cast<uintptr_t>(obs) & 15) || (reinterpret_cast<uintptr_t>(actions) & 7) ||
+        (reinterpret_cast<uintptr_t>(clipped) & 7) || (mean && (reinterpret_cast<uintptr_t>(mean) & 7)))
+        return po_fail(RL_E_INVALID, "rl_policy_value_sample: blobs / obs need 16-byte, actions / clipped / mean 8-byte alignment");
+    SampleArgs sa = {};
+    sa.log_std = log_std; sa.actions = actions; sa.clipped = clipped; sa.log_prob = log_prob; sa.mean = mean;
+    sa.seed = seed; sa.draw = draw; sa.row_offset = (unsigned long long)row_offset;
+    sa.lo0 = low2[0]; sa.lo1 = low2[1]; sa.hi0 = high2[0]; sa.hi1 = high2[1];      // HOST pointers: two floats each
+    return launch_pair(blob_pi, blob_vf, obs, actions, values, n, sa, (cudaStream_t)stream);
 }
 
 }  // extern "C"

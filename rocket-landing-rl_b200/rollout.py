@@ -200,11 +200,39 @@ class FusedActorCritic:
         self.draw += 1
         return actions, clipped, log_prob, mean
 
+    def act_and_value(self, obs: torch.Tensor, actions: Optional[torch.Tensor] = None,
+                      log_prob: Optional[torch.Tensor] = None, values: Optional[torch.Tensor] = None,
+                      want_mean: bool = False):
+        """``act`` and ``predict_values`` of the same observations in ONE launch
+        (``rl_policy_value_sample``: some CTAs run the policy net, the others the value net).  Returns
+        ``(actions, clipped, log_prob, mean or None, values)``, bit-identical to the two separate calls."""
+        if obs.dtype != torch.float32 or not obs.is_contiguous():
+            obs = obs.to(torch.float32).contiguous()
+        n = obs.shape[0]
+        f32 = dict(dtype=torch.float32, device=obs.device)
+        actions = torch.empty((n, 2), **f32) if actions is None else actions
+        log_prob = torch.empty((n,), **f32) if log_prob is None else log_prob
+        values = torch.empty((n,), **f32) if values is None else values
+        clipped = torch.empty((n, 2), **f32)
+        mean = torch.empty((n, 2), **f32) if want_mean else None
+        assert actions.is_contiguous() and log_prob.is_contiguous() and values.is_contiguous() and values.numel() == n
+        if n == 0:
+            return actions, clipped, log_prob, mean, values
+        rc = self._L.rl_policy_value_sample(self._pi.data_ptr(), self._vf.data_ptr(), obs.data_ptr(), self._log_std.data_ptr(),
+                                            self.seed, self.draw, self.row_offset, self._low, self._high, actions.data_ptr(),
+                                            clipped.data_ptr(), log_prob.data_ptr(),
+                                            mean.data_ptr() if mean is not None else None, values.data_ptr(), n,
+                                            torch.cuda.current_stream(obs.device).cuda_stream)
+        if rc != 0:
+            raise _lib.RocketLibraryError(f"rl_policy_value_sample failed ({rc}): {self._L.rl_policy_last_error().decode()}")
+        self.draw += 1
+        return actions, clipped, log_prob, mean, values
+
     def forward(self, obs: torch.Tensor, generator: Optional[torch.Generator] = None):
         """``(actions, values, log_prob)`` as ``ActorCriticMLP.forward``.  ``generator`` is ignored:
         the noise comes from the kernel's own Philox stream (``seed``, ``draw``)."""
-        actions, _, log_prob, _ = self.act(obs)
-        return actions, self.predict_values(obs), log_prob
+        actions, _, log_prob, _, values = self.act_and_value(obs)
+        return actions, values, log_prob
 
     __call__ = forward
 
@@ -247,7 +275,7 @@ def collect_rollout(env, policy, buffer: DeviceRolloutBuffer, last_obs: torch.Te
     low = torch.tensor([0.0, -1.0], device=last_obs.device)
     high = torch.tensor([1.0, 1.0], device=last_obs.device)
     T = buffer.n_steps
-    fused = hasattr(policy, "act")
+    fused = hasattr(policy, "act_and_value")
     direct = hasattr(env, "venv")          # DeviceVecNormalize can write its outputs straight into the buffer
     buffer.observations[0].copy_(last_obs)
     buffer.episode_starts[0].copy_(last_episode_starts)
@@ -261,9 +289,8 @@ def collect_rollout(env, policy, buffer: DeviceRolloutBuffer, last_obs: torch.Te
     if bootstrap_timeouts:
         scratch["any"].zero_()
     for t in range(T):
-        if fused:     # sample, clip and log-prob in the policy kernel's epilogue, straight into the buffer
-            _, clipped, _, _ = policy.act(obs, buffer.actions[t], buffer.log_probs[t])
-            policy.predict_values(obs, out=buffer.values[t])
+        if fused:     # sample, clip and log-prob in the policy net's epilogue, the value net in the same launch, straight into the buffer
+            _, clipped, _, _, _ = policy.act_and_value(obs, buffer.actions[t], buffer.log_probs[t], buffer.values[t])
         else:
             actions, values, log_probs = policy(obs, generator)
             buffer.actions[t].copy_(actions)

@@ -100,6 +100,8 @@ def test_create_fails_loudly_without_gpu_or_with_bad_args():
     assert lib.rl_episode_flags(None, None, None, None, None, 16, None) == -1 and b"null" in lib.rl_rollout_last_error()
     assert lib.rl_gae(None, None, None, None, None, None, None, 1, 16, 0.99, 0.95, None) == -1
     assert lib.rl_mlp_forward(None, None, None, 16, 1, None) == -1 and b"null" in lib.rl_policy_last_error()
+    assert lib.rl_policy_value_sample(None, None, None, None, 0, 0, 0, None, None, None, None, None, None, None, 16, None) == -1
+    assert b"rl_policy_value_sample" in lib.rl_policy_last_error()
 
 
 def test_product_never_imports_the_oracle():

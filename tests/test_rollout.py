@@ -245,6 +245,36 @@ def test_fused_action_sampling():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 127, 129, 300, 5000, 20000, 262144 + 77])
+def test_policy_and_value_net_in_one_launch_are_bit_identical_to_two(n):
+    """rl_policy_value_sample runs the policy net on some CTAs and the value net on the others: every
+    output word equals what rl_policy_sample + rl_mlp_forward produce (same seed and draw), for batches
+    smaller than one row block, smaller than the grid, and far larger; rows outside [0, n) stay untouched."""
+    import torch
+    from rocket_landing_rl_b200 import ActorCriticMLP, FusedActorCritic
+    torch.manual_seed(5)
+    net = ActorCriticMLP().cuda()
+    with torch.no_grad():
+        net.log_std.fill_(-0.7)
+    obs = (torch.randn((n, 8), device="cuda") * 3.0).clamp_(-10, 10)
+    two = FusedActorCritic(net, seed=9, row_offset=1000)
+    one = FusedActorCritic(net, seed=9, row_offset=1000)
+    for _ in range(2):                                           # two draws: the counter advances alike
+        a2, c2, l2, m2 = two.act(obs, want_mean=True)
+        v2 = two.predict_values(obs)
+        pad = 64
+        acts = torch.full((n + pad, 2), 7.0, device="cuda")
+        logp = torch.full((n + pad,), 7.0, device="cuda")
+        vals = torch.full((n + pad,), 7.0, device="cuda")
+        a1, c1, l1, m1, v1 = one.act_and_value(obs, acts[:n], logp[:n], vals[:n], want_mean=True)
+        for got, want in ((a1, a2), (c1, c2), (l1, l2), (m1, m2), (v1, v2)):
+            assert torch.equal(got, want)
+        assert bool((acts[n:] == 7.0).all()) and bool((logp[n:] == 7.0).all()) and bool((vals[n:] == 7.0).all())
+    a, v, lp = one(obs)
+    assert a.shape == (n, 2) and v.shape == (n,) and lp.shape == (n,)
+
+
+@pytest.mark.gpu
 def test_policy_noise_is_independent_of_the_reset_stream_for_equal_seeds():
     """Both streams are Philox4x32-10 and both default to seed 0.  With the SAME key the policy's
     counter (row, draw, 0) would coincide with the reset's counter (global id, epoch, block 0)
