@@ -156,7 +156,8 @@ int launch_step(RlEnv* e, const float* actions, float* obs, float* reward, uint8
     }
     a.chunk = (uint32_t)chunk;
     const int grid = a.chunk ? (int)((ctas + a.chunk - 1) / a.chunk) : (int)(ctas < cap ? ctas : cap);
-    step_kernel_for(e->folded, auto_reset != 0, single, chunk != 0)<<<grid, rl::kCtaThreads, 0, stream>>>(e->dev, a);
+    RL_CUDA(rl::rl_launch(step_kernel_for(e->folded, auto_reset != 0, single, chunk != 0), dim3(grid), dim3(rl::kCtaThreads), 0, stream,
+                          e->dev, a));
     e->launches += 1;
     RL_CUDA(cudaGetLastError());
     return RL_OK;

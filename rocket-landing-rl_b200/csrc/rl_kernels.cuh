@@ -29,6 +29,7 @@
 #include <type_traits>
 
 #include "rl_device.cuh"
+#include "rl_launch.cuh"
 
 namespace rl {
 
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(kCtaThreads, RL_MIN_CTAS) step_kernel(const __
     __shared__ BlockStats bs;
     __shared__ ObsStage obs_stage[kCtaThreads / 32];
 
+    rl_grid_dependency_wait();                             // (programmatic dependent launch: rl_launch.cuh)
     const auto& P = ParamSel<PP>::get(Prt);
     const uint32_t tid = threadIdx.x;
     const uint32_t stride = kChunked ? 1u : gridDim.x;

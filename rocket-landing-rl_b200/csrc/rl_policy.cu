@@ -68,6 +68,7 @@
 
 #include "../../include/rocket_landing_b200.h"
 #include "rl_device.cuh"
+#include "rl_launch.cuh"
 
 namespace {
 
@@ -317,6 +318,7 @@ template <int kOut>
 __device__ __forceinline__ void mlp_body(const unsigned char* __restrict__ blob, const float* __restrict__ obs,
                                          float* __restrict__ out, int64_t n, const SampleArgs& sa, int64_t cta, int64_t n_ctas) {
     extern __shared__ __align__(128) unsigned char smem[];
+    rl::rl_grid_dependency_wait();                                // (programmatic dependent launch: rl_launch.cuh)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bars = sbase + kSmBar;
@@ -666,11 +668,11 @@ int launch_mlp(const void* blob, const float* obs, float* out, int64_t n, int ou
     if (out_dim == 2) {
         e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
         if (e == cudaSuccess)
-            tc5::mlp_forward_tc5_kernel<2><<<grid, tc5::kThreads, tc5::kSmemBytes, stream>>>((const unsigned char*)blob, obs, out, n, sa);
+            e = rl::rl_launch(tc5::mlp_forward_tc5_kernel<2>, dim3(grid), dim3(tc5::kThreads), tc5::kSmemBytes, stream, (const unsigned char*)blob, obs, out, n, sa);
     } else {
         e = cudaFuncSetAttribute(tc5::mlp_forward_tc5_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
         if (e == cudaSuccess)
-            tc5::mlp_forward_tc5_kernel<1><<<grid, tc5::kThreads, tc5::kSmemBytes, stream>>>((const unsigned char*)blob, obs, out, n, sa);
+            e = rl::rl_launch(tc5::mlp_forward_tc5_kernel<1>, dim3(grid), dim3(tc5::kThreads), tc5::kSmemBytes, stream, (const unsigned char*)blob, obs, out, n, sa);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return po_fail(RL_E_CUDA, "rl_mlp_forward launch failed: %s", cudaGetErrorString(e));
@@ -700,8 +702,8 @@ int launch_pair(const void* blob_pi, const void* blob_vf, const float* obs, floa
     n_vf = n_vf < 1 ? 1 : (n_vf > blocks ? blocks : n_vf);
     cudaError_t e = cudaFuncSetAttribute(tc5::mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
     if (e == cudaSuccess)
-        tc5::mlp_pair_kernel<<<(int)(n_pi + n_vf), tc5::kThreads, tc5::kSmemBytes, stream>>>(
-            (const unsigned char*)blob_pi, (const unsigned char*)blob_vf, obs, out_pi, values, n, sa, (int)n_pi);
+        e = rl::rl_launch(tc5::mlp_pair_kernel, dim3((unsigned)(n_pi + n_vf)), dim3(tc5::kThreads), tc5::kSmemBytes, stream,
+                          (const unsigned char*)blob_pi, (const unsigned char*)blob_vf, obs, out_pi, values, n, sa, (int)n_pi);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return po_fail(RL_E_CUDA, "rl_policy_value_sample launch failed: %s", cudaGetErrorString(e));
     return RL_OK;

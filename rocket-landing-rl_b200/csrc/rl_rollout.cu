@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/rocket_landing_b200.h"
+#include "rl_launch.cuh"
 
 namespace {
 
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) episode_flags_kernel(const uint8_t* __res
                                                             uint8_t* __restrict__ episode_start_next,
                                                             uint8_t* __restrict__ time_limit, int* __restrict__ any_time_limit,
                                                             int64_t n, int vectorised) {
+    rl::rl_grid_dependency_wait();                     // (programmatic dependent launch: rl_launch.cuh)
     const int64_t t = blockIdx.x * 256ll + threadIdx.x;
     uint32_t any = 0;
     if (vectorised) {                                      // 16 rockets per thread (all pointers 16-byte aligned)
@@ -145,9 +147,9 @@ int rl_episode_flags(const uint8_t* terminated, const uint8_t* truncated, uint8_
     const int vectorised = (bits & 15) == 0;
     const int64_t threads = vectorised ? (n_envs + 15) / 16 : n_envs;
     if ((threads + 255) / 256 > 2147483647LL) return ro_fail(RL_E_INVALID, "rl_episode_flags: too many rockets per call");
-    episode_flags_kernel<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(terminated, truncated, episode_start_next,
-                                                                                       time_limit, any_time_limit, n_envs, vectorised);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = rl::rl_launch(episode_flags_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+                                  terminated, truncated, episode_start_next, time_limit, any_time_limit, n_envs, vectorised);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return ro_fail(RL_E_CUDA, "rl_episode_flags launch failed: %s", cudaGetErrorString(e));
     return RL_OK;
 }

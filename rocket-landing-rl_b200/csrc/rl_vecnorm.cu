@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/rocket_landing_b200.h"
+#include "rl_launch.cuh"
 
 namespace {
 
@@ -64,6 +65,7 @@ struct VnState {
 __global__ void __launch_bounds__(kThreads) vn_moments(VnState* __restrict__ st, const float4* __restrict__ obs,
                                                        const float* __restrict__ reward, float* __restrict__ returns,
                                                        uint32_t n, float gamma, int with_obs, int with_ret, uint32_t chunk) {
+    rl::rl_grid_dependency_wait();                     // (programmatic dependent launch: rl_launch.cuh)
     __shared__ double red[kThreads / 32][kAcc];
     const uint32_t tid = threadIdx.x;
     const uint32_t r0 = blockIdx.x * chunk;                                  // this CTA's rockets [r0, r1)
@@ -161,6 +163,7 @@ __device__ void fold(double& mean, double& var, double count, double batch_mean,
 }
 
 __global__ void vn_finalize(VnState* st, double batch_count, double epsilon, int update_obs, int update_ret) {
+    rl::rl_grid_dependency_wait();
     const int k = threadIdx.x;
     __shared__ double acc[kAcc];
     {   // fold (and clear) the kAccSlots copies of the batch sums: lane = slot, one shuffle tree per word;
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(kThreads) vn_apply(const VnState* __restrict__
                                                      const uint8_t* __restrict__ truncated, float4* __restrict__ terminal_obs,
                                                      float* __restrict__ returns, uint32_t n, float clip_obs,
                                                      float clip_reward, int norm_obs, int norm_reward) {
+    rl::rl_grid_dependency_wait();                     // (programmatic dependent launch: rl_launch.cuh)
     const uint32_t tid = threadIdx.x;
     const uint32_t r0 = blockIdx.x * (uint32_t)kChunk, r1 = min(n, r0 + (uint32_t)kChunk);
     if (obs_in) {
@@ -390,14 +394,14 @@ int rl_vecnorm_step(RlVecNorm* v, const float* obs_in, const float* reward_in, c
     Guard g(v->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (training) {
-        vn_moments<<<v->mom_grid, kThreads, 0, st>>>(v->st, (const float4*)obs_in, reward_in, v->returns, (uint32_t)v->n,
-                                                (float)v->gamma, norm_obs, 1, (uint32_t)v->mom_chunk);
-        vn_finalize<<<1, 32, 0, st>>>(v->st, (double)v->n, v->epsilon, norm_obs, 1);
+        rl::rl_launch(vn_moments, dim3(v->mom_grid), dim3(kThreads), 0, st, v->st, (const float4*)obs_in, reward_in, v->returns,
+                      (uint32_t)v->n, (float)v->gamma, norm_obs, 1, (uint32_t)v->mom_chunk);
+        rl::rl_launch(vn_finalize, dim3(1), dim3(32), 0, st, v->st, (double)v->n, v->epsilon, norm_obs, 1);
         v->launches += 2;
     }
-    vn_apply<<<v->grid, kThreads, 0, st>>>(v->st, (const float4*)obs_in, (float4*)obs_out, reward_in, reward_out,
-                                          terminated, truncated, (float4*)terminal_obs, v->returns, (uint32_t)v->n,
-                                          (float)v->clip_obs, (float)v->clip_reward, norm_obs, norm_reward);
+    rl::rl_launch(vn_apply, dim3(v->grid), dim3(kThreads), 0, st, (const VnState*)v->st, (const float4*)obs_in, (float4*)obs_out,
+                  reward_in, reward_out, terminated, truncated, (float4*)terminal_obs, v->returns, (uint32_t)v->n,
+                  (float)v->clip_obs, (float)v->clip_reward, norm_obs, norm_reward);
     v->launches += 1;
     VN_CUDA(cudaGetLastError());
     return RL_OK;

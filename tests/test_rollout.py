@@ -425,3 +425,44 @@ def test_fused_mlp_kernels_stay_inside_their_output_rows(n):
         assert bool((t[n:] == -7.0).all()) and bool(torch.isfinite(t[:n]).all())
     assert clipped.shape == (n, 2) and mean.shape == (n, 2)
     assert torch.equal(fused.predict_values(obs), vals[:n])
+
+
+_PDL_DIGEST = r"""
+import hashlib, sys, torch
+sys.path.insert(0, sys.argv[1])
+from rocket_landing_rl_b200 import (ActorCriticMLP, DeviceRolloutBuffer, DeviceVecNormalize, FusedActorCritic,
+                                    RocketLandingVecEnv, collect_rollout)
+torch.manual_seed(2)
+n, T = 20000, 12
+env = DeviceVecNormalize(RocketLandingVecEnv(n, device="cuda:0", seed=4), gamma=0.99)
+policy = FusedActorCritic(ActorCriticMLP().cuda(), seed=6)
+buf = DeviceRolloutBuffer(T, n, "cuda:0")
+obs = env.reset()
+starts = torch.ones(n, dtype=torch.bool, device="cuda:0")
+h = hashlib.sha256()
+for _ in range(3):
+    obs, starts = collect_rollout(env, policy, buf, obs, starts)
+    for t in (buf.observations, buf.actions, buf.rewards, buf.values, buf.log_probs, buf.advantages, buf.returns):
+        h.update(t.cpu().numpy().tobytes())
+    h.update(buf.episode_starts.cpu().numpy().tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+@pytest.mark.gpu
+def test_programmatic_dependent_launch_changes_no_bit():
+    """The kernels of a rollout step are chained by programmatic dependent launch (csrc/rl_launch.cuh): each
+    may be set up while its predecessor drains and waits for it before it touches memory.  Three collection
+    passes (actor-critic, env step with auto-reset, VecNormalize, flags, GAE) with and without it
+    (RL_B200_PDL=0 launches everything the ordinary way) must produce the same bytes."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = []
+    for pdl in ("1", "0"):
+        env = dict(os.environ, RL_B200_PDL=pdl)
+        out = subprocess.run([sys.executable, "-c", _PDL_DIGEST, root], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests.append([line for line in out.stdout.splitlines() if line.startswith("DIGEST")][0])
+    assert digests[0] == digests[1]
