@@ -303,8 +303,9 @@ int rl_gae(const float *rewards, const float *values, const uint8_t *episode_sta
 /* What SB3's collect_rollouts (on_policy_algorithm.py, driven by scripts/train.py:136-144) derives on the
  * host from `dones` and `infos` after every env step, in one pass: episode_start_next[i] = terminated[i] |
  * truncated[i] (nullable), time_limit[i] = truncated[i] & !terminated[i] (the rockets whose reward gets the
- * gamma V(terminal_observation) bootstrap, infos[i]["TimeLimit.truncated"]), and *any_time_limit |= 1
- * (int32, DEVICE memory) if there is any such rocket.  Flags are uint8 [N] with values 0 / 1.  Enqueue only. */
+ * gamma V(terminal_observation) bootstrap, infos[i]["TimeLimit.truncated"]), and *any_time_limit = 1
+ * (int32: device memory, or pinned host memory -- the rollout reads it on the host after an event, without a
+ * copy) if there is any such rocket.  Flags are uint8 [N] with values 0 / 1.  Enqueue only. */
 int rl_episode_flags(const uint8_t *terminated, const uint8_t *truncated, uint8_t *episode_start_next,
                      uint8_t *time_limit, int32_t *any_time_limit, int64_t n_envs, void *stream);
 

@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(256) episode_flags_kernel(const uint8_t* __res
         time_limit[t] = tl;
         any = tl;
     }
-    if (__any_sync(0xffffffffu, any != 0) && (threadIdx.x & 31) == 0) atomicOr(any_time_limit, 1);
+    // (every writer stores the same 1: a plain store, which also works when the word lives in pinned host memory)
+    if (__any_sync(0xffffffffu, any != 0) && (threadIdx.x & 31) == 0) *reinterpret_cast<volatile int*>(any_time_limit) = 1;
 }
 
 }  // namespace
@@ -136,8 +137,9 @@ int rl_gae(const float* rewards, const float* values, const uint8_t* episode_sta
 }
 
 // terminated, truncated: uint8 [N] (0 / 1) of the step just taken.  Writes episode_start_next[i] = terminated |
-// truncated (nullable), time_limit[i] = truncated & !terminated, and ORs 1 into *any_time_limit (int32, DEVICE)
-// if any rocket ended by the time limit alone.  DEVICE pointers, enqueue only.
+// truncated (nullable), time_limit[i] = truncated & !terminated, and stores 1 into *any_time_limit (int32: device
+// memory, or pinned host memory the caller reads after an event) if any rocket ended by the time limit alone.
+// DEVICE pointers, enqueue only.
 int rl_episode_flags(const uint8_t* terminated, const uint8_t* truncated, uint8_t* episode_start_next, uint8_t* time_limit,
                      int32_t* any_time_limit, int64_t n_envs, void* stream) {
     if (!terminated || !truncated || !time_limit || !any_time_limit) return ro_fail(RL_E_INVALID, "rl_episode_flags: null argument");

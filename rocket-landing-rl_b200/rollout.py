@@ -287,7 +287,7 @@ def collect_rollout(env, policy, buffer: DeviceRolloutBuffer, last_obs: torch.Te
     flag = _pinned_flags(T, last_obs.device)
     scratch = _scratch(T, n_envs, last_obs.device)
     if bootstrap_timeouts:
-        scratch["any"].zero_()
+        flag["host"].zero_()               # (every event of the previous pass has been synchronised: no kernel writes it now)
     for t in range(T):
         if fused:     # sample, clip and log-prob in the policy net's epilogue, the value net in the same launch, straight into the buffer
             _, clipped, _, _, _ = policy.act_and_value(obs, buffer.actions[t], buffer.log_probs[t], buffer.values[t])
@@ -316,11 +316,12 @@ def collect_rollout(env, policy, buffer: DeviceRolloutBuffer, last_obs: torch.Te
             # still intact then.  One kernel (rl_episode_flags) derives the next episode_start, the
             # time-limit mask and the "any" flag from the step's two flag arrays.
             timeout = scratch["timeout"][t & 1]
+            # (the "any" word is written straight into pinned host memory -- under unified addressing the device
+            # reaches it by the host pointer -- so no copy sits between this kernel and the next step's)
             rc = L.rl_episode_flags(terminated.data_ptr(), truncated.data_ptr(), starts_out.data_ptr(), timeout.data_ptr(),
-                                    scratch["any"][t].data_ptr(), n_envs, torch.cuda.current_stream(last_obs.device).cuda_stream)
+                                    flag["host"][t:t + 1].data_ptr(), n_envs, torch.cuda.current_stream(last_obs.device).cuda_stream)
             if rc != 0:
                 raise _lib.RocketLibraryError(f"rl_episode_flags failed ({rc}): {L.rl_rollout_last_error().decode()}")
-            flag["host"][t].copy_(scratch["any"][t], non_blocking=True)
             flag["events"][t].record()
             if pending is not None:
                 _bootstrap(policy, buffer, info, pending, flag, gamma, starts_out)
@@ -350,11 +351,10 @@ def _pinned_flags(n_steps: int, device) -> dict:
 
 def _scratch(n_steps: int, n_envs: int, device) -> dict:
     """Per-(device, shape) device scratch of ``collect_rollout``: two alternating time-limit masks (a mask is
-    read one step after it was written), the per-step "any time-limit truncation" words, the last step's dones."""
+    read one step after it was written) and the last step's dones."""
     key = (str(device), n_steps, n_envs)
     if key not in _SCRATCH:
         _SCRATCH[key] = {"timeout": torch.zeros((2, n_envs), dtype=torch.bool, device=device),
-                         "any": torch.zeros(n_steps, dtype=torch.int32, device=device),
                          "last_starts": torch.zeros(n_envs, dtype=torch.bool, device=device)}
     return _SCRATCH[key]
 
