@@ -473,22 +473,30 @@ def main() -> None:
 
         copies()
         barrier()
-        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c0.record()
-        for _ in range(3):
+        # a CEILING: the best of five repetitions (one repetition = this rank's bytes of one step, both directions at
+        # once); a mean over a few copies has come out below what rl_step_host then sustained on the same box
+        best = float("inf")
+        cur = torch.cuda.current_stream(dev)
+        for _ in range(5):
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev)
+            c0.record()
+            s_out.wait_stream(cur)
+            s_in.wait_stream(cur)
             copies()
-        torch.cuda.current_stream(dev).wait_stream(s_out)
-        torch.cuda.current_stream(dev).wait_stream(s_in)
-        c1.record()
-        torch.cuda.synchronize(dev)
-        t_c = torch.tensor([c0.elapsed_time(c1) / 3.0], device=dev, dtype=torch.float64)
+            cur.wait_stream(s_out)
+            cur.wait_stream(s_in)
+            c1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, c0.elapsed_time(c1))
+        t_c = torch.tensor([best], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
         ceiling = float(args.rockets) * args.substeps / (float(t_c[0]) * 1e-3)
         e2e["copy_ceiling"] = {"env_steps_per_s": ceiling, "d2h_gbs_aggregate": 38.0 * args.rockets / (float(t_c[0]) * 1e-3) / 1e9,
                                "h2d_gbs_aggregate": 8.0 * args.rockets / (float(t_c[0]) * 1e-3) / 1e9,
                                "how": "all ranks at once: cudaMemcpyAsync of 38 B/rocket D2H + 8 B/rocket H2D, pinned memory, "
-                                      "two streams, slowest rank"}
+                                      "two streams, best of five repetitions, slowest rank"}
         e2e["frac_of_copy_ceiling"] = e2e["value"] / ceiling
         del d_out, h_out, d_in
 
