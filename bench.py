@@ -480,6 +480,7 @@ def main() -> None:
         for _ in range(5):
             c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(dev)
+            barrier()                                        # every repetition: all ranks copy at the same time
             c0.record()
             s_out.wait_stream(cur)
             s_in.wait_stream(cur)
@@ -488,15 +489,16 @@ def main() -> None:
             cur.wait_stream(s_in)
             c1.record()
             torch.cuda.synchronize(dev)
-            best = min(best, c0.elapsed_time(c1))
+            t_rep = torch.tensor([c0.elapsed_time(c1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t_rep, op=dist.ReduceOp.MAX)    # the slowest rank of THIS repetition
+            best = min(best, float(t_rep[0]))
         t_c = torch.tensor([best], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t_c, op=dist.ReduceOp.MAX)
         ceiling = float(args.rockets) * args.substeps / (float(t_c[0]) * 1e-3)
         e2e["copy_ceiling"] = {"env_steps_per_s": ceiling, "d2h_gbs_aggregate": 38.0 * args.rockets / (float(t_c[0]) * 1e-3) / 1e9,
                                "h2d_gbs_aggregate": 8.0 * args.rockets / (float(t_c[0]) * 1e-3) / 1e9,
                                "how": "all ranks at once: cudaMemcpyAsync of 38 B/rocket D2H + 8 B/rocket H2D, pinned memory, "
-                                      "two streams, best of five repetitions, slowest rank"}
+                                      "two streams, slowest rank of a repetition, best of five repetitions"}
         e2e["frac_of_copy_ceiling"] = e2e["value"] / ceiling
         del d_out, h_out, d_in
 
