@@ -688,18 +688,26 @@ int launch_pair(const void* blob_pi, const void* blob_vf, const float* obs, floa
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t blocks = (n + tc5::kM - 1) / tc5::kM;
-    // CTAs in proportion to the two nets' time per row block (the policy net carries a second head row and the
-    // sampling: 0.53 of the sum, profiles/README.md), at most one CTA per row block on either side
+    // CTAs so that both sides finish together: a row block of the policy net (second head row, sampling epilogue)
+    // takes `ratio` = 1.18 times one of the value net (measured in the pair kernel, profiles/README.md); choose the
+    // split that minimises max(ceil(blocks / n_pi) ratio, ceil(blocks / n_vf)) -- at most one CTA per row block
+    // on either side.  RL_B200_PI_RATIO=<percent> overrides the ratio (experiment knob).
     const int64_t total = 2 * blocks < sms ? 2 * blocks : sms;
-    static const int share = [] {                                 // experiment knob: the policy net's share in 1/64
-        const char* t = getenv("RL_B200_PI_SHARE");
+    static const double ratio = [] {
+        const char* t = getenv("RL_B200_PI_RATIO");
         const long v = t ? strtol(t, nullptr, 10) : 0;
-        return (v >= 1 && v <= 63) ? (int)v : 34;
+        return (v >= 50 && v <= 300) ? (double)v / 100.0 : 1.18;
     }();
-    int64_t n_pi = (total * share + 32) / 64;
-    n_pi = n_pi < 1 ? 1 : (n_pi > blocks ? blocks : n_pi);
-    int64_t n_vf = total - n_pi;
-    n_vf = n_vf < 1 ? 1 : (n_vf > blocks ? blocks : n_vf);
+    int64_t n_pi = 1, n_vf = 1;
+    double best = 1e300;
+    for (int64_t p = 1; p < total || p == 1; ++p) {
+        const int64_t a_pi = p > blocks ? blocks : p;
+        int64_t a_vf = total - p < 1 ? 1 : total - p;
+        a_vf = a_vf > blocks ? blocks : a_vf;
+        const double t_pi = (double)((blocks + a_pi - 1) / a_pi) * ratio, t_vf = (double)((blocks + a_vf - 1) / a_vf);
+        const double t = t_pi > t_vf ? t_pi : t_vf;
+        if (t < best - 1e-9) { best = t; n_pi = a_pi; n_vf = a_vf; }
+    }
     cudaError_t e = cudaFuncSetAttribute(tc5::mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc5::kSmemBytes);
     if (e == cudaSuccess)
         e = rl::rl_launch(tc5::mlp_pair_kernel, dim3((unsigned)(n_pi + n_vf)), dim3(tc5::kThreads), tc5::kSmemBytes, stream,
